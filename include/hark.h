@@ -1,0 +1,195 @@
+/*
+ * hark.h — C ABI of libhark.so, the B200-native replacement for the Futhark-generated
+ * library behind HarkDB's relational operator path.
+ *
+ * What it replaces (reference file:line, all under /root/reference):
+ *   - the CFFI module `_main` built by setup.sh:12-13 (`futhark c --library futhark/main.fut`
+ *     + `build_futhark_ffi main`) and driven from FutharkContext.py:41,65-66,70-71;
+ *   - entry points main.fut:7 (`query_sel`) and main.fut:9 (`query_groupby`), plus the
+ *     orphan entry join.fut:52 (`join`), with the argument order of those entries kept;
+ *   - the array marshalling futhark_ffi does around them (futhark_new_* / futhark_values_* /
+ *     futhark_shape_* / futhark_free_*): here hark_table_from_host / hark_table_to_host /
+ *     hark_table_shape / hark_table_free.  A literally link-compatible `futhark_*` alias
+ *     layer is declared in include/hark_futhark_compat.h.
+ *
+ * Conventions (same as the Futhark C API): every function returns int, 0 = success; inputs
+ * are borrowed and never consumed; outputs are fresh handles owned by the caller; no C++
+ * exception or abort() crosses this boundary for a user-level fault; a context serialises
+ * its calls (one call at a time per context); the last error text is retrievable with
+ * hark_context_get_error().  One context drives ONE GPU (one process per GPU; the
+ * multi-GPU layer lives above this ABI).
+ *
+ * There is no CPU fallback: every entry runs hand-written sm_100a kernels and fails with
+ * HARK_ERR_CUDA when no device is usable.
+ */
+#ifndef HARK_H
+#define HARK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HARK_ABI_VERSION 1
+
+typedef struct hark_ctx hark_ctx;     /* opaque: device, stream, memory pool, scratch, stats */
+typedef struct hark_table hark_table; /* opaque: n rows x m device-resident columns (SoA)    */
+
+typedef enum { HARK_I32 = 0, HARK_U32 = 1, HARK_I64 = 2, HARK_F32 = 3, HARK_F64 = 4 } hark_dtype;
+
+typedef enum {
+    HARK_OK = 0,
+    HARK_ERR_ARG = 1,         /* bad argument, incl. a column index out of bounds (the Futhark
+                                 entry would return non-zero with "Index [i] out of bounds") */
+    HARK_ERR_CUDA = 2,        /* CUDA runtime / launch failure, or no usable device            */
+    HARK_ERR_OOM = 3,         /* device or host allocation failed                              */
+    HARK_ERR_UNSUPPORTED = 4  /* well-formed request this build does not implement             */
+} hark_status;
+
+/* Comparison operators of a WHERE / HAVING conjunct. */
+typedef enum { HARK_GT = 0, HARK_GE = 1, HARK_LT = 2, HARK_LE = 3, HARK_EQ = 4, HARK_NE = 5 } hark_cmp;
+
+/* One conjunct `column <op> constant`.  Integer columns (i32/u32/i64) are widened to int64
+ * and compared with `ival`; f32 columns compare in f32 against (float)fval, f64 columns in
+ * f64 against fval; NaN compares false except under HARK_NE (IEEE).                        */
+typedef struct {
+    int32_t col;   /* column index into the table the predicate is evaluated on */
+    int32_t op;    /* hark_cmp */
+    int64_t ival;
+    double fval;
+} hark_pred;
+
+/* Aggregate codes.  0-4 are exactly parse.py:81 / groupby.fut:35-41 (0 and any unknown code
+ * fall through to `min`, groupby.fut:41); 5 and 6 are extensions.                            */
+typedef enum {
+    HARK_AGG_KEY = 0, HARK_AGG_PROD = 1, HARK_AGG_SUM = 2, HARK_AGG_MAX = 3, HARK_AGG_MIN = 4,
+    HARK_AGG_COUNT = 5, HARK_AGG_AVG = 6
+} hark_agg;
+
+/* Synthetic column generator (hark_table_synth).  Value of (column c, global row r) is a pure
+ * function of (seed, c, r): h = hark_mix64(seed, c, r) as defined in DESIGN.md §generator, so
+ * the host oracle can regenerate any row range.                                              */
+typedef enum {
+    HARK_GEN_UNIFORM = 0, /* ints: lo + mulhi64(h, range)  (range 0: lo + h, wrapping);
+                             f32: fmaf(u24, fhi-flo, flo), u24 = (h>>40)*2^-24;
+                             f64: fma (u53, fhi-flo, flo), u53 = (h>>11)*2^-53               */
+    HARK_GEN_AFFINE = 1,  /* ((a*r + b) mod 2^64) mod range (range 0: no mod) — unique keys when
+                             gcd(a, range) = 1 and a*r+b does not wrap                       */
+    HARK_GEN_CONST = 2    /* lo (ints) / flo (floats)                                         */
+} hark_gen_kind;
+
+typedef struct {
+    int32_t kind; /* hark_gen_kind */
+    int32_t reserved;
+    int64_t lo;
+    uint64_t range;
+    double flo, fhi;
+    uint64_t a, b;
+} hark_colspec;
+
+/* Per-entry measurements taken with CUDA events on the context's stream. */
+typedef struct {
+    double kernel_ms;   /* device time of the entry's dominant kernel(s)                     */
+    double total_ms;    /* device time of the whole entry (first launch to last)             */
+    int64_t alg_bytes;  /* algorithmic bytes of the entry              */
+    int64_t rows_in;
+    int64_t rows_out;
+    int64_t launches;   /* kernels this entry launched                                       */
+} hark_stats;
+
+/* ---- context (replaces futhark_context_config_new / futhark_context_new, FutharkContext.py:41) ---- */
+int hark_abi_version(void);
+/* device: CUDA ordinal, -1 = the calling thread's current device.
+ * stream: a cudaStream_t to launch on (borrowed), or NULL for a stream the context owns.     */
+hark_ctx *hark_context_new(int device, void *stream);
+void hark_context_free(hark_ctx *ctx);
+int hark_context_sync(hark_ctx *ctx);
+char *hark_context_get_error(hark_ctx *ctx); /* malloc'd, caller frees; NULL if no error      */
+int hark_context_device(hark_ctx *ctx);
+/* Text of the last failure of hark_context_new (static storage), for when it returned NULL.  */
+const char *hark_last_init_error(void);
+
+/* ---- tables (replace futhark_new_{i32,u32}_2d / futhark_values_* / futhark_shape_* / futhark_free_*) ---- */
+/* Row-major homogeneous host array [n][m] -> device SoA (table.py:52-74 data model).          */
+int hark_table_from_host(hark_ctx *ctx, hark_table **out, const void *rowmajor, int64_t n, int64_t m,
+                         int32_t dtype);
+/* m host column arrays, one dtype each. */
+int hark_table_from_columns(hark_ctx *ctx, hark_table **out, const void *const *host_cols,
+                            const int32_t *dtypes, int64_t n, int64_t m);
+/* m device column arrays (16-byte aligned), borrowed: the table never frees them.             */
+int hark_table_from_device(hark_ctx *ctx, hark_table **out, void *const *dev_cols, const int32_t *dtypes,
+                           int64_t n, int64_t m);
+/* Generated on the device; rows are global rows row0 .. row0+n-1 of the synthetic relation.    */
+int hark_table_synth(hark_ctx *ctx, hark_table **out, int64_t n, int64_t m, const int32_t *dtypes,
+                     uint64_t seed, const hark_colspec *specs, int64_t row0);
+int hark_table_shape(hark_ctx *ctx, const hark_table *t, int64_t shape[2]);
+int hark_table_dtypes(hark_ctx *ctx, const hark_table *t, int32_t *dtypes_out /* [m] */);
+/* Device SoA -> row-major host [n][m]; all columns must share one dtype.                      */
+int hark_table_to_host(hark_ctx *ctx, const hark_table *t, void *rowmajor_out);
+int hark_table_column_to_host(hark_ctx *ctx, const hark_table *t, int32_t col, int64_t row0, int64_t nrows,
+                              void *out);
+void *hark_table_column_ptr(hark_ctx *ctx, const hark_table *t, int32_t col); /* device pointer, borrowed */
+int hark_table_free(hark_ctx *ctx, hark_table *t);
+
+/* ---- reference-pinned entries: argument order of main.fut:7,9 and join.fut:52-54 ---- */
+/* out[r][j] = db[r][cols[j]]  (select.fut:9-23).  Any dtype; row order kept.                   */
+int hark_entry_query_sel(hark_ctx *ctx, hark_table **out, const hark_table *db, const int32_t *cols, int64_t k);
+/* groupby.fut:51-62: all columns i32/u32, compared and combined as u32; one row per distinct
+ * key ascending unsigned; row = [key, agg_1..agg_c], agg_i = fold(op t_cols[i-1]) over
+ * db[rows of group][s_cols[i-1]], codes 0-4 as hark_agg (0/unknown -> min).  Output u32.       */
+int hark_entry_query_groupby(hark_ctx *ctx, hark_table **out, const hark_table *db, int32_t g_col,
+                             const int32_t *s_cols, const int32_t *t_cols, int64_t c);
+/* join.fut:52-75: inner equi-join on db1[:,col1] == db2[:,col2] (u32); row = db1[r1][cols1] ++
+ * db2[r2][cols2]; ordered by key ascending unsigned, then r1, then r2.                         */
+int hark_entry_join(hark_ctx *ctx, hark_table **out, const hark_table *db1, const hark_table *db2, int32_t col1,
+                    int32_t col2, const int32_t *cols1, int64_t l, const int32_t *cols2, int64_t k);
+
+/* ---- extensions (no reference implementation; semantics in DESIGN.md §extensions) ---- */
+/* SELECT cols WHERE p_1 AND ... AND p_np; input row order kept (what `filter` at select.fut:18
+ * would do).                                                                                   */
+int hark_entry_query_filter(hark_ctx *ctx, hark_table **out, const hark_table *db, const int32_t *cols, int64_t k,
+                            const hark_pred *preds, int64_t np);
+/* Typed GROUP BY: key column any integer dtype, ordered by its own signedness; value columns any
+ * dtype; codes 0-6; SUM/PROD wrap in the column's width, COUNT -> i64 column, AVG -> f64 column;
+ * HAVING = conjunction over OUTPUT column indices (0 = key).                                   */
+int hark_entry_query_groupby_ex(hark_ctx *ctx, hark_table **out, const hark_table *db, int32_t g_col,
+                                const int32_t *s_cols, const int32_t *ops, int64_t c, const hark_pred *having,
+                                int64_t nh);
+/* SELECT cols ORDER BY key_cols[0] [DESC], key_cols[1] ... ; stable w.r.t. input row order;
+ * signed order for i32/i64, IEEE total order with NaN last for f32/f64.                       */
+int hark_entry_query_orderby(hark_ctx *ctx, hark_table **out, const hark_table *db, const int32_t *cols, int64_t k,
+                             const int32_t *key_cols, const int32_t *desc, int64_t nk);
+/* SELECT d.g_col, agg(f.s_cols) FROM fact f JOIN dim d ON f.fk_col = d.pk_col GROUP BY d.g_col
+ * (dim.pk_col unique).  Output as hark_entry_query_groupby_ex.                                */
+int hark_entry_join_groupby(hark_ctx *ctx, hark_table **out, const hark_table *fact, const hark_table *dim,
+                            int32_t fk_col, int32_t pk_col, int32_t g_col, const int32_t *s_cols, const int32_t *ops,
+                            int64_t c);
+
+/* ---- building blocks exported for the multi-GPU layer and for tests ---- */
+/* Stable LSD radix sort of whole rows by one column (ascending; signedness of the dtype).      */
+int hark_table_sort_by(hark_ctx *ctx, hark_table **out, const hark_table *db, int32_t key_col);
+/* Stable partition of rows into nparts buckets by mix(key) % nparts (integer key column);
+ * counts_out[nparts] (host) receives the bucket sizes; rows of bucket p are contiguous.        */
+int hark_table_partition_by_hash(hark_ctx *ctx, hark_table **out, const hark_table *db, int32_t key_col,
+                                 int32_t nparts, int64_t *counts_out);
+/* Rows [row0, row0+nrows) of t as a new table (device copy). */
+int hark_table_slice(hark_ctx *ctx, hark_table **out, const hark_table *t, int64_t row0, int64_t nrows);
+/* Concatenate two tables with equal schemas. */
+int hark_table_concat(hark_ctx *ctx, hark_table **out, const hark_table *a, const hark_table *b);
+
+/* ---- measurement ---- */
+int hark_stats_last(hark_ctx *ctx, hark_stats *out);
+int64_t hark_stats_total_launches(hark_ctx *ctx);
+/* Tuning knobs for experiments ("filter.impl", "filter.ctas_per_sm", ...); returns HARK_ERR_ARG
+ * for an unknown key.                                                                          */
+int hark_context_set_option(hark_ctx *ctx, const char *key, int64_t value);
+
+/* ---- pinned host memory for callers that want DMA-speed uploads ---- */
+void *hark_host_alloc(int64_t bytes);
+void hark_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HARK_H */

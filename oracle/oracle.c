@@ -1,0 +1,475 @@
+/*
+ * oracle.c — CPU restatement of HarkDB's operator path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library.  Nothing under harkdb_b200/ links, loads or calls it: the product path is
+ * libhark.so (CUDA) and fails loudly without a GPU.
+ *
+ * What is restated (reference file:line under /root/reference):
+ *   segmented primitives   futhark/lib/github.com/diku-dk/segmented/segmented.fut:7-103
+ *   query_sel              futhark/select.fut:9-23, futhark/main.fut:7
+ *   query_groupby          futhark/groupby.fut:8-62, futhark/main.fut:9
+ *   join                   futhark/join.fut:9-75
+ * with the sequential meaning of the SOACs (what `futhark c`, setup.sh:12, executes): left folds,
+ * u32 wrap-around, i32 indices.  The radix sort is kept as the reference writes it — 32 stable
+ * 1-bit passes that move whole rows (groupby.fut:21-22) — because these functions double as
+ * "the reference's CPU algorithm" in bench.py; a pass is written as count + stable split rather
+ * than the scan/map/scatter chain, which computes the same permutation with fewer sweeps, so the
+ * CPU baseline is if anything flattered.
+ *
+ * Pinning: the segmented primitives are checked against the reference's own known-answer tests
+ * (segmented_tests.fut:5-72, tests/golden/segmented_kats.json).  query_sel / query_groupby / join
+ * have NO expected outputs anywhere in the reference => PARITY UNPINNED by reference tests; they
+ * are checked against oracle/hark_ref.py, a line-by-line SOAC simulation of the sources.
+ * oracle_query_filter and oracle_synth_column restate extensions the reference does not have
+ * (select.fut:18 is a commented-out stub): PARITY UNPINNED, oracle-defined.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "../include/hark.h"
+
+/* ------------------------------------------------------------------------------------------
+ * segmented.fut — instantiated at i32 with (+), which is what the reference's tests exercise.
+ * ---------------------------------------------------------------------------------------- */
+
+/* segmented.fut:7-13 */
+void oracle_segmented_scan_add_i32(const uint8_t *flags, const int32_t *as, int64_t n, int32_t *out) {
+    int f_acc = 0;
+    int32_t v_acc = 0; /* (false, ne) */
+    for (int64_t i = 0; i < n; i++) {
+        int yf = flags[i] != 0;
+        v_acc = yf ? as[i] : (int32_t)((uint32_t)v_acc + (uint32_t)as[i]);
+        f_acc = f_acc || yf;
+        out[i] = v_acc;
+    }
+    (void)f_acc;
+}
+
+/* segmented.fut:20-37.  Returns the number of segments; out must hold n entries. */
+int64_t oracle_segmented_reduce_add_i32(const uint8_t *flags, const int32_t *as, int64_t n, int32_t *out) {
+    if (n == 0) return 0;
+    int32_t *scanned = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
+    oracle_segmented_scan_add_i32(flags, as, n, scanned);
+    /* segment_ends = rotate 1 flags; offsets = scan (+) of them; scatter at offset-1 where end */
+    int32_t off = 0;
+    int64_t nseg = 0;
+    for (int64_t i = 0; i < n; i++) {
+        int end = flags[(i + 1) % n] != 0;
+        off += end;
+        if (end) out[off - 1] = scanned[i];
+    }
+    nseg = off;
+    free(scanned);
+    return nseg;
+}
+
+/* segmented.fut:44-50.  Returns the output length; out must hold sum(reps) entries. */
+int64_t oracle_replicated_iota(const int32_t *reps, int64_t n, int32_t *out) {
+    int64_t total = 0;
+    for (int64_t i = 0; i < n; i++) total += reps[i];
+    if (total == 0) return 0;
+    int32_t *tmp = (int32_t *)calloc((size_t)total, sizeof(int32_t));
+    int32_t s1_prev = 0; /* s2[i] = i==0 ? 0 : s1[i-1] */
+    for (int64_t i = 0; i < n; i++) {
+        int32_t s2 = (i == 0) ? 0 : s1_prev;
+        if (s2 >= 0 && s2 < total && (int32_t)i > tmp[s2]) tmp[s2] = (int32_t)i; /* reduce_by_index max */
+        s1_prev += reps[i];
+    }
+    uint8_t *flags = (uint8_t *)malloc((size_t)total);
+    for (int64_t j = 0; j < total; j++) flags[j] = tmp[j] > 0;
+    oracle_segmented_scan_add_i32(flags, tmp, total, out);
+    free(flags);
+    free(tmp);
+    return total;
+}
+
+/* segmented.fut:58-60 */
+void oracle_segmented_iota(const uint8_t *flags, int64_t n, int32_t *out) {
+    int32_t *ones = (int32_t *)calloc((size_t)(n ? n : 1), sizeof(int32_t));
+    for (int64_t i = 0; i < n; i++) ones[i] = 1;
+    oracle_segmented_scan_add_i32(flags, ones, n, out);
+    for (int64_t i = 0; i < n; i++) out[i] -= 1;
+    free(ones);
+}
+
+typedef int32_t (*oracle_sz_fn)(int32_t);
+typedef int32_t (*oracle_get_fn)(int32_t, int32_t);
+
+/* segmented.fut:70-74 on i32 sources.  idxs/iotas scratch is internal.  Returns output length. */
+static int64_t expand_i32(oracle_sz_fn sz, oracle_get_fn get, const int32_t *arr, int64_t n, int32_t **out_p,
+                          uint8_t **flags_p) {
+    int32_t *szs = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n ? n : 1));
+    int64_t total = 0;
+    for (int64_t i = 0; i < n; i++) {
+        szs[i] = sz(arr[i]);
+        total += szs[i];
+    }
+    int32_t *idxs = (int32_t *)malloc(sizeof(int32_t) * (size_t)(total ? total : 1));
+    oracle_replicated_iota(szs, n, idxs);
+    uint8_t *flags = (uint8_t *)malloc((size_t)(total ? total : 1));
+    for (int64_t j = 0; j < total; j++) flags[j] = idxs[j] != idxs[(j - 1 + total) % total]; /* rotate -1 */
+    int32_t *iotas = (int32_t *)malloc(sizeof(int32_t) * (size_t)(total ? total : 1));
+    oracle_segmented_iota(flags, total, iotas);
+    int32_t *out = (int32_t *)malloc(sizeof(int32_t) * (size_t)(total ? total : 1));
+    for (int64_t j = 0; j < total; j++) out[j] = get(arr[idxs[j]], iotas[j]);
+    free(szs);
+    free(idxs);
+    free(iotas);
+    *out_p = out;
+    if (flags_p) *flags_p = flags; else free(flags);
+    return total;
+}
+
+static int32_t sz_id(int32_t x) { return x; }
+static int32_t get_mul(int32_t x, int32_t i) { return (int32_t)((uint32_t)x * (uint32_t)i); }
+static int32_t sz_id_or_1(int32_t x) { return x == 0 ? 1 : x; }
+static int32_t get_mul_or_ne(int32_t x, int32_t i) { return x == 0 ? 0 : get_mul(x, i); }
+
+/* segmented_tests.fut:51-56: expand (\x -> x) (\x i -> x*i) */
+int64_t oracle_expand_mul(const int32_t *arr, int64_t n, int32_t *out) {
+    int32_t *tmp;
+    int64_t total = expand_i32(sz_id, get_mul, arr, n, &tmp, NULL);
+    memcpy(out, tmp, sizeof(int32_t) * (size_t)total);
+    free(tmp);
+    return total;
+}
+
+/* segmented.fut:84-91 at the instantiation of segmented_tests.fut:59-64 */
+int64_t oracle_expand_reduce_mul_add(const int32_t *arr, int64_t n, int32_t *out) {
+    int32_t *vs;
+    uint8_t *flags;
+    int64_t total = expand_i32(sz_id, get_mul, arr, n, &vs, &flags);
+    int64_t nseg = oracle_segmented_reduce_add_i32(flags, vs, total, out);
+    free(vs);
+    free(flags);
+    return nseg;
+}
+
+/* segmented.fut:97-103 at the instantiation of segmented_tests.fut:67-72 */
+int64_t oracle_expand_outer_reduce_mul_add(const int32_t *arr, int64_t n, int32_t *out) {
+    int32_t *vs;
+    uint8_t *flags;
+    int64_t total = expand_i32(sz_id_or_1, get_mul_or_ne, arr, n, &vs, &flags);
+    int64_t nseg = oracle_segmented_reduce_add_i32(flags, vs, total, out);
+    free(vs);
+    free(flags);
+    return nseg;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * select.fut:9-23 — projection.  Returns 1 on an out-of-bounds column (Futhark bounds error).
+ * ---------------------------------------------------------------------------------------- */
+int oracle_query_sel_i32(const int32_t *db, int64_t n, int64_t m, const int32_t *cols, int64_t k, int32_t *out) {
+    for (int64_t j = 0; j < k; j++)
+        if (cols[j] < 0 || cols[j] >= m) return n > 0 ? 1 : 0; /* `map` over zero rows never indexes */
+    for (int64_t r = 0; r < n; r++)
+        for (int64_t j = 0; j < k; j++) out[r * k + j] = db[r * m + cols[j]];
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * groupby.fut
+ * ---------------------------------------------------------------------------------------- */
+
+/* groupby.fut:8-18: stable split of rows (width s) on bit `bitn` of column 0. */
+static void rsort_step_rows(const uint32_t *src, uint32_t *dst, int64_t n, int64_t s, int bitn) {
+    int64_t zeros = 0;
+    for (int64_t i = 0; i < n; i++) zeros += !((src[i * s] >> bitn) & 1u);
+    int64_t p0 = 0, p1 = zeros;
+    for (int64_t i = 0; i < n; i++) {
+        int64_t d = ((src[i * s] >> bitn) & 1u) ? p1++ : p0++;
+        memcpy(dst + d * s, src + i * s, sizeof(uint32_t) * (size_t)s);
+    }
+}
+
+/* groupby.fut:35-41 */
+static inline uint32_t type_func(int32_t typ, uint32_t v1, uint32_t v2) {
+    switch (typ) {
+    case 1: return v1 * v2;
+    case 2: return v1 + v2;
+    case 3: return v1 > v2 ? v1 : v2;
+    case 4: return v1 < v2 ? v1 : v2;
+    default: return v1 < v2 ? v1 : v2;
+    }
+}
+
+/* main.fut:9 -> groupby.fut:60-62 -> :51-58.  out must hold n*(c+1) u32; *G receives the group
+ * count.  Returns 1 on an out-of-bounds column index. */
+int oracle_query_groupby_u32(const uint32_t *db, int64_t n, int64_t m, int32_t g_col, const int32_t *s_cols,
+                             const int32_t *t_cols, int64_t c, uint32_t *out, int64_t *G) {
+    int64_t s = c + 1;
+    *G = 0;
+    if (n == 0) return 0;
+    if (g_col < 0 || g_col >= m) return 1;
+    for (int64_t j = 0; j < c; j++)
+        if (s_cols[j] < 0 || s_cols[j] >= m) return 1;
+    uint32_t *a = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(n * s));
+    uint32_t *b = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(n * s));
+    if (!a || !b) { free(a); free(b); return 3; }
+    for (int64_t r = 0; r < n; r++) { /* :52-53 keep = [g_col] ++ s_cols */
+        a[r * s] = db[r * m + g_col];
+        for (int64_t j = 0; j < c; j++) a[r * s + 1 + j] = db[r * m + s_cols[j]];
+    }
+    for (int bit = 0; bit < 32; bit++) { /* :21-22 */
+        rsort_step_rows(a, b, n, s, bit);
+        uint32_t *t = a; a = b; b = t;
+    }
+    /* :55-58 flags + segmented scan with merge + take each segment's last element */
+    int64_t g = -1;
+    for (int64_t r = 0; r < n; r++) {
+        if (r == 0 || a[(r - 1) * s] != a[r * s]) {
+            g++;
+            memcpy(out + g * s, a + r * s, sizeof(uint32_t) * (size_t)s);
+        } else {
+            for (int64_t j = 1; j < s; j++) out[g * s + j] = type_func(t_cols[j - 1], out[g * s + j], a[r * s + j]);
+        }
+    }
+    *G = g + 1;
+    free(a);
+    free(b);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * join.fut
+ * ---------------------------------------------------------------------------------------- */
+typedef struct { uint32_t key; int32_t tag; int32_t rowid; } triple_t;
+
+static void rsort_step_triples(const triple_t *src, triple_t *dst, int64_t n, int bitn) {
+    int64_t zeros = 0;
+    for (int64_t i = 0; i < n; i++) zeros += !((src[i].key >> bitn) & 1u);
+    int64_t p0 = 0, p1 = zeros;
+    for (int64_t i = 0; i < n; i++) dst[((src[i].key >> bitn) & 1u) ? p1++ : p0++] = src[i];
+}
+
+/* join.fut:52-75.  *out is malloc'd here ([P][l+k] u32, caller frees with oracle_free). */
+int oracle_join_u32(const uint32_t *db1, int64_t n, int64_t m, const uint32_t *db2, int64_t s, int64_t t,
+                    int32_t col1, int32_t col2, const int32_t *cols1, int64_t l, const int32_t *cols2, int64_t k,
+                    uint32_t **out, int64_t *P) {
+    *out = NULL;
+    *P = 0;
+    if ((n > 0 && (col1 < 0 || col1 >= m)) || (s > 0 && (col2 < 0 || col2 >= t))) return 1;
+    int64_t tot = n + s;
+    triple_t *a = (triple_t *)malloc(sizeof(triple_t) * (size_t)(tot ? tot : 1));
+    triple_t *b = (triple_t *)malloc(sizeof(triple_t) * (size_t)(tot ? tot : 1));
+    for (int64_t i = 0; i < n; i++) a[i] = (triple_t){db1[i * m + col1], 1, (int32_t)i};     /* :55 */
+    for (int64_t i = 0; i < s; i++) a[n + i] = (triple_t){db2[i * t + col2], 2, (int32_t)i}; /* :56-57 */
+    for (int bit = 0; bit < 32; bit++) {                                                     /* :58 */
+        rsort_step_triples(a, b, tot, bit);
+        triple_t *tmp = a; a = b; b = tmp;
+    }
+    /* :59-68: per key segment, partition by tag (stable) and emit the left-major cross product */
+    int64_t cap = 16, np = 0;
+    int32_t *p1 = (int32_t *)malloc(sizeof(int32_t) * (size_t)cap), *p2 = (int32_t *)malloc(sizeof(int32_t) * (size_t)cap);
+    int64_t st = 0;
+    while (st < tot) {
+        int64_t fn = st + 1;
+        while (fn < tot && a[fn].key == a[st].key) fn++;
+        for (int64_t i = st; i < fn; i++) {
+            if (a[i].tag != 1) continue;
+            for (int64_t j = st; j < fn; j++) {
+                if (a[j].tag == 1) continue;
+                if (np == cap) {
+                    cap *= 2;
+                    p1 = (int32_t *)realloc(p1, sizeof(int32_t) * (size_t)cap);
+                    p2 = (int32_t *)realloc(p2, sizeof(int32_t) * (size_t)cap);
+                }
+                p1[np] = a[i].rowid;
+                p2[np] = a[j].rowid;
+                np++;
+            }
+        }
+        st = fn;
+    }
+    int rc = 0;
+    if (np > 0) {
+        for (int64_t j = 0; j < l; j++) if (cols1[j] < 0 || cols1[j] >= m) rc = 1;
+        for (int64_t j = 0; j < k; j++) if (cols2[j] < 0 || cols2[j] >= t) rc = 1;
+    }
+    if (rc == 0) {
+        int64_t w = l + k;
+        uint32_t *o = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)((np * w) ? np * w : 1));
+        for (int64_t p = 0; p < np; p++) { /* :69-75 */
+            for (int64_t j = 0; j < l; j++) o[p * w + j] = db1[(int64_t)p1[p] * m + cols1[j]];
+            for (int64_t j = 0; j < k; j++) o[p * w + l + j] = db2[(int64_t)p2[p] * t + cols2[j]];
+        }
+        *out = o;
+        *P = np;
+    }
+    free(a); free(b); free(p1); free(p2);
+    return rc;
+}
+
+void oracle_free(void *p) { free(p); }
+
+/* ------------------------------------------------------------------------------------------
+ * Extension: SELECT cols WHERE conjunction (what `filter` at select.fut:18 + `map (sel cols)` at
+ * :19 would compute).  Row-major in, row-major out, input order kept.  `threads` > 1 uses OpenMP
+ * (chunk -> count -> prefix -> write), the stand-in for `futhark multicore`.
+ * ---------------------------------------------------------------------------------------- */
+static inline size_t dtype_size(int dt) { return (dt == HARK_I64 || dt == HARK_F64) ? 8 : 4; }
+
+static inline int cmp_i64(int op, int64_t x, int64_t c) {
+    switch (op) {
+    case HARK_GT: return x > c;
+    case HARK_GE: return x >= c;
+    case HARK_LT: return x < c;
+    case HARK_LE: return x <= c;
+    case HARK_EQ: return x == c;
+    default: return x != c;
+    }
+}
+static inline int cmp_f32(int op, float x, float c) {
+    switch (op) {
+    case HARK_GT: return x > c;
+    case HARK_GE: return x >= c;
+    case HARK_LT: return x < c;
+    case HARK_LE: return x <= c;
+    case HARK_EQ: return x == c;
+    default: return x != c;
+    }
+}
+static inline int cmp_f64(int op, double x, double c) {
+    switch (op) {
+    case HARK_GT: return x > c;
+    case HARK_GE: return x >= c;
+    case HARK_LT: return x < c;
+    case HARK_LE: return x <= c;
+    case HARK_EQ: return x == c;
+    default: return x != c;
+    }
+}
+
+static inline int row_passes(const char *row, int dt, const hark_pred *preds, int64_t np) {
+    for (int64_t p = 0; p < np; p++) {
+        int ok;
+        switch (dt) {
+        case HARK_I32: ok = cmp_i64(preds[p].op, ((const int32_t *)row)[preds[p].col], preds[p].ival); break;
+        case HARK_U32: ok = cmp_i64(preds[p].op, ((const uint32_t *)row)[preds[p].col], preds[p].ival); break;
+        case HARK_I64: ok = cmp_i64(preds[p].op, ((const int64_t *)row)[preds[p].col], preds[p].ival); break;
+        case HARK_F32: ok = cmp_f32(preds[p].op, ((const float *)row)[preds[p].col], (float)preds[p].fval); break;
+        default: ok = cmp_f64(preds[p].op, ((const double *)row)[preds[p].col], preds[p].fval); break;
+        }
+        if (!ok) return 0;
+    }
+    return 1;
+}
+
+static int64_t filter_range(const char *db, int64_t r0, int64_t r1, int64_t m, int dt, const int32_t *cols, int64_t k,
+                            const hark_pred *preds, int64_t np, char *out /* NULL = count only */) {
+    size_t w = dtype_size(dt);
+    int64_t cnt = 0;
+    for (int64_t r = r0; r < r1; r++) {
+        const char *row = db + (size_t)r * (size_t)m * w;
+        if (!row_passes(row, dt, preds, np)) continue;
+        if (out) {
+            char *o = out + (size_t)cnt * (size_t)k * w;
+            if (w == 4) for (int64_t j = 0; j < k; j++) ((uint32_t *)o)[j] = ((const uint32_t *)row)[cols[j]];
+            else        for (int64_t j = 0; j < k; j++) ((uint64_t *)o)[j] = ((const uint64_t *)row)[cols[j]];
+        }
+        cnt++;
+    }
+    return cnt;
+}
+
+int oracle_query_filter(const void *db, int64_t n, int64_t m, int32_t dtype, const int32_t *cols, int64_t k,
+                        const hark_pred *preds, int64_t np, void *out, int64_t *n_out, int32_t threads) {
+    *n_out = 0;
+    if (dtype < HARK_I32 || dtype > HARK_F64) return 1;
+    for (int64_t j = 0; j < k; j++) if (cols[j] < 0 || cols[j] >= m) return 1;
+    for (int64_t p = 0; p < np; p++)
+        if (preds[p].col < 0 || preds[p].col >= m || preds[p].op < HARK_GT || preds[p].op > HARK_NE) return 1;
+    size_t w = dtype_size(dtype);
+#ifdef _OPENMP
+    if (threads > 1) {
+        int T = threads;
+        int64_t *cnt = (int64_t *)calloc((size_t)T + 1, sizeof(int64_t));
+#pragma omp parallel num_threads(T)
+        {
+            int tid = omp_get_thread_num();
+            int64_t r0 = n * tid / T, r1 = n * (tid + 1) / T;
+            cnt[tid + 1] = filter_range((const char *)db, r0, r1, m, dtype, cols, k, preds, np, NULL);
+#pragma omp barrier
+#pragma omp single
+            { for (int i = 0; i < T; i++) cnt[i + 1] += cnt[i]; }
+            filter_range((const char *)db, r0, r1, m, dtype, cols, k, preds, np,
+                         (char *)out + (size_t)cnt[tid] * (size_t)k * w);
+        }
+        *n_out = cnt[T];
+        free(cnt);
+        return 0;
+    }
+#endif
+    (void)threads;
+    *n_out = filter_range((const char *)db, 0, n, m, dtype, cols, k, preds, np, (char *)out);
+    return 0;
+}
+
+int oracle_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Synthetic relation generator (include/hark.h hark_colspec).  Restated on
+ * the host so any row range of a device-generated table can be regenerated and checked.
+ * ---------------------------------------------------------------------------------------- */
+uint64_t oracle_mix64(uint64_t seed, uint64_t col, uint64_t row) {
+    uint64_t z = (seed ^ ((col + 1) * 0xD6E8FEB86659FD93ULL)) + (row + 1) * 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+static inline uint64_t mulhi64(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
+
+int oracle_synth_column(int32_t dtype, const hark_colspec *spec, uint64_t seed, int32_t col, int64_t row0, int64_t n,
+                        void *out, int32_t threads) {
+    if (dtype < HARK_I32 || dtype > HARK_F64) return 1;
+    (void)threads;
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(threads > 0 ? threads : 1) schedule(static)
+#endif
+    for (int64_t i = 0; i < n; i++) {
+        uint64_t r = (uint64_t)(row0 + i);
+        uint64_t iv = 0;
+        double fv = 0.0;
+        float ffv = 0.0f;
+        int is_f = (dtype == HARK_F32 || dtype == HARK_F64);
+        switch (spec->kind) {
+        case HARK_GEN_UNIFORM: {
+            uint64_t h = oracle_mix64(seed, (uint64_t)col, r);
+            if (dtype == HARK_F32) ffv = fmaf((float)(h >> 40) * 0x1p-24f, (float)(spec->fhi - spec->flo), (float)spec->flo);
+            else if (dtype == HARK_F64) fv = fma((double)(h >> 11) * 0x1p-53, spec->fhi - spec->flo, spec->flo);
+            else iv = (uint64_t)spec->lo + (spec->range ? mulhi64(h, spec->range) : h);
+            break;
+        }
+        case HARK_GEN_AFFINE: {
+            uint64_t v = spec->a * r + spec->b; /* wraps mod 2^64 first, then mod range */
+            if (spec->range) v %= spec->range;
+            iv = v; fv = (double)v; ffv = (float)v;
+            break;
+        }
+        default:
+            iv = (uint64_t)spec->lo; fv = spec->flo; ffv = (float)spec->flo;
+            break;
+        }
+        (void)is_f;
+        switch (dtype) {
+        case HARK_I32: case HARK_U32: ((uint32_t *)out)[i] = (uint32_t)iv; break;
+        case HARK_I64: ((uint64_t *)out)[i] = iv; break;
+        case HARK_F32: ((float *)out)[i] = ffv; break;
+        default: ((double *)out)[i] = fv; break;
+        }
+    }
+    return 0;
+}
