@@ -1,0 +1,293 @@
+"""SQL statement -> operator plan.  Same entry point and plan keys as the reference's parse.py.
+
+Mirrors /root/reference/parse.py: ``getIndex`` (:9-13) and ``sql_parse(tables, sql_statement)``
+(:16-91).  For the two statement forms the reference implements, the returned dict has exactly its
+keys — ``{"table", "select"}`` (:58) and ``{"select", "groupbys", "table", "g_col"}`` (:90) — with the
+same column-index lists and aggregate codes (``prod 1, sum 2, max 3, min 4``, :81; the group column
+itself contributes ``(g_col, 0)``, :73-75), and the same exception messages (:33,54,69,78,87).
+
+Extensions (clauses the reference's README lists but parse.py ignores): ``where``
+(conjunction of column-vs-constant comparisons), ``count``/``avg`` (codes 5, 6), ``having``,
+``orderby``, ``join``, ``limit``, ``select *`` and the single-column select that crashes the
+reference (:48-51 iterates a dict).  They appear as extra plan keys; a plan without them is
+byte-for-byte what the reference would build.
+
+``moz_sql_parser`` is not installed here; ``sqlmini.parse`` emits the same dict shapes.
+"""
+
+from .sqlmini import parse
+
+FUNC_TO_FUT = {"prod": 1, "sum": 2, "max": 3, "min": 4}          # parse.py:81
+FUNC_TO_FUT_EXT = {**FUNC_TO_FUT, "count": 5, "avg": 6}
+CMP_TO_CODE = {"gt": 0, "gte": 1, "lt": 2, "lte": 3, "eq": 4, "neq": 5}
+_FLIP = {"gt": "lt", "gte": "lte", "lt": "gt", "lte": "gte", "eq": "eq", "neq": "neq"}
+
+
+def getIndex(elements, value):
+    for i, v in enumerate(elements):
+        if v == value:
+            return i
+    return -1
+
+
+def _as_list(x):
+    return x if isinstance(x, list) else [x]
+
+
+def _strip_qualifier(name, aliases):
+    """`f.col` -> (table_key, col); bare `col` -> (None, col)."""
+    if isinstance(name, str) and "." in name:
+        q, c = name.split(".", 1)
+        return aliases.get(q, q), c
+    return None, name
+
+
+def _conjuncts(expr):
+    if isinstance(expr, dict) and "and" in expr:
+        out = []
+        for e in expr["and"]:
+            out.extend(_conjuncts(e))
+        return out
+    return [expr]
+
+
+def _pred(expr, resolve):
+    """{"gt": ["a", 4]} -> (col_index, op_code, ival, fval).  `resolve(operand) -> column index`."""
+    if not isinstance(expr, dict) or len(expr) != 1:
+        raise Exception(f"unsupported predicate {expr}")
+    (op, args), = expr.items()
+    if op not in CMP_TO_CODE or not isinstance(args, list) or len(args) != 2:
+        raise Exception(f"unsupported predicate operator {op} (only AND of column-vs-constant comparisons)")
+    lhs, rhs = args
+    if isinstance(lhs, (int, float)) and not isinstance(rhs, (int, float)):
+        lhs, rhs, op = rhs, lhs, _FLIP[op]
+    if not isinstance(rhs, (int, float)):
+        raise Exception(f"unsupported predicate {expr}: right-hand side must be a numeric constant")
+    idx = resolve(lhs)
+    ival = int(rhs) if float(rhs) == int(rhs) else None
+    return (idx, CMP_TO_CODE[op], ival, float(rhs))
+
+
+def finalize_pred(pred, is_int_column):
+    """Integer columns compare in int64: fold a fractional constant into an equivalent integer one."""
+    import math
+    col, op, ival, fval = pred
+    if not is_int_column:
+        return (col, op, 0 if ival is None else ival, fval)
+    if ival is not None:
+        return (col, op, ival, fval)
+    # x > 2.5 <=> x > 2 ; x >= 2.5 <=> x > 2 ; x < 2.5 <=> x < 3 ; x <= 2.5 <=> x < 3 ; = never ; != always
+    fl = math.floor(fval)
+    if op in (0, 1):
+        return (col, 0, fl, fval)
+    if op in (2, 3):
+        return (col, 2, fl + 1, fval)
+    if op == 4:
+        return (col, 2, -(2 ** 63), fval)      # x < INT64_MIN: never true
+    return (col, 1, -(2 ** 63), fval)          # x >= INT64_MIN: always true
+
+
+def sql_parse(tables, sql_statement):
+    """Parses an SQL statement into the plan dict FutharkContext.sql dispatches on."""
+    js_obj = parse(sql_statement)
+
+    # ---- FROM (parse.py:28-33), extended with JOIN ----
+    from_items = _as_list(js_obj["from"])
+    aliases = {}
+
+    def table_of(item):
+        name = item["value"] if isinstance(item, dict) and "value" in item else item
+        if isinstance(item, dict) and "name" in item:
+            aliases[item["name"]] = name
+        if name in tables:
+            return name, tables[name]
+        raise Exception(f"{name} is not in tables")
+
+    table_name, table = table_of(from_items[0])
+    columns = table.get_schema()
+    plan_join = None
+    if len(from_items) > 1:
+        if len(from_items) > 2:
+            raise Exception("only a single JOIN is supported")
+        j = from_items[1]
+        jkey = "inner join" if "inner join" in j else "join"
+        name2, table2 = table_of(j[jkey])
+        on = j["on"]
+        if not (isinstance(on, dict) and "eq" in on):
+            raise Exception("JOIN needs an equality ON condition")
+        plan_join = {"name2": name2, "table2": table2, "on": on["eq"]}
+
+    def col_index(col_name, tname=table_name, cols=columns):
+        idx = getIndex(cols, col_name)
+        if idx < 0:
+            raise Exception(f"{col_name} is not in the schema of table {tname}")
+        return idx
+
+    if plan_join is not None:
+        return _plan_join(js_obj, table_name, table, plan_join, aliases)
+
+    def resolve_plain(operand):
+        _, c = _strip_qualifier(operand, aliases)
+        if not isinstance(c, str):
+            raise Exception(f"unsupported predicate operand {operand}")
+        return col_index(c)
+
+    where = [_pred(e, resolve_plain) for e in _conjuncts(js_obj["where"])] if "where" in js_obj else []
+    orderby = _as_list(js_obj["orderby"]) if "orderby" in js_obj else []
+    extras = {}
+    if where:
+        extras["where"] = where
+    if "limit" in js_obj:
+        extras["limit"] = int(js_obj["limit"])
+
+    # ---- plain SELECT (parse.py:42-58) ----
+    if "groupby" not in js_obj.keys():
+        fut_cols_selects = []
+        if js_obj["select"] == "*":
+            fut_cols_selects = list(range(len(columns)))
+        else:
+            for pair in _as_list(js_obj["select"]):
+                if "value" in pair:
+                    col_name = pair["value"]
+                    if not isinstance(col_name, str):
+                        raise Exception(f"{col_name} needs a GROUP BY clause")
+                    fut_cols_selects += [col_index(_strip_qualifier(col_name, aliases)[1])]
+        if orderby:
+            extras["orderby"] = [(col_index(_strip_qualifier(k["value"], aliases)[1]),
+                                  1 if k.get("sort") == "desc" else 0) for k in orderby]
+        return {"table": table.get_handle(), "select": fut_cols_selects, **extras}
+
+    # ---- GROUP BY (parse.py:60-90) ----
+    fut_cols_selects = []
+    typ_cols_selects = []
+    gb = js_obj["groupby"]
+    if isinstance(gb, list):
+        raise Exception("GROUP BY over several columns is not supported")
+    g_col_name = _strip_qualifier(gb["value"], aliases)[1]
+    g_col = getIndex(columns, g_col_name)
+    if g_col < 0:
+        raise Exception(f"{g_col_name} is not in the schema of table {table_name}")
+
+    out_names = []      # output column descriptors, for HAVING / ORDER BY resolution
+    select_pairs = _as_list(js_obj["select"]) if js_obj["select"] != "*" else [{"value": g_col_name}]
+    for dic in select_pairs:
+        val = dic["value"]
+        if isinstance(val, str) and _strip_qualifier(val, aliases)[1] == g_col_name:
+            fut_cols_selects += [g_col]
+            typ_cols_selects += [0]
+            out_names.append(g_col_name)
+        elif isinstance(val, str):
+            raise Exception(f"{val} is not an aggregation function or the columns thats grouped on")
+        else:
+            for agg_func, agg_val in FUNC_TO_FUT_EXT.items():
+                if agg_func in val:
+                    agg_col_name = val[agg_func]
+                    if agg_col_name == "*":
+                        agg_col = g_col
+                    else:
+                        agg_col_name = _strip_qualifier(agg_col_name, aliases)[1]
+                        agg_col = getIndex(columns, agg_col_name)
+                        if agg_col < 0:
+                            raise Exception(f"{agg_col_name} is not in the schema of table {table_name}")
+                    fut_cols_selects += [agg_col]
+                    typ_cols_selects += [agg_val]
+                    out_names.append((agg_func, agg_col))
+        if "name" in dic and out_names:
+            extras.setdefault("aliases", {})[dic["name"]] = len(out_names)      # output index (0 = key)
+
+    def resolve_output(operand):
+        """HAVING / ORDER BY operand -> output column index (0 = key, i = i-th select item)."""
+        if isinstance(operand, dict):
+            (f, c), = operand.items()
+            c_idx = g_col if c == "*" else col_index(_strip_qualifier(c, aliases)[1])
+            for i, nm in enumerate(out_names):
+                if nm == (f, c_idx):
+                    return i + 1
+            raise Exception(f"{f}({c}) must appear in the select list to be used in HAVING / ORDER BY")
+        _, c = _strip_qualifier(operand, aliases)
+        if c in extras.get("aliases", {}):
+            return extras["aliases"][c]
+        if c == g_col_name:
+            return 0
+        raise Exception(f"{c} is not an output column of the GROUP BY")
+
+    if "having" in js_obj:
+        extras["having"] = [_pred(e, resolve_output) for e in _conjuncts(js_obj["having"])]
+    if orderby:
+        extras["orderby"] = [(resolve_output(k["value"]), 1 if k.get("sort") == "desc" else 0) for k in orderby]
+    extras.pop("aliases", None)
+    return {"select": fut_cols_selects, "groupbys": typ_cols_selects, "table": table.get_handle(), "g_col": g_col,
+            **extras}
+
+
+def _plan_join(js_obj, name1, table1, pj, aliases):
+    """FROM t1 JOIN t2 ON t1.a = t2.b, plain select list (join.fut:52 argument order) or
+    GROUP BY over a t2 column with aggregates over t1 columns (hark_entry_join_groupby)."""
+    name2, table2 = pj["name2"], pj["table2"]
+    schema = {name1: table1.get_schema(), name2: table2.get_schema()}
+
+    def locate(name):
+        q, c = _strip_qualifier(name, aliases)
+        if q is not None:
+            if q not in schema:
+                raise Exception(f"{q} is not in tables")
+            idx = getIndex(schema[q], c)
+            if idx < 0:
+                raise Exception(f"{c} is not in the schema of table {q}")
+            return q, idx
+        hits = [(t, getIndex(schema[t], c)) for t in (name1, name2) if getIndex(schema[t], c) >= 0]
+        if not hits:
+            raise Exception(f"{c} is not in the schema of table {name1}")
+        if len(hits) > 1 and name1 != name2:
+            raise Exception(f"{c} is ambiguous between {name1} and {name2}")
+        return hits[0]
+
+    (ta, ca), (tb, cb) = locate(pj["on"][0]), locate(pj["on"][1])
+    if ta == name2 and tb == name1:
+        (ta, ca), (tb, cb) = (tb, cb), (ta, ca)
+    if not (ta == name1 and tb == name2):
+        raise Exception("JOIN condition must compare one column of each table")
+    plan = {"table": table1.get_handle(), "table2": table2.get_handle(), "join": (ca, cb)}
+    for key in ("where", "having", "orderby"):
+        if key in js_obj:
+            raise Exception(f"{key.upper()} together with JOIN is not supported")
+    if "groupby" in js_obj:
+        gq, gc = locate(js_obj["groupby"]["value"])
+        if gq != name2:
+            raise Exception("JOIN ... GROUP BY must group on a column of the joined (second) table")
+        s_cols, ops = [], []
+        for dic in _as_list(js_obj["select"]):
+            val = dic["value"]
+            if isinstance(val, str):
+                if locate(val) != (gq, gc):
+                    raise Exception(f"{val} is not an aggregation function or the columns thats grouped on")
+                continue            # the key is output column 0 anyway
+            for agg_func, agg_val in FUNC_TO_FUT_EXT.items():
+                if agg_func in val:
+                    if val[agg_func] == "*":
+                        s_cols.append(ca)
+                    else:
+                        q, c = locate(val[agg_func])
+                        if q != name1:
+                            raise Exception("aggregates after a JOIN must be over columns of the first table")
+                        s_cols.append(c)
+                    ops.append(agg_val)
+        plan.update({"g_col": gc, "select": s_cols, "groupbys": ops})
+        return plan
+    cols1, cols2 = [], []
+    sel = js_obj["select"]
+    if sel == "*":
+        cols1, cols2 = list(range(len(schema[name1]))), list(range(len(schema[name2])))
+    else:
+        seen_second = False
+        for dic in _as_list(sel):
+            q, c = locate(dic["value"])
+            if q == name1 and not seen_second:
+                cols1.append(c)
+            elif q == name2:
+                seen_second = True
+                cols2.append(c)
+            else:
+                raise Exception("select list after a JOIN must list first-table columns before second-table columns")
+    plan.update({"select": cols1, "select2": cols2})
+    return plan

@@ -1,0 +1,69 @@
+"""End-to-end through HarkDB's public API (FutharkContext.create_table / sql) on the GPU (-m gpu)."""
+
+import json
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import np_oracle as NO
+from tests.gpu_util import need_gpu
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def fc():
+    need_gpu()
+    from harkdb_b200 import FutharkContext
+    ctx = FutharkContext()
+    d = json.load(open(os.path.join(GOLDEN, "data_csv.json")))
+    ctx.create_table("game_1", pd.DataFrame(d["rows"], columns=d["columns"]))
+    return ctx
+
+
+def test_readme_select(fc):
+    # README.md:42 / BASELINE config 1
+    out = fc.sql("select col1, col3 from game_1")
+    assert out.tolist() == [[6, 6], [0, 0], [0, 0], [0, 0], [0, 0], [6, 6], [1, 3]]
+
+
+def test_statements_the_reference_crashes_on(fc):
+    assert fc.sql("select col8 from game_1").tolist() == [[6], [0], [0], [0], [0], [6], [1]]
+    assert fc.sql("select * from game_1").shape == (7, 8)
+
+
+def test_csv_file_and_upload_per_query(tmp_path):
+    need_gpu()
+    from harkdb_b200 import FutharkContext
+    d = json.load(open(os.path.join(GOLDEN, "data_csv.json")))
+    p = tmp_path / "data.csv"
+    pd.DataFrame(d["rows"], columns=d["columns"]).to_csv(p, index=False)
+    ctx = FutharkContext(resident=False)       # the reference's behaviour: upload on every query
+    ctx.create_table("game_1", str(p))
+    assert ctx.sql("select col1, col3 from game_1").tolist() == [[6, 6], [0, 0], [0, 0], [0, 0], [0, 0], [6, 6], [1, 3]]
+    ctx.drop_table("game_1")
+    with pytest.raises(Exception, match="game_1 is not in tables"):
+        ctx.sql("select col1 from game_1")
+
+
+def test_where(fc):
+    out = fc.sql("select col1, col3 from game_1 where col2 > 0 and col5 < 6")
+    assert out.tolist() == [[1, 3]]
+    out = fc.sql("select col1 from game_1 where col2 >= 0.5")
+    assert out.tolist() == [[6], [6], [1]]
+    assert fc.sql("select col1 from game_1 where col1 > 100").shape == (0, 1)
+
+
+def test_where_float_table():
+    need_gpu()
+    from harkdb_b200 import FutharkContext
+    rng = np.random.default_rng(5)
+    a = rng.random((100000, 8)).astype(np.float32)
+    ctx = FutharkContext()
+    ctx.create_table("t", pd.DataFrame(a, columns=[f"col{i}" for i in range(1, 9)]))
+    out = ctx.sql("SELECT col1,col3 FROM t WHERE col2 > 0.5 AND col5 < 0.25")
+    m = (a[:, 1] > np.float32(0.5)) & (a[:, 4] < np.float32(0.25))
+    assert out.dtype == np.float32 and np.array_equal(out, a[m][:, [0, 2]])
