@@ -190,6 +190,8 @@ def run_gpu_arm(args):
     env = hark_ffi.Futhark(device=local_rank, stream=stream)
     if args.filter_ctas_per_sm:
         env.set_option("filter.ctas_per_sm", args.filter_ctas_per_sm)
+    if args.filter_impl:
+        env.set_option("filter.impl", args.filter_impl)
 
     rows = args.rows
     free_b, _ = torch.cuda.mem_get_info()
@@ -314,7 +316,7 @@ def run_gpu_arm(args):
                    "l2_policy": f"inputs larger than L2 ({rows * 16 / 1e9:.1f} GB read per step vs 126 MB L2)",
                    "parallelism": f"row-range shards x{world}, no collective"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "hk_filter_kernel<4,2,2>", "kernel_ms": k_ms,
+                     "traffic": None, "kernel": "hk_filter2_kernel<4,2,2>" if args.filter_impl in (0, 3) else "hk_filter_kernel<4,2,2>", "kernel_ms": k_ms,
                      "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                      "frac_of_nominal_8TBs": achieved / 8000.0,
                      "kernel_share_of_step": k_ms / (elapsed_ms / args.steps)},
@@ -353,6 +355,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--filter-ctas-per-sm", type=int, default=0)
+    ap.add_argument("--filter-impl", type=int, default=0, help="0 = v2 (default), 1 = v1 per-tile kernel, 3 = v2 runtime counts")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "hark" else args.warmup
     if args.impl == "reference":

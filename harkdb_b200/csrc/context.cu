@@ -19,7 +19,8 @@ static thread_local char g_init_err[512] = "";
 // context
 // ------------------------------------------------------------------------------------------
 int hark_ctx::dalloc(void **p, size_t bytes) {
-    if (bytes < 256) bytes = 256;
+    bytes = (bytes + 255) & ~(size_t)255; // padded: a 16-byte group load of a ragged column end stays in bounds
+    if (bytes == 0) bytes = 256;
     cudaError_t e = cudaMallocFromPoolAsync(p, bytes, pool, stream);
     if (e != cudaSuccess) {
         cudaGetLastError();

@@ -18,7 +18,7 @@ from typing import List, Optional, Sequence, Tuple, Union
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhark.so")
+LIB_PATH = os.environ.get("HARK_LIB") or os.path.join(_HERE, "libhark.so")   # HARK_LIB: kernel-variant experiments
 
 I32, U32, I64, F32, F64 = 0, 1, 2, 3, 4
 NP_DTYPES = {I32: np.dtype(np.int32), U32: np.dtype(np.uint32), I64: np.dtype(np.int64),
