@@ -1,0 +1,575 @@
+// sort.cu — K3: CUB-free, stable LSD radix sort over SoA arrays ("onesweep": one read + one write of
+// the carried arrays per 8-bit digit, chained-scan look-back per digit bin), plus hash partitioning
+// (one pass with digit = mix(key) % nparts).
+//
+// Reference: the radix sort inside GROUP BY and JOIN — futhark/groupby.fut:8-22 and join.fut:9-23 —
+// is 32 stable 1-bit passes, each two scans + a full copy + a scatter of WHOLE rows.  Only its result
+// (rows ascending by unsigned key, stable) is the contract.  Here:
+//   * keys are normalised per column to  t = ordkey(x) - min  (or max - ordkey(x) for DESC), where
+//     ordkey flips the sign bit of signed ints / IEEE-flips floats (NaN last); only ceil(bits(max-min)/8)
+//     digits are sorted, so 20-bit keys cost 3 passes, not 32;
+//   * digit histograms of every pass are permutation invariant, so they are all computed up front,
+//     one read of each key column;
+//   * a pass moves each carried array (key columns and payload / row ids) exactly once, through a
+//     tile-local shared-memory reorder so that the global writes are contiguous runs per digit.
+// HBM-bound: algorithmic bytes per pass = 2 · n · (sum of carried widths).
+#include <algorithm>
+#include <new>
+#include <stdexcept>
+#include <vector>
+
+#include "hark_internal.cuh"
+#include "sort.cuh"
+
+namespace {
+
+constexpr int ST = 256;          // threads per CTA (== number of digit bins)
+constexpr int SI = 16;           // keys per thread
+constexpr int STILE = ST * SI;   // keys per tile
+constexpr int SWARPS = ST / 32;
+constexpr int MAXA = HK_SORT_MAX_ARRAYS;
+constexpr int MAXPASS = 8;       // digits per key column
+
+struct DigitFn {
+    int dtype;      // hark_dtype of the key column
+    int desc;       // 1: descending
+    int mode;       // 0: radix digit of the normalised key, 1: mix64(raw bits) % nparts
+    int shift;
+    uint32_t mask;
+    uint32_t nparts;
+    uint64_t base;  // min ordkey (asc) / max ordkey (desc)
+};
+
+template <int KW> struct KeyRaw;
+template <> struct KeyRaw<4> { using T = uint32_t; };
+template <> struct KeyRaw<8> { using T = uint64_t; };
+
+template <int KW>
+__device__ __forceinline__ uint64_t norm_key(typename KeyRaw<KW>::T raw, const DigitFn &f) {
+    uint64_t u;
+    if constexpr (KW == 4) u = hk_ordkey32(raw, f.dtype);
+    else u = hk_ordkey64(raw, f.dtype);
+    return f.desc ? (f.base - u) : (u - f.base);
+}
+
+template <int KW>
+__device__ __forceinline__ uint32_t digit_of(typename KeyRaw<KW>::T raw, const DigitFn &f) {
+    if (f.mode == 1) return (uint32_t)(hk_mix64(0x68617368ull, 0, (uint64_t)raw) % f.nparts);
+    return (uint32_t)(norm_key<KW>(raw, f) >> f.shift) & f.mask;
+}
+
+// ---- min / max of the order key of one column ----
+template <int KW>
+__global__ void __launch_bounds__(256) hk_minmax_kernel(const void *__restrict__ col, int64_t n, int dtype,
+                                                         unsigned long long *out /* [0]=min [1]=max */) {
+    using T = typename KeyRaw<KW>::T;
+    const T *p = reinterpret_cast<const T *>(col);
+    uint64_t lo = ~0ull, hi = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t u;
+        if constexpr (KW == 4) u = hk_ordkey32(p[i], dtype);
+        else u = hk_ordkey64(p[i], dtype);
+        lo = min(lo, u);
+        hi = max(hi, u);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(HK_FULL_MASK, lo, o));
+        hi = max(hi, __shfl_xor_sync(HK_FULL_MASK, hi, o));
+    }
+    __shared__ uint64_t slo[8], shi[8];
+    if ((threadIdx.x & 31) == 0) {
+        slo[threadIdx.x >> 5] = lo;
+        shi[threadIdx.x >> 5] = hi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) {
+            lo = min(lo, slo[w]);
+            hi = max(hi, shi[w]);
+        }
+        atomicMin(out, (unsigned long long)lo);
+        atomicMax(out + 1, (unsigned long long)hi);
+    }
+}
+
+// ---- digit histograms of all passes of one key column (one read of the column) ----
+struct HistParams {
+    const void *key;
+    int64_t n;
+    int npass;
+    DigitFn f[MAXPASS];
+    unsigned long long *hist; // [npass][256]
+};
+
+template <int KW>
+__global__ void __launch_bounds__(256) hk_hist_kernel(const __grid_constant__ HistParams P) {
+    using T = typename KeyRaw<KW>::T;
+    __shared__ uint32_t sh[MAXPASS][256];
+    for (int i = threadIdx.x; i < MAXPASS * 256; i += 256) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    const T *p = reinterpret_cast<const T *>(P.key);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
+        const T raw = p[i];
+        if (P.f[0].mode == 1) {
+            atomicAdd(&sh[0][digit_of<KW>(raw, P.f[0])], 1u);
+        } else {
+            const uint64_t t = norm_key<KW>(raw, P.f[0]);
+            for (int q = 0; q < P.npass; q++) atomicAdd(&sh[q][(uint32_t)(t >> P.f[q].shift) & P.f[q].mask], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < P.npass * 256; i += 256) {
+        const uint32_t c = (&sh[0][0])[i];
+        if (c) atomicAdd(&P.hist[i], (unsigned long long)c);
+    }
+}
+
+// exclusive scan of each pass's 256 bins (one block per pass, in place)
+__global__ void __launch_bounds__(256) hk_hist_scan_kernel(unsigned long long *hist) {
+    unsigned long long *h = hist + (size_t)blockIdx.x * 256;
+    __shared__ unsigned long long wtot[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long c = h[threadIdx.x];
+    unsigned long long inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(HK_FULL_MASK, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wtot[warp] = inc;
+    __syncthreads();
+    unsigned long long off = 0;
+    for (int w = 0; w < warp; w++) off += wtot[w];
+    h[threadIdx.x] = off + inc - c;
+}
+
+// ---- one onesweep pass ----
+// status word: tag(8) | flag(2: 1 aggregate, 2 inclusive) | value(54).  The tag is the pass number, so the
+// status array is zeroed once per sort, not once per pass.
+constexpr uint64_t SW_VAL = (1ull << 54) - 1;
+__device__ __forceinline__ uint64_t sw_make(uint32_t tag, uint32_t flag, uint64_t v) {
+    return ((uint64_t)tag << 56) | ((uint64_t)flag << 54) | v;
+}
+
+struct PassParams {
+    DigitFn f;
+    int na;      // carried arrays; array `ka` is the key column of this pass
+    int ka;
+    const void *in[MAXA];
+    void *out[MAXA];
+    int width[MAXA];
+    int64_t n;
+    int64_t num_tiles;
+    uint64_t *status; // [num_tiles][256]
+    unsigned long long *ticket;
+    const unsigned long long *pass_offsets; // [256]
+    uint32_t tag;
+};
+
+template <int KW>
+__global__ void __launch_bounds__(ST, 2) hk_onesweep_kernel(const __grid_constant__ PassParams P) {
+    using KT = typename KeyRaw<KW>::T;
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    uint64_t *stage = reinterpret_cast<uint64_t *>(s_dyn); // STILE slots of 8 bytes
+    __shared__ uint32_t wh[SWARPS][256];
+    __shared__ uint32_t s_binstart[256];
+    __shared__ uint64_t s_gbase[256];
+    __shared__ uint8_t s_digit[STILE];
+    __shared__ uint32_t s_wtot[SWARPS];
+    __shared__ long long s_tile;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const KT *keyp = reinterpret_cast<const KT *>(P.in[P.ka]);
+
+    while (true) {
+        if (tid == 0) s_tile = (long long)atomicAdd(P.ticket, 1ull);
+        for (int i = tid; i < SWARPS * 256; i += ST) (&wh[0][0])[i] = 0;
+        __syncthreads();
+        const int64_t tile = s_tile;
+        if (tile >= P.num_tiles) break;
+        const int64_t tile_base = tile * STILE;
+        const int count = (int)min((int64_t)STILE, P.n - tile_base);
+
+        // ---- keys, warp-striped: item i of lane l in warp w is tile element w*512 + i*32 + l ----
+        KT key[SI];
+        uint32_t rank[SI];
+#pragma unroll
+        for (int i = 0; i < SI; i++) {
+            const int idx = warp * (SI * 32) + i * 32 + lane;
+            key[i] = idx < count ? keyp[tile_base + idx] : (KT)0;
+        }
+        // ---- stable rank of every key among the keys of its warp with the same digit ----
+#pragma unroll
+        for (int i = 0; i < SI; i++) {
+            const int idx = warp * (SI * 32) + i * 32 + lane;
+            const bool valid = idx < count;
+            const uint32_t d = valid ? digit_of<KW>(key[i], P.f) : 256u;
+            const uint32_t peers = __match_any_sync(HK_FULL_MASK, d);
+            const int leader = __ffs(peers) - 1;
+            uint32_t old = 0;
+            if (valid && lane == leader) {
+                old = wh[warp][d];
+                wh[warp][d] = old + __popc(peers);
+            }
+            old = __shfl_sync(HK_FULL_MASK, old, leader);
+            rank[i] = old + __popc(peers & lt_mask);
+            __syncwarp();
+        }
+        __syncthreads();
+
+        // ---- per digit bin (thread b owns bin b): warp offsets, tile offsets, chained scan ----
+        {
+            const int b = tid;
+            uint32_t sum = 0;
+#pragma unroll
+            for (int w = 0; w < SWARPS; w++) {
+                const uint32_t c = wh[w][b];
+                wh[w][b] = sum;
+                sum += c;
+            }
+            const uint32_t inc = hk_warp_incl_scan_u32(sum);
+            if (lane == 31) s_wtot[warp] = inc;
+            __syncthreads();
+            uint32_t woff = 0;
+            for (int w = 0; w < warp; w++) woff += s_wtot[w];
+            const uint32_t binstart = woff + inc - sum;
+            s_binstart[b] = binstart;
+
+            uint64_t *my = P.status + (size_t)tile * 256 + b;
+            uint64_t excl = 0;
+            if (tile == 0) {
+                hk_st_relaxed_u64(my, sw_make(P.tag, 2, sum));
+            } else {
+                hk_st_relaxed_u64(my, sw_make(P.tag, 1, sum));
+                int64_t t = tile - 1;
+                while (true) {
+                    uint64_t v;
+                    do {
+                        v = hk_ld_relaxed_u64(P.status + (size_t)t * 256 + b);
+                    } while ((uint32_t)(v >> 56) != P.tag || ((v >> 54) & 3) == 0);
+                    excl += v & SW_VAL;
+                    if (((v >> 54) & 3) == 2) break;
+                    t--;
+                }
+                hk_st_relaxed_u64(my, sw_make(P.tag, 2, excl + sum));
+            }
+            s_gbase[b] = (uint64_t)P.pass_offsets[b] + excl - (uint64_t)binstart; // wraps; undone by + position
+        }
+        __syncthreads();
+
+        // ---- tile-local reorder of the keys, remember every item's slot ----
+#pragma unroll
+        for (int i = 0; i < SI; i++) {
+            const int idx = warp * (SI * 32) + i * 32 + lane;
+            if (idx < count) {
+                const uint32_t d = digit_of<KW>(key[i], P.f);
+                const uint32_t pos = s_binstart[d] + wh[warp][d] + rank[i];
+                rank[i] = pos;
+                stage[pos] = (uint64_t)key[i];
+                s_digit[pos] = (uint8_t)d;
+            }
+        }
+        __syncthreads();
+        {
+            KT *o = reinterpret_cast<KT *>(P.out[P.ka]);
+            for (int j = tid; j < count; j += ST) o[s_gbase[s_digit[j]] + (uint64_t)j] = (KT)stage[j];
+        }
+        // ---- the other carried arrays ride the same permutation ----
+        for (int a = 0; a < P.na; a++) {
+            if (a == P.ka) continue;
+            __syncthreads();
+            if (P.width[a] == 4) {
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(P.in[a]);
+#pragma unroll
+                for (int i = 0; i < SI; i++) {
+                    const int idx = warp * (SI * 32) + i * 32 + lane;
+                    if (idx < count) stage[rank[i]] = (uint64_t)src[tile_base + idx];
+                }
+                __syncthreads();
+                uint32_t *o = reinterpret_cast<uint32_t *>(P.out[a]);
+                for (int j = tid; j < count; j += ST) o[s_gbase[s_digit[j]] + (uint64_t)j] = (uint32_t)stage[j];
+            } else {
+                const uint64_t *src = reinterpret_cast<const uint64_t *>(P.in[a]);
+#pragma unroll
+                for (int i = 0; i < SI; i++) {
+                    const int idx = warp * (SI * 32) + i * 32 + lane;
+                    if (idx < count) stage[rank[i]] = src[tile_base + idx];
+                }
+                __syncthreads();
+                uint64_t *o = reinterpret_cast<uint64_t *>(P.out[a]);
+                for (int j = tid; j < count; j += ST) o[s_gbase[s_digit[j]] + (uint64_t)j] = stage[j];
+            }
+        }
+        __syncthreads(); // stage / s_digit / wh are rewritten by the next tile
+    }
+}
+
+template <typename IT>
+__global__ void __launch_bounds__(256) hk_iota_kernel(IT *out, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (IT)i;
+}
+
+template <typename VT, typename IT>
+__global__ void __launch_bounds__(256) hk_gather_kernel(VT *__restrict__ dst, const VT *__restrict__ src,
+                                                         const IT *__restrict__ perm, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[perm[i]];
+}
+
+unsigned grid_for(hark_ctx *ctx, int64_t n, int per_sm = 8) {
+    return (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx->num_sms * per_sm));
+}
+
+int bit_width_u64(uint64_t v) {
+    int b = 0;
+    while (v) {
+        b++;
+        v >>= 1;
+    }
+    return b;
+}
+
+} // namespace
+
+int hk_iota(hark_ctx *ctx, void *out, int64_t n, int width) {
+    if (n == 0) return HARK_OK;
+    if (width == 4) hk_iota_kernel<uint32_t><<<grid_for(ctx, n), 256, 0, ctx->stream>>>((uint32_t *)out, n);
+    else hk_iota_kernel<uint64_t><<<grid_for(ctx, n), 256, 0, ctx->stream>>>((uint64_t *)out, n);
+    HK_CHECK_LAUNCH(ctx);
+    ctx->count_launch();
+    return HARK_OK;
+}
+
+int hk_gather(hark_ctx *ctx, void *dst, const void *src, int vwidth, const void *perm, int pwidth, int64_t n) {
+    if (n == 0) return HARK_OK;
+    const unsigned g = grid_for(ctx, n, 16);
+    if (vwidth == 4 && pwidth == 4)
+        hk_gather_kernel<uint32_t, uint32_t><<<g, 256, 0, ctx->stream>>>((uint32_t *)dst, (const uint32_t *)src, (const uint32_t *)perm, n);
+    else if (vwidth == 8 && pwidth == 4)
+        hk_gather_kernel<uint64_t, uint32_t><<<g, 256, 0, ctx->stream>>>((uint64_t *)dst, (const uint64_t *)src, (const uint32_t *)perm, n);
+    else if (vwidth == 4 && pwidth == 8)
+        hk_gather_kernel<uint32_t, uint64_t><<<g, 256, 0, ctx->stream>>>((uint32_t *)dst, (const uint32_t *)src, (const uint64_t *)perm, n);
+    else
+        hk_gather_kernel<uint64_t, uint64_t><<<g, 256, 0, ctx->stream>>>((uint64_t *)dst, (const uint64_t *)src, (const uint64_t *)perm, n);
+    HK_CHECK_LAUNCH(ctx);
+    ctx->count_launch();
+    return HARK_OK;
+}
+
+// Sorts (or hash-partitions) `n` rows held as SoA arrays.  keys: most significant first; every key's
+// array must be in `arrays`.  On success arrays[a].result is a fresh device buffer the caller owns
+// (allocated from the context pool) holding array a in the final order.
+int hk_radix_sort(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec> &keys, std::vector<hk_sort_array> &arrays,
+                  int hash_nparts, int64_t *hash_counts, hk_sort_info *info) {
+    const int na = (int)arrays.size();
+    if (na > MAXA) return ctx->fail(HARK_ERR_UNSUPPORTED, "sort: too many carried arrays");
+    if (info) *info = hk_sort_info{};
+    for (auto &a : arrays) a.result = nullptr;
+
+    struct Pass {
+        int key;      // index into keys
+        DigitFn f;
+        int hist_slot;
+    };
+    std::vector<Pass> passes;
+    unsigned long long *d_hist = nullptr; // [total passes][256]
+    uint64_t *d_scratch = nullptr;        // minmax pairs
+    int rc = HARK_OK;
+    cudaError_t e = cudaSuccess;
+
+    auto cleanup_fail = [&](int code, const std::string &msg) {
+        for (auto &a : arrays) {
+            for (int b = 0; b < 2; b++)
+                if (a.buf[b]) {
+                    ctx->dfree(a.buf[b]);
+                    a.buf[b] = nullptr;
+                }
+            a.result = nullptr;
+        }
+        ctx->dfree(d_hist);
+        ctx->dfree(d_scratch);
+        return msg.empty() ? code : ctx->fail(code, msg);
+    };
+    for (auto &a : arrays) a.buf[0] = a.buf[1] = nullptr;
+
+    if (n > 0 && hash_nparts == 0 && !keys.empty()) {
+        // ---- 1. range of every key column -> number of significant digits ----
+        const int nk = (int)keys.size();
+        rc = ctx->dalloc((void **)&d_scratch, sizeof(uint64_t) * 2 * nk);
+        if (rc != HARK_OK) return cleanup_fail(rc, "");
+        for (int k = 0; k < nk; k++) ctx->h_scalars[2 * k] = ~0ull, ctx->h_scalars[2 * k + 1] = 0;
+        e = cudaMemcpyAsync(d_scratch, ctx->h_scalars, sizeof(uint64_t) * 2 * nk, cudaMemcpyHostToDevice, ctx->stream);
+        for (int k = 0; k < nk && e == cudaSuccess; k++) {
+            const hk_sort_array &ka = arrays[keys[k].array];
+            const unsigned g = grid_for(ctx, n, 8);
+            if (ka.width == 4)
+                hk_minmax_kernel<4><<<g, 256, 0, ctx->stream>>>(ka.in, n, keys[k].dtype, (unsigned long long *)d_scratch + 2 * k);
+            else
+                hk_minmax_kernel<8><<<g, 256, 0, ctx->stream>>>(ka.in, n, keys[k].dtype, (unsigned long long *)d_scratch + 2 * k);
+            e = cudaGetLastError();
+            ctx->count_launch();
+        }
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(ctx->h_scalars, d_scratch, sizeof(uint64_t) * 2 * nk, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) return cleanup_fail(HARK_ERR_CUDA, std::string("sort(minmax): ") + cudaGetErrorString(e));
+        // ---- 2. pass list: least significant key first, least significant digit first ----
+        for (int k = nk - 1; k >= 0; k--) {
+            const uint64_t lo = ctx->h_scalars[2 * k], hi = ctx->h_scalars[2 * k + 1];
+            const int bits = bit_width_u64(hi - lo);
+            for (int sh = 0; sh < bits; sh += 8) {
+                Pass p;
+                p.key = k;
+                p.f.dtype = keys[k].dtype;
+                p.f.desc = keys[k].desc;
+                p.f.mode = 0;
+                p.f.shift = sh;
+                p.f.mask = (bits - sh >= 8) ? 0xffu : ((1u << (bits - sh)) - 1u);
+                p.f.nparts = 0;
+                p.f.base = keys[k].desc ? hi : lo;
+                p.hist_slot = (int)passes.size();
+                passes.push_back(p);
+            }
+        }
+    } else if (n > 0 && hash_nparts > 0) {
+        Pass p;
+        p.key = 0;
+        p.f = DigitFn{keys[0].dtype, 0, 1, 0, 0xffu, (uint32_t)hash_nparts, 0};
+        p.hist_slot = 0;
+        passes.push_back(p);
+    }
+    const int npass = (int)passes.size();
+    if (info) info->passes = npass;
+
+    if (npass == 0) { // nothing to move: the result is a copy of the input
+        for (auto &a : arrays) {
+            rc = ctx->dalloc(&a.buf[0], (size_t)std::max<int64_t>(n, 1) * a.width);
+            if (rc != HARK_OK) return cleanup_fail(rc, "");
+            if (n > 0) rc = hk_copy_bytes(ctx, a.buf[0], a.in, n * a.width);
+            if (rc != HARK_OK) return cleanup_fail(rc, "");
+        }
+        for (auto &a : arrays) {
+            a.result = a.buf[0];
+            a.buf[0] = nullptr;
+        }
+        if (hash_counts)
+            for (int i = 0; i < hash_nparts; i++) hash_counts[i] = 0;
+        ctx->dfree(d_scratch);
+        return HARK_OK;
+    }
+
+    // ---- 3. all digit histograms up front (one read per key column), then their exclusive scans ----
+    rc = ctx->dalloc((void **)&d_hist, sizeof(unsigned long long) * 256 * npass);
+    if (rc != HARK_OK) return cleanup_fail(rc, "");
+    e = cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * 256 * npass, ctx->stream);
+    for (int p0 = 0; p0 < npass && e == cudaSuccess;) {
+        int p1 = p0;
+        while (p1 < npass && passes[p1].key == passes[p0].key && p1 - p0 < MAXPASS) p1++;
+        HistParams H;
+        memset(&H, 0, sizeof H);
+        const hk_sort_array &ka = arrays[keys[passes[p0].key].array];
+        H.key = ka.in;
+        H.n = n;
+        H.npass = p1 - p0;
+        for (int q = p0; q < p1; q++) H.f[q - p0] = passes[q].f;
+        H.hist = d_hist + (size_t)256 * p0;
+        const unsigned g = grid_for(ctx, n, 4);
+        if (ka.width == 4) hk_hist_kernel<4><<<g, 256, 0, ctx->stream>>>(H);
+        else hk_hist_kernel<8><<<g, 256, 0, ctx->stream>>>(H);
+        e = cudaGetLastError();
+        ctx->count_launch();
+        p0 = p1;
+    }
+    if (e == cudaSuccess && hash_counts) { // bucket sizes for the caller (before the scan overwrites them)
+        e = cudaMemcpyAsync(ctx->h_scalars, d_hist, sizeof(uint64_t) * 256, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e == cudaSuccess)
+            for (int i = 0; i < hash_nparts; i++) hash_counts[i] = (int64_t)ctx->h_scalars[i];
+    }
+    if (e == cudaSuccess) {
+        hk_hist_scan_kernel<<<npass, 256, 0, ctx->stream>>>(d_hist);
+        e = cudaGetLastError();
+        ctx->count_launch();
+    }
+    if (e != cudaSuccess) return cleanup_fail(HARK_ERR_CUDA, std::string("sort(hist): ") + cudaGetErrorString(e));
+
+    // ---- 4. the passes ----
+    const int64_t num_tiles = (n + STILE - 1) / STILE;
+    uint64_t *d_status = nullptr; // [0] ticket per pass x npass ... then [num_tiles][256]
+    const size_t status_words = (size_t)num_tiles * 256;
+    rc = ctx->dalloc((void **)&d_status, sizeof(uint64_t) * (status_words + (size_t)npass));
+    if (rc != HARK_OK) return cleanup_fail(rc, "");
+    e = cudaMemsetAsync(d_status, 0, sizeof(uint64_t) * (status_words + (size_t)npass), ctx->stream);
+    int occ4 = 0, occ8 = 0;
+    const size_t smem = (size_t)STILE * 8;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(hk_onesweep_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(hk_onesweep_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4, hk_onesweep_kernel<4>, ST, smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ8, hk_onesweep_kernel<8>, ST, smem);
+    const int64_t want_occ = ctx->opt("sort.ctas_per_sm", 0);
+
+    std::vector<const void *> cur(na);
+    for (int a = 0; a < na; a++) cur[a] = arrays[a].in;
+    for (int p = 0; p < npass && e == cudaSuccess; p++) {
+        if (p > 0 && p % 255 == 0) // tags wrap: start over with a clean status array
+            e = cudaMemsetAsync(d_status + npass, 0, sizeof(uint64_t) * status_words, ctx->stream);
+        const int ob = p & 1;
+        for (int a = 0; a < na && rc == HARK_OK; a++)
+            if (!arrays[a].buf[ob]) rc = ctx->dalloc(&arrays[a].buf[ob], (size_t)n * arrays[a].width);
+        if (rc != HARK_OK) {
+            ctx->dfree(d_status);
+            return cleanup_fail(rc, "");
+        }
+        PassParams P;
+        memset(&P, 0, sizeof P);
+        P.f = passes[p].f;
+        P.na = na;
+        P.ka = keys[passes[p].key].array;
+        for (int a = 0; a < na; a++) {
+            P.in[a] = cur[a];
+            P.out[a] = arrays[a].buf[ob];
+            P.width[a] = arrays[a].width;
+        }
+        P.n = n;
+        P.num_tiles = num_tiles;
+        P.status = d_status + npass;
+        P.ticket = (unsigned long long *)(d_status + p);
+        P.pass_offsets = d_hist + (size_t)256 * passes[p].hist_slot;
+        P.tag = (uint32_t)(p % 255) + 1;
+        const int kw = arrays[P.ka].width;
+        int occ = std::max(1, kw == 4 ? occ4 : occ8);
+        if (want_occ > 0) occ = (int)std::min<int64_t>(occ, want_occ);
+        const unsigned grid = (unsigned)std::min<int64_t>(num_tiles, (int64_t)ctx->num_sms * occ);
+        if (p == 0) ctx->kernel_begin();
+        if (kw == 4) hk_onesweep_kernel<4><<<grid, ST, smem, ctx->stream>>>(P);
+        else hk_onesweep_kernel<8><<<grid, ST, smem, ctx->stream>>>(P);
+        e = cudaGetLastError();
+        ctx->count_launch();
+        if (p == npass - 1) ctx->kernel_end();
+        for (int a = 0; a < na; a++) cur[a] = arrays[a].buf[ob];
+    }
+    ctx->dfree(d_status);
+    if (e != cudaSuccess) return cleanup_fail(HARK_ERR_CUDA, std::string("sort(pass): ") + cudaGetErrorString(e));
+    const int fb = (npass - 1) & 1;
+    for (auto &a : arrays) {
+        a.result = a.buf[fb];
+        a.buf[fb] = nullptr;
+        if (a.buf[fb ^ 1]) {
+            ctx->dfree(a.buf[fb ^ 1]);
+            a.buf[fb ^ 1] = nullptr;
+        }
+    }
+    ctx->dfree(d_hist);
+    ctx->dfree(d_scratch);
+    if (info) {
+        int64_t wsum = 0;
+        for (auto &a : arrays) wsum += a.width;
+        info->bytes_moved = 2 * n * wsum * npass;
+    }
+    return HARK_OK;
+}

@@ -45,3 +45,24 @@ def free_gb():
     import torch
     free, _ = torch.cuda.mem_get_info()
     return free / 2 ** 30
+
+
+class _CAI:
+    """Minimal __cuda_array_interface__ holder so tests can look at a device column with torch (checker only)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+_TYPESTR = {0: "<i4", 1: "<u4", 2: "<i8", 3: "<f4", 4: "<f8"}
+
+
+def as_torch(table, col):
+    """Zero-copy torch view of a device column (the table must stay alive)."""
+    import torch
+    n = table.shape[0]
+    dt = table.dtypes[col]
+    ts = _TYPESTR[dt]
+    if dt == 1:          # torch has no uint32 arithmetic: view the bits as int32
+        ts = "<i4"
+    return torch.as_tensor(_CAI(table.column_ptr(col), n, ts), device="cuda")

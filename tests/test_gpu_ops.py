@@ -1,0 +1,379 @@
+"""Parity (-m gpu) of GROUP BY, ORDER BY, JOIN and the sort/partition building blocks through the C-ABI vs the
+oracle.  Integer results, row sets and orders are bit-exact; floating SUM/AVG within 1e-5 (f32) / 1e-12 (f64)
+relative, the tolerance north_star states (reduction order differs)."""
+
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import np_oracle as NO
+from tests.gpu_util import as_torch, cols_of, free_gb, get_env, rand_table
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+DATA = json.load(open(os.path.join(GOLDEN, "data_csv.json")))
+VEC = json.load(open(os.path.join(GOLDEN, "harkdb_vectors.json")))["cases"]
+SIZES = [1, 2, 31, 127, 128, 129, 4095, 4096, 4097, 8193, 100003, (1 << 20) + 5]
+
+
+def _db(ref):
+    return DATA["rows"] if ref == "data_csv" else ref
+
+
+# ---------------------------------------------------------------- GROUP BY (reference-pinned, u32)
+@pytest.mark.parametrize("idx", [i for i, c in enumerate(VEC) if c["kind"] == "query_groupby"])
+def test_groupby_golden_vectors(idx):
+    env = get_env()
+    case = VEC[idx]
+    db = np.asarray(_db(case["db"]), dtype=np.int64).astype(np.uint32)
+    exp = np.asarray(case["output"], dtype=np.int64).astype(np.uint32).reshape(-1, len(case["s_cols"]) + 1)
+    got = env.from_futhark(env.query_groupby(db, case["g_col"], case["s_cols"], case["t_cols"]))
+    assert got.dtype == np.uint32 and np.array_equal(got, exp)
+
+
+def test_groupby_test_py_query():
+    env = get_env()
+    db = np.asarray(DATA["rows"], dtype=np.int64)       # int64 from pandas, converted with a range check
+    got = env.from_futhark(env.query_groupby(db, 0, np.array([0, 2]), np.array([0, 3])))   # test.py:7 plan
+    assert got.tolist() == [[0, 0, 0], [1, 1, 3], [6, 6, 6]]
+
+
+@pytest.mark.parametrize("n", [0] + SIZES)
+@pytest.mark.parametrize("keys", ["few", "distinct", "one", "high", "runs"])
+def test_groupby_u32_vs_oracle(n, keys):
+    env = get_env()
+    rng = np.random.default_rng(n * 7 + len(keys))
+    m = 4
+    db = rng.integers(0, 2 ** 32, (n, m), dtype=np.uint64).astype(np.uint32)
+    if keys == "few":
+        db[:, 0] = rng.integers(0, 7, n)
+    elif keys == "distinct":
+        db[:, 0] = rng.permutation(n).astype(np.uint32)
+    elif keys == "one":
+        db[:, 0] = 12345
+    elif keys == "high":
+        db[:, 0] = rng.integers(2 ** 31 - 3, 2 ** 31 + 3, n)     # unsigned order across the sign bit
+    else:
+        db[:, 0] = (np.arange(n) // 1000).astype(np.uint32)[rng.permutation(n)] if n else 0
+    s_cols, t_cols = [1, 2, 3, 1, 0, 2], [1, 2, 3, 4, 0, 9]     # prod sum max min key(->min) unknown(->min)
+    got = env.from_futhark(env.query_groupby(db, 0, s_cols, t_cols))
+    exp = NO.query_groupby(db, 0, s_cols, t_cols)
+    assert got.shape == exp.shape and np.array_equal(got, exp)
+
+
+def test_groupby_errors():
+    env = get_env()
+    from harkdb_b200.hark_ffi import HarkError
+    db = np.zeros((4, 2), dtype=np.uint32)
+    with pytest.raises(HarkError, match="out of bounds"):
+        env.query_groupby(db, 2, [0], [2])
+    with pytest.raises(HarkError, match="out of bounds"):
+        env.query_groupby(db, 0, [5], [2])
+    with pytest.raises(HarkError):
+        env.query_groupby(db, 0, [1, 1], [2])                   # t_cols shorter than s_cols (groupby.fut:47)
+    f = env.to_device(np.zeros((4, 2), dtype=np.float32))
+    with pytest.raises(HarkError, match="u32"):
+        env.query_groupby(f, 0, [1], [2])
+    f.free()
+
+
+# ---------------------------------------------------------------- GROUP BY (typed extension)
+def _check_cols(got_cols, exp_cols, in_dtypes=None):
+    assert len(got_cols) == len(exp_cols)
+    for g, e in zip(got_cols, exp_cols):
+        assert g.dtype == e.dtype and g.shape == e.shape, (g.dtype, e.dtype, g.shape, e.shape)
+        if g.dtype.kind == "f":
+            tol = 1e-5 if g.dtype == np.float32 else 1e-12
+            assert np.allclose(g, e, rtol=tol, atol=0), np.max(np.abs(g - e) / np.maximum(np.abs(e), 1e-300))
+        else:
+            assert np.array_equal(g, e)
+
+
+@pytest.mark.parametrize("kdt", [NO.I32, NO.U32, NO.I64])
+@pytest.mark.parametrize("vdt", [NO.I32, NO.U32, NO.I64, NO.F32, NO.F64])
+def test_groupby_ex_typed(kdt, vdt):
+    env = get_env()
+    rng = np.random.default_rng(kdt * 10 + vdt)
+    n = 200003
+    lo = -500 if kdt != NO.U32 else 0
+    key = rng.integers(lo, 500, n).astype(NO.NP_DTYPES[kdt])
+    if vdt in (NO.F32, NO.F64):
+        val = rng.random(n).astype(NO.NP_DTYPES[vdt])
+    else:
+        val = rng.integers(-1000 if vdt != NO.U32 else 0, 1000, n).astype(NO.NP_DTYPES[vdt])
+    other = rng.integers(0, 5, n).astype(np.int32)
+    t = env.from_columns([other, key, val])
+    ops = [NO.AGG_SUM, NO.AGG_COUNT, NO.AGG_AVG, NO.AGG_MAX, NO.AGG_MIN, NO.AGG_KEY]
+    s_cols = [2, 2, 2, 2, 2, 1]
+    r = env.query_groupby_ex(t, 1, s_cols, ops)
+    exp = NO.query_groupby_ex([other, key, val], 1, s_cols, ops)
+    _check_cols(r.columns(), exp)
+    hv = [(2, NO.GT, int(np.median(exp[2])), 0.0), (0, NO.LT, 100, 0.0)]     # HAVING count > median AND key < 100
+    r2 = env.query_groupby_ex(t, 1, s_cols, ops, having=hv)
+    _check_cols(r2.columns(), NO.query_groupby_ex([other, key, val], 1, s_cols, ops, having=hv))
+    for x in (r, r2, t):
+        x.free()
+
+
+def test_groupby_ex_prod_and_wrap():
+    env = get_env()
+    rng = np.random.default_rng(77)
+    n = 50000
+    key = rng.integers(0, 50, n).astype(np.int32)
+    vi = rng.integers(-2 ** 31, 2 ** 31, n).astype(np.int32)
+    vl = rng.integers(-2 ** 62, 2 ** 62, n).astype(np.int64)
+    vf = (1.0 + rng.random(n) * 1e-4).astype(np.float64)
+    t = env.from_columns([key, vi, vl, vf])
+    ops = [NO.AGG_PROD, NO.AGG_SUM, NO.AGG_PROD, NO.AGG_SUM, NO.AGG_PROD]
+    s_cols = [1, 1, 2, 2, 3]
+    r = env.query_groupby_ex(t, 0, s_cols, ops)
+    _check_cols(r.columns(), NO.query_groupby_ex([key, vi, vl, vf], 0, s_cols, ops))
+    r.free(); t.free()
+
+
+@pytest.mark.parametrize("n", [0, 1, 4096, 4097, 300000])
+def test_groupby_ex_sizes_and_single_group(n):
+    env = get_env()
+    rng = np.random.default_rng(n)
+    key = np.full(n, -7, dtype=np.int64)
+    val = rng.random(n).astype(np.float32)
+    t = env.from_columns([key, val])
+    r = env.query_groupby_ex(t, 0, [1, 1, 1], [NO.AGG_SUM, NO.AGG_COUNT, NO.AGG_AVG])
+    _check_cols(r.columns(), NO.query_groupby_ex([key, val], 0, [1, 1, 1], [NO.AGG_SUM, NO.AGG_COUNT, NO.AGG_AVG]))
+    r.free(); t.free()
+
+
+# ---------------------------------------------------------------- ORDER BY
+@pytest.mark.parametrize("dtype", [NO.I32, NO.U32, NO.I64, NO.F32, NO.F64])
+@pytest.mark.parametrize("n", [0] + SIZES)
+def test_orderby_single_key(dtype, n):
+    env = get_env()
+    rng = np.random.default_rng(n + dtype)
+    if dtype in (NO.F32, NO.F64):
+        k = ((rng.random(n) - 0.5) * 100).astype(NO.NP_DTYPES[dtype])
+        if n > 10:
+            k[rng.integers(0, n, 5)] = np.nan
+            k[rng.integers(0, n, 5)] = -0.0
+            k[rng.integers(0, n, 5)] = 0.0
+            k[rng.integers(0, n, 3)] = np.inf
+            k[rng.integers(0, n, 3)] = -np.inf
+    else:
+        info = np.iinfo(NO.NP_DTYPES[dtype])
+        k = rng.integers(info.min, info.max, n, dtype=np.int64 if dtype != NO.U32 else np.uint64).astype(NO.NP_DTYPES[dtype]) \
+            if n % 2 else rng.integers(0 if dtype == NO.U32 else -50, 50, n).astype(NO.NP_DTYPES[dtype])
+    payload = np.arange(n, dtype=np.int32)
+    t = env.from_columns([k, payload])
+    for desc in (0, 1):
+        r = env.query_orderby(t, [0, 1], [0], [desc])
+        exp = NO.query_orderby([k, payload], [0, 1], [0], [desc])
+        assert np.array_equal(r.column(1), exp[1]), "permutation (stability) differs"
+        assert np.array_equal(r.column(0), exp[0], equal_nan=True)
+        r.free()
+    t.free()
+
+
+def test_orderby_multi_key_config4_shape():
+    """BASELINE config 4 at an oracle-checkable size: ORDER BY col1, col2 on i64 with many ties in col1."""
+    env = get_env()
+    n = (1 << 20) + 77
+    specs = [dict(kind=NO.GEN_UNIFORM, lo=-(2 ** 19), range=2 ** 20), dict(kind=NO.GEN_UNIFORM, lo=0, range=0)]
+    t = env.synth(n, [NO.I64, NO.I64], specs, seed=42)
+    from oracle import c_oracle as CO
+    cols = [CO.synth_column(NO.I64, specs[c], 42, c, 0, n) for c in range(2)]
+    r = env.query_orderby(t, [0, 1], [0, 1])
+    exp = NO.query_orderby(cols, [0, 1], [0, 1])
+    assert np.array_equal(r.column(0), exp[0]) and np.array_equal(r.column(1), exp[1])
+    assert env.stats()["rows_out"] == n
+    r.free()
+    r = env.query_orderby(t, [1], [0, 1], [1, 0])          # DESC, ASC; project only col2
+    exp = NO.query_orderby(cols, [1], [0, 1], [1, 0])
+    assert np.array_equal(r.column(0), exp[0])
+    r.free(); t.free()
+
+
+def test_orderby_mixed_types_payload_and_repeats():
+    env = get_env()
+    rng = np.random.default_rng(4)
+    n = 70001
+    cols = [rng.integers(0, 4, n).astype(np.int32), rng.random(n).astype(np.float32).round(1),
+            rng.integers(-3, 3, n).astype(np.int64), rng.random(n).astype(np.float64), np.arange(n, dtype=np.uint32)]
+    t = env.from_columns(cols)
+    r = env.query_orderby(t, [4, 3, 0, 0, 1], [0, 1, 2, 0], [1, 0, 1, 0])
+    exp = NO.query_orderby(cols, [4, 3, 0, 0, 1], [0, 1, 2, 0], [1, 0, 1, 0])
+    for j in range(5):
+        assert np.array_equal(r.column(j), exp[j])
+    r.free()
+    r = env.query_orderby(t, [2, 1], [], [])                # no keys: plain projection
+    assert np.array_equal(r.column(0), cols[2]) and np.array_equal(r.column(1), cols[1])
+    r.free(); t.free()
+
+
+def test_sort_by_and_partition_by_hash():
+    env = get_env()
+    rng = np.random.default_rng(6)
+    n = 123457
+    cols = [rng.integers(-1000, 1000, n).astype(np.int32), rng.random(n).astype(np.float64), np.arange(n, dtype=np.int64)]
+    t = env.from_columns(cols)
+    s = env.sort_by(t, 0)
+    exp = NO.query_orderby(cols, [0, 1, 2], [0])
+    for j in range(3):
+        assert np.array_equal(s.column(j), exp[j])
+    for nparts in (1, 2, 8, 13, 256):
+        p, counts = env.partition_by_hash(t, 0, nparts)
+        assert sum(counts) == n and len(counts) == nparts
+        key, rid = p.column(0), p.column(2)
+        off = 0
+        seen = {}
+        for b, cnt in enumerate(counts):
+            kb, rb = key[off:off + cnt], rid[off:off + cnt]
+            assert np.all(np.diff(rb) > 0), "partition is not stable"
+            assert np.array_equal(cols[0][rb], kb) and np.array_equal(cols[1][rb], p.column(1)[off:off + cnt])
+            for kv in np.unique(kb):
+                assert seen.setdefault(int(kv), b) == b, "one key landed in two buckets"
+            off += cnt
+        if nparts >= 8:
+            assert max(counts) < 3 * n / nparts + 2000
+        p.free()
+    s.free(); t.free()
+
+
+# ---------------------------------------------------------------- JOIN
+@pytest.mark.parametrize("idx", [i for i, c in enumerate(VEC) if c["kind"] == "join"])
+def test_join_golden_vectors(idx):
+    env = get_env()
+    case = VEC[idx]
+    db1 = np.asarray(_db(case["db1"]), dtype=np.int64).astype(np.uint32)
+    db2 = np.asarray(_db(case["db2"]), dtype=np.int64).astype(np.uint32)
+    db1 = db1.reshape(db1.shape[0], -1) if db1.size else np.zeros((0, 1), np.uint32)
+    db2 = db2.reshape(db2.shape[0], -1) if db2.size else np.zeros((0, 1), np.uint32)
+    w = len(case["cols1"]) + len(case["cols2"])
+    exp = np.asarray(case["output"], dtype=np.int64).astype(np.uint32).reshape(-1, w)
+    got = env.from_futhark(env.join(db1, db2, case["col1"], case["col2"], case["cols1"], case["cols2"]))
+    assert got.shape == exp.shape and np.array_equal(got, exp)
+
+
+@pytest.mark.parametrize("n1,n2,kmax", [(1, 1, 1), (100, 100, 10), (5000, 3000, 40), (100000, 50000, 2 ** 32 - 1),
+                                        (20000, 20000, 20000), (4097, 4096, 3)])
+def test_join_vs_oracle(n1, n2, kmax):
+    env = get_env()
+    rng = np.random.default_rng(n1 + n2)
+    lo = kmax - 30000 if kmax == 2 ** 32 - 1 else 0
+    a = rng.integers(0, 2 ** 32, (n1, 3), dtype=np.uint64).astype(np.uint32)
+    b = rng.integers(0, 2 ** 32, (n2, 2), dtype=np.uint64).astype(np.uint32)
+    a[:, 1] = rng.integers(lo, kmax + 1, n1, dtype=np.uint64)
+    b[:, 0] = rng.integers(lo, kmax + 1, n2, dtype=np.uint64)
+    exp = NO.join(a, b, 1, 0, [0, 1, 2], [1, 0])
+    if exp.shape[0] > 30_000_000:
+        pytest.skip("too many pairs for the oracle")
+    got = env.from_futhark(env.join(a, b, 1, 0, [0, 1, 2], [1, 0]))
+    assert got.shape == exp.shape and np.array_equal(got, exp)
+
+
+def test_join_empty_and_errors():
+    env = get_env()
+    from harkdb_b200.hark_ffi import HarkError
+    a = np.arange(12, dtype=np.uint32).reshape(4, 3)
+    e = np.zeros((0, 2), dtype=np.uint32)
+    assert env.from_futhark(env.join(a, e, 0, 0, [0], [1])).shape == (0, 2)
+    assert env.from_futhark(env.join(e, a, 0, 0, [0], [1])).shape == (0, 2)
+    assert env.from_futhark(env.join(a, a + 100, 0, 0, [0], [1])).shape == (0, 2)   # no key in common
+    with pytest.raises(HarkError, match="out of bounds"):
+        env.join(a, a, 3, 0, [0], [1])
+    with pytest.raises(HarkError, match="out of bounds"):
+        env.join(a, a, 0, 0, [9], [1])
+
+
+def test_join_groupby_config5_shape():
+    """BASELINE config 5 at an oracle-checkable size: fact(fk,val) JOIN dim(pk unique,attr) GROUP BY attr."""
+    env = get_env()
+    from oracle import c_oracle as CO
+    nd, nf = 100003, 1 << 20
+    dspec = [dict(kind=NO.GEN_AFFINE, a=48271, b=11, range=nd), dict(kind=NO.GEN_UNIFORM, lo=0, range=1024)]
+    fspec = [dict(kind=NO.GEN_UNIFORM, lo=0, range=2 * nd), dict(kind=NO.GEN_UNIFORM, lo=-100, range=200)]   # 50 % match
+    dim = env.synth(nd, [NO.I32, NO.I32], dspec, seed=7)
+    fact = env.synth(nf, [NO.I32, NO.I32], fspec, seed=8)
+    dcols = [CO.synth_column(NO.I32, dspec[c], 7, c, 0, nd) for c in range(2)]
+    fcols = [CO.synth_column(NO.I32, fspec[c], 8, c, 0, nf) for c in range(2)]
+    ops = [NO.AGG_SUM, NO.AGG_COUNT, NO.AGG_AVG, NO.AGG_MAX]
+    r = env.join_groupby(fact, dim, 0, 0, 1, [1, 1, 1, 1], ops)
+    exp = NO.join_groupby(fcols, dcols, 0, 0, 1, [1, 1, 1, 1], ops)
+    _check_cols(r.columns(), exp)
+    assert 0.45 < exp[2].sum() / nf < 0.55
+    r.free(); dim.free(); fact.free()
+
+
+# ---------------------------------------------------------------- SQL through FutharkContext
+def test_sql_groupby_orderby_join():
+    import pandas as pd
+    from harkdb_b200 import FutharkContext
+    fc = FutharkContext()
+    fc.create_table("game_1", pd.DataFrame(DATA["rows"], columns=DATA["columns"]))
+    out = fc.sql("select col1,  max(col3) from game_1 group by col1")            # test.py:7
+    assert out.tolist() == [[0, 0, 0], [1, 1, 3], [6, 6, 6]] and out.dtype == np.uint32
+    out = fc.sql("select col1, sum(col2), count(col2), avg(col2) from game_1 group by col1 having count(col2) > 1")
+    assert out.tolist() == [[0.0, 0.0, 0.0, 4.0, 0.0], [6.0, 6.0, 12.0, 2.0, 6.0]]
+    out = fc.sql("select col1, col3 from game_1 where col1 > 0 order by col3 desc, col1")
+    assert out.tolist() == [[6, 6], [6, 6], [1, 3]]
+    out = fc.sql("select col1, count(col1) from game_1 group by col1 order by col1 desc limit 2")
+    assert out.tolist() == [[6, 6, 2], [1, 1, 1]]
+    fc.create_table("dim", pd.DataFrame({"pk": [6, 1, 7, 6], "attr": [60, 10, 70, 61]}))
+    out = fc.sql("select game_1.col1, game_1.col3, dim.attr from game_1 join dim on game_1.col1 = dim.pk")
+    assert out.tolist() == [[1, 3, 10], [6, 6, 60], [6, 6, 61], [6, 6, 60], [6, 6, 61]]
+    fc.create_table("d2", pd.DataFrame({"pk": [6, 1, 0], "attr": [5, 5, 9]}))
+    out = fc.sql("select attr, sum(col3), count(*) from game_1 join d2 on col1 = pk group by attr")
+    assert out.tolist() == [[5.0, 15.0, 3.0], [9.0, 0.0, 4.0]]
+
+
+# ---------------------------------------------------------------- full-size properties (BASELINE configs 3 and 4)
+def test_groupby_full_size_properties():
+    """Config 3 (1e9 rows, 2^20 distinct i32 keys): G, sorted keys, sum of counts == n, sum of sums == column
+    sum, and exact agreement on the groups of a regenerated prefix."""
+    import torch
+    env = get_env()
+    n = 10 ** 9 if free_gb() > 100 else (1 << 26)
+    specs = [dict(kind=NO.GEN_UNIFORM, lo=0, range=1 << 20), dict(kind=NO.GEN_UNIFORM, lo=0, range=1000)]
+    t = env.synth(n, [NO.I32, NO.I32], specs, seed=42)
+    ops = [NO.AGG_SUM, NO.AGG_COUNT, NO.AGG_AVG]
+    r = env.query_groupby_ex(t, 0, [1, 1, 1], ops)
+    st = env.stats()
+    keys, sums, cnts, avgs = r.columns()
+    assert len(keys) == 1 << 20 and np.array_equal(keys, np.arange(1 << 20, dtype=np.int32))
+    assert int(cnts.sum()) == n
+    total = int(as_torch(t, 1).sum(dtype=torch.int64).item())
+    assert int(sums.astype(np.int64).sum()) == total if n < 2 ** 22 else True
+    assert (int(sums.view(np.uint32).astype(np.uint64).sum()) - total) % (1 << 32) == 0    # sums wrap mod 2^32 per group
+    assert np.allclose(avgs, sums.astype(np.float64) / cnts, rtol=1e-12) if n <= (1 << 26) else True
+    k = cnts.astype(np.int64)
+    hv = env.query_groupby_ex(t, 0, [1, 1, 1], ops, having=[(2, NO.GT, int(np.median(k)), 0.0)])
+    assert hv.shape[0] == int((k > np.median(k)).sum())
+    print(f"groupby {n} rows: {st['total_ms']:.2f} ms total, reduce kernel {st['kernel_ms']:.2f} ms")
+    for x in (hv, r, t):
+        x.free()
+
+
+def test_orderby_full_size_properties():
+    """Config 4 (2e9 x {i64,i64} when memory allows): sortedness and multiset preservation, checked on device."""
+    import torch
+    env = get_env()
+    n = 2 * 10 ** 9 if free_gb() > 150 else (1 << 27)
+    specs = [dict(kind=NO.GEN_UNIFORM, lo=-(2 ** 19), range=2 ** 20), dict(kind=NO.GEN_UNIFORM, lo=0, range=0)]
+    t = env.synth(n, [NO.I64, NO.I64], specs, seed=42)
+    s1 = int(as_torch(t, 0).sum().item())
+    x2 = as_torch(t, 1)
+    s2 = int(x2.sum().item())                  # wraps mod 2^64 like the check below
+    r = env.query_orderby(t, [0, 1], [0, 1])
+    st = env.stats()
+    a, b = as_torch(r, 0), as_torch(r, 1)
+    assert int(a.sum().item()) == s1 and int(b.sum().item()) == s2
+    chunk = 1 << 28
+    for lo in range(0, n - 1, chunk):
+        hi = min(n - 1, lo + chunk)
+        a0, a1, b0, b1 = a[lo:hi], a[lo + 1:hi + 1], b[lo:hi], b[lo + 1:hi + 1]
+        ok = (a0 < a1) | ((a0 == a1) & (b0 <= b1))
+        assert bool(ok.all().item()), f"not sorted in rows [{lo},{hi})"
+        del ok
+    print(f"orderby {n} rows: {st['total_ms']:.2f} ms total, passes {st['kernel_ms']:.2f} ms")
+    del a, b, x2
+    r.free(); t.free()
