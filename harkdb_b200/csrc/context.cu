@@ -22,6 +22,12 @@ int hark_ctx::dalloc(void **p, size_t bytes) {
     bytes = (bytes + 255) & ~(size_t)255; // padded: a 16-byte group load of a ragged column end stays in bounds
     if (bytes == 0) bytes = 256;
     cudaError_t e = cudaMallocFromPoolAsync(p, bytes, pool, stream);
+    if (e == cudaErrorMemoryAllocation) { // fragmented pool: hand every free block back to the driver and retry once
+        cudaGetLastError();
+        cudaStreamSynchronize(stream);
+        cudaMemPoolTrimTo(pool, 0);
+        e = cudaMallocFromPoolAsync(p, bytes, pool, stream);
+    }
     if (e != cudaSuccess) {
         cudaGetLastError();
         *p = nullptr;

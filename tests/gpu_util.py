@@ -60,6 +60,7 @@ _TYPESTR = {0: "<i4", 1: "<u4", 2: "<i8", 3: "<f4", 4: "<f8"}
 def as_torch(table, col):
     """Zero-copy torch view of a device column (the table must stay alive)."""
     import torch
+    table._env.sync()    # libhark launches on its own stream; torch must not read the column before it is written
     n = table.shape[0]
     dt = table.dtypes[col]
     ts = _TYPESTR[dt]

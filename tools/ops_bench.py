@@ -1,0 +1,174 @@
+#!/usr/bin/env python
+"""Operator timings for BASELINE configs 3-5 (GROUP BY, ORDER BY, JOIN+GROUP BY) on one GPU, with cheap
+on-device result checks (size-independent properties).  Not the driver's bench line (that is bench.py, config 2);
+this is the measurement behind DESIGN.md §roofline and profiles/*_ops.json.
+
+  python tools/ops_bench.py [--ops groupby,orderby,join] [--scale 1.0] [--reps 3] [--out gpurun_out/ops.json]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+I32, U32, I64, F32, F64 = 0, 1, 2, 3, 4
+GT = 0
+AGG_SUM, AGG_COUNT, AGG_AVG = 2, 5, 6
+
+
+class _CAI:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+_TS = {0: "<i4", 1: "<i4", 2: "<i8", 3: "<f4", 4: "<f8"}
+
+
+def as_torch(table, col):
+    import torch
+    table._env.sync()    # libhark launches on its own stream; torch must not read the column before it is written
+    return torch.as_tensor(_CAI(table.column_ptr(col), table.shape[0], _TS[table.dtypes[col]]), device="cuda")
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def timed(env, fn, reps):
+    import torch
+    out = []
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = fn()
+        env.sync()
+        wall = (time.perf_counter() - t0) * 1e3
+        st = env.stats()
+        st["wall_ms"] = wall
+        out.append((st, r))
+    best = min(out, key=lambda x: x[0]["total_ms"])
+    for st, r in out:
+        if r is not best[1]:
+            r.free()
+    return best
+
+
+def line(name, n, st, extra=None):
+    pk = peak()
+    gbs = st["alg_bytes"] / (st["total_ms"] * 1e-3) / 1e9 if st["total_ms"] > 0 else 0.0
+    d = {"op": name, "rows": n, "total_ms": st["total_ms"], "kernel_ms": st["kernel_ms"], "wall_ms": st["wall_ms"],
+         "alg_bytes": st["alg_bytes"], "rows_out": st["rows_out"], "launches": st["launches"],
+         "rows_per_s": n / (st["total_ms"] * 1e-3), "alg_gbs": gbs, "frac_of_measured_peak": gbs / pk, "peak_gbs": pk}
+    if extra:
+        d.update(extra)
+    print(json.dumps(d), flush=True)
+    return d
+
+
+def run_groupby(env, scale, reps):
+    import torch
+    n = int(10 ** 9 * scale)
+    specs = [dict(kind=0, lo=0, range=1 << 20), dict(kind=0, lo=0, range=1000)]
+    t = env.synth(n, [I32, I32], specs, seed=42)
+    ops = [AGG_SUM, AGG_COUNT, AGG_AVG]
+    st, r = timed(env, lambda: env.query_groupby_ex(t, 0, [1, 1, 1], ops), reps)
+    keys, sums, cnts, avgs = r.columns()
+    ok = (len(keys) == min(1 << 20, len(keys)) and np.all(np.diff(keys.astype(np.int64)) > 0) and int(cnts.sum()) == n)
+    total = int(as_torch(t, 1).sum(dtype=torch.int64).item())
+    ok = ok and (int(sums.view(np.uint32).astype(np.uint64).sum()) - total) % (1 << 32) == 0
+    med = int(np.median(cnts))
+    st2, r2 = timed(env, lambda: env.query_groupby_ex(t, 0, [1, 1, 1], ops, having=[(2, GT, med, 0.0)]), 1)
+    ok = ok and r2.shape[0] == int((cnts > med).sum())
+    d = line("groupby_cfg3", n, st, {"groups": len(keys), "check_ok": bool(ok), "having_total_ms": st2["total_ms"]})
+    r.free(); r2.free(); t.free()
+    return d
+
+
+def run_orderby(env, scale, reps):
+    import torch
+    n = int(2 * 10 ** 9 * scale)
+    specs = [dict(kind=0, lo=-(2 ** 19), range=2 ** 20), dict(kind=0, lo=0, range=0)]
+    t = env.synth(n, [I64, I64], specs, seed=42)
+    a0, b0 = as_torch(t, 0), as_torch(t, 1)
+    s1, s2 = int(a0.sum().item()), int(b0.sum().item())
+    x2 = int(torch.bitwise_xor(a0 * 0x9E3779B97F4A7C15 + b0, b0 >> 7).sum().item())   # pairing-sensitive multiset hash
+    torch.cuda.empty_cache()
+    st, r = timed(env, lambda: env.query_orderby(t, [0, 1], [0, 1]), reps)
+    a, b = as_torch(r, 0), as_torch(r, 1)
+    sums_ok = int(a.sum().item()) == s1 and int(b.sum().item()) == s2
+    pair_ok = int(torch.bitwise_xor(a * 0x9E3779B97F4A7C15 + b, b >> 7).sum().item()) == x2
+    torch.cuda.empty_cache()
+    sorted_ok = True
+    chunk = 1 << 28
+    for lo in range(0, n - 1, chunk):
+        hi = min(n - 1, lo + chunk)
+        okv = (a[lo:hi] < a[lo + 1:hi + 1]) | ((a[lo:hi] == a[lo + 1:hi + 1]) & (b[lo:hi] <= b[lo + 1:hi + 1]))
+        sorted_ok = sorted_ok and bool(okv.all().item())
+        del okv
+    d = line("orderby_cfg4", n, st, {"check_ok": bool(sums_ok and pair_ok and sorted_ok), "sums_ok": sums_ok,
+                                     "pair_ok": pair_ok, "sorted_ok": sorted_ok})
+    del a, b, a0, b0
+    r.free(); t.free()
+    return d
+
+
+def run_join(env, scale, reps):
+    import torch
+    nf, nd = int(4 * 10 ** 9 * scale), int(10 ** 8 * min(1.0, scale * 4))
+    # dim: pk = (a*r+b) mod nd with gcd(a, nd)=1 -> a permutation of 0..nd-1 (unique); attr uniform over 1024
+    a = 2654435761
+    while np.gcd(a, nd) != 1:
+        a += 2
+    dim = env.synth(nd, [I32, I32], [dict(kind=1, a=a, b=12345, range=nd), dict(kind=0, lo=0, range=1024)], seed=7)
+    fact = env.synth(nf, [I32, I32], [dict(kind=0, lo=0, range=nd), dict(kind=0, lo=0, range=1000)], seed=42)
+    ops = [AGG_SUM, AGG_COUNT]
+    st, r = timed(env, lambda: env.join_groupby(fact, dim, 0, 0, 1, [1, 1], ops), reps)
+    keys, sums, cnts = r.columns()
+    total = int(as_torch(fact, 1).sum(dtype=torch.int64).item())
+    ok = (len(keys) == 1024 and np.array_equal(keys, np.arange(1024, dtype=np.int32)) and int(cnts.sum()) == nf
+          and (int(sums.view(np.uint32).astype(np.uint64).sum()) - total) % (1 << 32) == 0)
+    d = line("join_groupby_cfg5", nf, st, {"dim_rows": nd, "groups": len(keys), "check_ok": bool(ok)})
+    r.free(); dim.free(); fact.free()
+    return d
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ops", default="groupby,orderby,join")
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--join-scale", type=float, default=None)
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--out", default="")
+    ap.add_argument("--opt", action="append", default=[], help="key=value context option")
+    args = ap.parse_args()
+    from harkdb_b200 import hark_ffi
+    env = hark_ffi.Futhark()
+    for kv in args.opt:
+        k, v = kv.split("=")
+        env.set_option(k, int(v))
+    res = []
+    for op in args.ops.split(","):
+        try:
+            if op == "groupby":
+                res.append(run_groupby(env, args.scale, args.reps))
+            elif op == "orderby":
+                res.append(run_orderby(env, args.scale, args.reps))
+            elif op == "join":
+                res.append(run_join(env, args.join_scale or args.scale, args.reps))
+        except Exception as e:  # keep going: one OOM must not hide the other operators' numbers
+            print(json.dumps({"op": op, "error": repr(e)[:400]}), flush=True)
+            res.append({"op": op, "error": repr(e)[:400]})
+    if args.out:
+        json.dump(res, open(args.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
