@@ -377,3 +377,65 @@ def test_orderby_full_size_properties():
     print(f"orderby {n} rows: {st['total_ms']:.2f} ms total, passes {st['kernel_ms']:.2f} ms")
     del a, b, x2
     r.free(); t.free()
+
+
+# ---------------------------------------------------------------- the futhark_* link-compat aliases
+def test_futhark_compat_layer_runs_the_reference_entries():
+    """Drives libhark.so ONLY through the names `futhark c --library main.fut` would generate (setup.sh:12):
+    data.csv GROUP BY of test.py:7 and the README projection, against the golden vectors."""
+    import ctypes as C
+    need_gpu()
+    from harkdb_b200 import hark_ffi
+    lib = C.CDLL(hark_ffi.LIB_PATH)
+    P = C.c_void_p
+    for name, res, args in [
+        ("futhark_context_config_new", P, []), ("futhark_context_new", P, [P]), ("futhark_context_free", None, [P]),
+        ("futhark_context_config_free", None, [P]), ("futhark_context_sync", C.c_int, [P]),
+        ("futhark_context_get_error", P, [P]),
+        ("futhark_new_u32_2d", P, [P, P, C.c_int64, C.c_int64]), ("futhark_new_i32_2d", P, [P, P, C.c_int64, C.c_int64]),
+        ("futhark_new_i32_1d", P, [P, P, C.c_int64]),
+        ("futhark_shape_u32_2d", C.POINTER(C.c_int64), [P, P]), ("futhark_shape_i32_2d", C.POINTER(C.c_int64), [P, P]),
+        ("futhark_values_u32_2d", C.c_int, [P, P, P]), ("futhark_values_i32_2d", C.c_int, [P, P, P]),
+        ("futhark_free_u32_2d", C.c_int, [P, P]), ("futhark_free_i32_2d", C.c_int, [P, P]),
+        ("futhark_free_i32_1d", C.c_int, [P, P]),
+        ("futhark_entry_query_sel", C.c_int, [P, C.POINTER(P), P, P]),
+        ("futhark_entry_query_groupby", C.c_int, [P, C.POINTER(P), P, C.c_int32, P, P]),
+    ]:
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    cfg = lib.futhark_context_config_new()
+    ctx = lib.futhark_context_new(cfg)
+    assert ctx
+    db = np.ascontiguousarray(np.asarray(DATA["rows"], dtype=np.uint32))
+    h_db = lib.futhark_new_u32_2d(ctx, db.ctypes.data, db.shape[0], db.shape[1])
+    s = np.array([0, 2], dtype=np.int32)
+    t = np.array([0, 3], dtype=np.int32)
+    h_s, h_t = lib.futhark_new_i32_1d(ctx, s.ctypes.data, 2), lib.futhark_new_i32_1d(ctx, t.ctypes.data, 2)
+    out = P()
+    assert lib.futhark_entry_query_groupby(ctx, C.byref(out), h_db, 0, h_s, h_t) == 0
+    assert lib.futhark_context_sync(ctx) == 0
+    shp = lib.futhark_shape_u32_2d(ctx, out)
+    res = np.empty((shp[0], shp[1]), dtype=np.uint32)
+    assert lib.futhark_values_u32_2d(ctx, out, res.ctypes.data) == 0
+    assert res.tolist() == [[0, 0, 0], [1, 1, 3], [6, 6, 6]]                        # SURVEY App. B / test.py:7
+    lib.futhark_free_u32_2d(ctx, out)
+    dbi = db.astype(np.int32)
+    h_dbi = lib.futhark_new_i32_2d(ctx, dbi.ctypes.data, dbi.shape[0], dbi.shape[1])
+    out = P()
+    assert lib.futhark_entry_query_sel(ctx, C.byref(out), h_dbi, h_s) == 0
+    shp = lib.futhark_shape_i32_2d(ctx, out)
+    res = np.empty((shp[0], shp[1]), dtype=np.int32)
+    assert lib.futhark_values_i32_2d(ctx, out, res.ctypes.data) == 0
+    assert res.tolist() == [[6, 6], [0, 0], [0, 0], [0, 0], [0, 0], [6, 6], [1, 3]]   # README.md:42
+    bad = np.array([0, 99], dtype=np.int32)
+    h_bad = lib.futhark_new_i32_1d(ctx, bad.ctypes.data, 2)
+    out2 = P()
+    assert lib.futhark_entry_query_sel(ctx, C.byref(out2), h_dbi, h_bad) != 0       # Futhark: index out of bounds
+    err = lib.futhark_context_get_error(ctx)
+    assert err and b"bounds" in C.string_at(err)
+    C.CDLL(None).free(P(err))
+    for h in (h_s, h_t, h_bad):
+        lib.futhark_free_i32_1d(ctx, h)
+    lib.futhark_free_i32_2d(ctx, out); lib.futhark_free_i32_2d(ctx, h_dbi); lib.futhark_free_u32_2d(ctx, h_db)
+    lib.futhark_context_free(ctx)
+    lib.futhark_context_config_free(cfg)
