@@ -22,6 +22,7 @@
 #include <stdexcept>
 #include <vector>
 
+#include "dense_agg.cuh"
 #include "hark_internal.cuh"
 #include "sort.cuh"
 
@@ -595,9 +596,71 @@ int hk_groupby(hark_ctx *ctx, hark_table **out, const hark_table *db, int32_t g_
         return HARK_OK;
     }
     ctx->entry_begin();
-
-    // carried arrays: the key column first, then each distinct value column that is not the key column
     const int32_t key_dtype = pinned_u32 ? HARK_U32 : db->cols[g_col].dtype;
+
+    // ---- K2: dense / partitioned shared-memory aggregation when the key range allows it (dense_agg.cu) ----
+    if (ctx->opt("groupby.impl", 0) != 1 && n > 0) {
+        hk_dense_req rq;
+        rq.n = n;
+        rq.key = db->cols[g_col].ptr;
+        rq.key_dtype = key_dtype;
+        rq.out_key_dtype = key_dtype;
+        rq.pinned_u32 = pinned_u32;
+        rq.c = (int)c;
+        bool eligible = c <= HK_DENSE_MAX_AGGS && hk_dtype_size(db->cols[g_col].dtype) == hk_dtype_size(key_dtype);
+        std::vector<int> val_of_col((size_t)m, -1);
+        for (int64_t j = 0; j < c && eligible; j++) {
+            int code = ops[j];
+            if (pinned_u32 && (code < HARK_AGG_PROD || code > HARK_AGG_MIN)) code = HARK_AGG_MIN; // groupby.fut:41
+            if (!pinned_u32 && (code < HARK_AGG_PROD || code > HARK_AGG_AVG)) code = HARK_AGG_MIN;
+            rq.agg_code[j] = code;
+            if (code == HARK_AGG_COUNT) {
+                rq.agg_val[j] = -1;
+                continue;
+            }
+            const int col = s_cols[j];
+            if (val_of_col[col] < 0) {
+                if (rq.nvals == HK_DENSE_MAX_VALS) {
+                    eligible = false;
+                    break;
+                }
+                val_of_col[col] = rq.nvals;
+                rq.vals[rq.nvals] = db->cols[col].ptr;
+                rq.val_dtypes[rq.nvals] = pinned_u32 ? HARK_U32 : db->cols[col].dtype;
+                rq.nvals++;
+            }
+            rq.agg_val[j] = val_of_col[col];
+        }
+        if (eligible) {
+            HK_TRY(hk_col_minmax(ctx, rq.key, key_dtype, n, &rq.g_lo, &rq.g_hi));
+            bool handled = false;
+            hark_table *t = nullptr;
+            HK_TRY(hk_dense_groupby(ctx, &t, rq, &handled));
+            if (handled) {
+                if (nh > 0) { // HAVING: K1 over the (small) group table; output column indices
+                    std::vector<int32_t> all;
+                    for (int64_t j = 0; j < 1 + c; j++) all.push_back((int32_t)j);
+                    hark_stats keep = ctx->last;
+                    const int64_t keep_launches = ctx->entry_launches;
+                    hark_table *f = nullptr;
+                    int rc = hk_filter(ctx, &f, t, all.data(), 1 + c, having, nh);
+                    hark_table_free(ctx, t);
+                    if (rc != HARK_OK) return rc;
+                    t = f;
+                    ctx->last = keep;
+                    ctx->entry_launches += keep_launches;
+                }
+                int64_t alg = n * hk_dtype_size(key_dtype);
+                for (int v = 0; v < rq.nvals; v++) alg += n * 4;
+                for (auto &col : t->cols) alg += t->n * hk_dtype_size(col.dtype);
+                ctx->entry_end(alg, n, t->n);
+                *out = t;
+                return HARK_OK;
+            }
+        }
+    }
+
+    // ---- sort path: carried arrays = the key column first, then each distinct value column ----
     std::vector<hk_sort_array> arrays;
     std::vector<int> array_of_col((size_t)m, -1);
     {

@@ -17,6 +17,7 @@
 #include <stdexcept>
 #include <vector>
 
+#include "dense_agg.cuh"
 #include "hark_internal.cuh"
 #include "sort.cuh"
 
@@ -122,6 +123,22 @@ __global__ void __launch_bounds__(256) hk_lut_build_kernel(const void *pk, int p
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_dim; i += stride) {
         const long long v = load_int(pk, pk_dtype, i) - pk_min;
         const uint32_t old = atomicMax(&lut[v], (uint32_t)(i + 1));
+        if (old != 0) *dup_flag = 1u;
+    }
+}
+
+// slot lookup for the fused probe + aggregate (dense_agg.cu, lut mode):
+// lut[pk - pk_min] = (ordkey(dim.g) - g_lo) + 1, 0 = no such key.  Duplicate pks raise dup_flag.
+__global__ void __launch_bounds__(256) hk_slot_lut_build_kernel(const void *pk, int pk_dtype, const void *g, int g_dtype,
+                                                                 int64_t n_dim, long long pk_min, unsigned long long g_lo,
+                                                                 uint32_t *lut, unsigned int *dup_flag) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_dim; i += stride) {
+        const long long v = load_int(pk, pk_dtype, i) - pk_min;
+        unsigned long long ord;
+        if (g_dtype == HARK_I64) ord = hk_ordkey64(reinterpret_cast<const unsigned long long *>(g)[i], g_dtype);
+        else ord = hk_ordkey32(reinterpret_cast<const uint32_t *>(g)[i], g_dtype);
+        const uint32_t old = atomicExch(&lut[v], (uint32_t)(ord - g_lo) + 1u);
         if (old != 0) *dup_flag = 1u;
     }
 }
@@ -314,6 +331,68 @@ int hk_join_groupby(hark_ctx *ctx, hark_table **out, const hark_table *fact, con
         HK_TRY(bufs.alloc((void **)&lut, sizeof(uint32_t) * (size_t)span));
         HK_CUDA(ctx, cudaMemsetAsync(lut, 0, sizeof(uint32_t) * (size_t)span, ctx->stream));
         unsigned int *dup = (unsigned int *)(d_mm); // reuse: [0] as the duplicate flag
+
+        // ---- K2 in lookup mode: probe and aggregate in one pass over the fact columns, no materialised join ----
+        if (ctx->opt("groupby.impl", 0) != 1 && nf > 0 && c <= HK_DENSE_MAX_AGGS) {
+            hk_dense_req rq;
+            rq.n = nf;
+            rq.key = fact->cols[fk_col].ptr;
+            rq.key_dtype = fact->cols[fk_col].dtype;
+            rq.out_key_dtype = g_dtype;
+            rq.c = (int)c;
+            bool eligible = true;
+            std::vector<int> val_of_col((size_t)mf, -1);
+            for (int64_t j = 0; j < c && eligible; j++) {
+                int code = ops[j];
+                if (code < HARK_AGG_PROD || code > HARK_AGG_AVG) code = HARK_AGG_MIN;
+                rq.agg_code[j] = code;
+                if (code == HARK_AGG_COUNT) {
+                    rq.agg_val[j] = -1;
+                    continue;
+                }
+                const int col = s_cols[j];
+                if (val_of_col[col] < 0) {
+                    if (rq.nvals == HK_DENSE_MAX_VALS) {
+                        eligible = false;
+                        break;
+                    }
+                    val_of_col[col] = rq.nvals;
+                    rq.vals[rq.nvals] = fact->cols[col].ptr;
+                    rq.val_dtypes[rq.nvals] = fact->cols[col].dtype;
+                    rq.nvals++;
+                }
+                rq.agg_val[j] = val_of_col[col];
+            }
+            if (eligible) {
+                HK_TRY(hk_col_minmax(ctx, dim->cols[g_col].ptr, g_dtype, nd, &rq.g_lo, &rq.g_hi));
+                if (rq.g_hi - rq.g_lo < (1ull << 20)) {
+                    HK_CUDA(ctx, cudaMemsetAsync(dup, 0, sizeof(unsigned int), ctx->stream));
+                    hk_slot_lut_build_kernel<<<grid_for(ctx, nd), 256, 0, ctx->stream>>>(
+                        dim->cols[pk_col].ptr, dim->cols[pk_col].dtype, dim->cols[g_col].ptr, g_dtype, nd, pk_min,
+                        (unsigned long long)rq.g_lo, lut, dup);
+                    HK_CHECK_LAUNCH(ctx);
+                    ctx->count_launch();
+                    HK_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, dup, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+                    HK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                    if (((unsigned int *)ctx->h_scalars)[0] != 0)
+                        return ctx->fail(HARK_ERR_ARG, "join_groupby: dim.pk is not unique");
+                    rq.lut = lut;
+                    rq.pk_min = pk_min;
+                    rq.pk_span = pk_span;
+                    bool handled = false;
+                    hark_table *t = nullptr;
+                    HK_TRY(hk_dense_groupby(ctx, &t, rq, &handled));
+                    if (handled) {
+                        int64_t alg = nf * hk_dtype_size(rq.key_dtype) + nf * 4 * rq.nvals;
+                        alg += nd * (hk_dtype_size(dim->cols[pk_col].dtype) + gw);
+                        ctx->entry_end(alg, nf + nd, t->n);
+                        *out = t;
+                        return HARK_OK;
+                    }
+                    HK_CUDA(ctx, cudaMemsetAsync(lut, 0, sizeof(uint32_t) * (size_t)span, ctx->stream)); // rebuild as row lut below
+                }
+            }
+        }
         HK_CUDA(ctx, cudaMemsetAsync(dup, 0, sizeof(unsigned int), ctx->stream));
         hk_lut_build_kernel<<<grid_for(ctx, nd), 256, 0, ctx->stream>>>(dim->cols[pk_col].ptr, dim->cols[pk_col].dtype, nd, pk_min, lut, dup);
         HK_CHECK_LAUNCH(ctx);

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from oracle import np_oracle as NO
-from tests.gpu_util import as_torch, cols_of, free_gb, get_env, rand_table
+from tests.gpu_util import as_torch, cols_of, free_gb, get_env, need_gpu, rand_table
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
@@ -20,6 +20,19 @@ SIZES = [1, 2, 31, 127, 128, 129, 4095, 4096, 4097, 8193, 100003, (1 << 20) + 5]
 
 def _db(ref):
     return DATA["rows"] if ref == "data_csv" else ref
+
+
+@pytest.fixture(params=["auto", "sort", "tiny_tables"])
+def gb_impl(request):
+    """GROUP BY strategies: `auto` = K2 dense/partitioned aggregation when the key range allows it,
+    `sort` = K3 radix sort + K4 segmented reduce only, `tiny_tables` = K2 with 256-slot shared-memory tables so that
+    small inputs exercise the partition pass and the bucket-to-bucket table merges."""
+    env = get_env()
+    env.set_option("groupby.impl", 1 if request.param == "sort" else 0)
+    env.set_option("dense.log2_slots", 8 if request.param == "tiny_tables" else 0)
+    yield request.param
+    env.set_option("groupby.impl", 0)
+    env.set_option("dense.log2_slots", 0)
 
 
 # ---------------------------------------------------------------- GROUP BY (reference-pinned, u32)
@@ -42,7 +55,7 @@ def test_groupby_test_py_query():
 
 @pytest.mark.parametrize("n", [0] + SIZES)
 @pytest.mark.parametrize("keys", ["few", "distinct", "one", "high", "runs"])
-def test_groupby_u32_vs_oracle(n, keys):
+def test_groupby_u32_vs_oracle(gb_impl, n, keys):
     env = get_env()
     rng = np.random.default_rng(n * 7 + len(keys))
     m = 4
@@ -93,7 +106,7 @@ def _check_cols(got_cols, exp_cols, in_dtypes=None):
 
 @pytest.mark.parametrize("kdt", [NO.I32, NO.U32, NO.I64])
 @pytest.mark.parametrize("vdt", [NO.I32, NO.U32, NO.I64, NO.F32, NO.F64])
-def test_groupby_ex_typed(kdt, vdt):
+def test_groupby_ex_typed(gb_impl, kdt, vdt):
     env = get_env()
     rng = np.random.default_rng(kdt * 10 + vdt)
     n = 200003
@@ -117,7 +130,7 @@ def test_groupby_ex_typed(kdt, vdt):
         x.free()
 
 
-def test_groupby_ex_prod_and_wrap():
+def test_groupby_ex_prod_and_wrap(gb_impl):
     env = get_env()
     rng = np.random.default_rng(77)
     n = 50000
@@ -134,7 +147,7 @@ def test_groupby_ex_prod_and_wrap():
 
 
 @pytest.mark.parametrize("n", [0, 1, 4096, 4097, 300000])
-def test_groupby_ex_sizes_and_single_group(n):
+def test_groupby_ex_sizes_and_single_group(gb_impl, n):
     env = get_env()
     rng = np.random.default_rng(n)
     key = np.full(n, -7, dtype=np.int64)
@@ -285,7 +298,7 @@ def test_join_empty_and_errors():
         env.join(a, a, 0, 0, [9], [1])
 
 
-def test_join_groupby_config5_shape():
+def test_join_groupby_config5_shape(gb_impl):
     """BASELINE config 5 at an oracle-checkable size: fact(fk,val) JOIN dim(pk unique,attr) GROUP BY attr."""
     env = get_env()
     from oracle import c_oracle as CO
