@@ -81,246 +81,13 @@ __global__ void __launch_bounds__(256) hk_dminmax_kernel(const void *__restrict_
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// partition pass
-// ------------------------------------------------------------------------------------------------
-constexpr int PT = 256;          // threads per CTA
-constexpr int PI = 16;           // rows per thread
-constexpr int PTILE = PT * PI;   // rows per tile
-constexpr int PMAXV = 3;
-
-template <int KW>
-__device__ __forceinline__ uint32_t part_digit(typename KRaw<KW>::T raw, const hk_part_spec &f) {
-    const uint64_t u = ordkey_of<KW>(raw, f.dtype) - f.base;
-    return (f.span != 0 && u >= f.span) ? 0u : (uint32_t)(u >> f.shift);
-}
-
-struct PartHistParams {
-    hk_part_spec f;
-    const void *key;
-    int64_t n;
-    unsigned long long *hist; // [256]
-};
-
-template <int KW>
-__global__ void __launch_bounds__(256) hk_part_hist_kernel(const __grid_constant__ PartHistParams P) {
-    using T = typename KRaw<KW>::T;
-    __shared__ uint32_t sh[256];
-    sh[threadIdx.x] = 0;
-    __syncthreads();
-    const T *p = reinterpret_cast<const T *>(P.key);
-    constexpr int V = 16 / KW;
-    const int64_t nvec = P.n / V;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
-        T x[V];
-        if constexpr (KW == 4) {
-            const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(p) + i);
-            x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
-        } else {
-            const ulonglong2 v = __ldcs(reinterpret_cast<const ulonglong2 *>(p) + i);
-            x[0] = v.x; x[1] = v.y;
-        }
-#pragma unroll
-        for (int e = 0; e < V; e++) atomicAdd(&sh[part_digit<KW>(x[e], P.f)], 1u);
-    }
-    if (blockIdx.x == 0 && threadIdx.x < (int)(P.n - nvec * V))
-        atomicAdd(&sh[part_digit<KW>(p[nvec * V + threadIdx.x], P.f)], 1u);
-    __syncthreads();
-    const uint32_t c = sh[threadIdx.x];
-    if (c) atomicAdd(&P.hist[threadIdx.x], (unsigned long long)c);
-}
-
-// exclusive scan of 256 counts in place; offsets[256] = total
-__global__ void __launch_bounds__(256) hk_part_scan_kernel(unsigned long long *h) {
-    __shared__ unsigned long long wtot[8];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned long long c = h[threadIdx.x];
-    unsigned long long inc = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long t = __shfl_up_sync(HK_FULL_MASK, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) wtot[warp] = inc;
-    __syncthreads();
-    unsigned long long off = 0;
-    for (int w = 0; w < warp; w++) off += wtot[w];
-    h[threadIdx.x] = off + inc - c;
-    if (threadIdx.x == 255) h[256] = off + inc;
-}
-
-struct PartParams {
-    hk_part_spec f;
-    const void *key_in;
-    void *key_out;
-    const uint32_t *val_in[PMAXV];
-    uint32_t *val_out[PMAXV];
-    int64_t n;
-    int64_t num_tiles;
-    uint64_t *status;                   // [num_tiles][nbins] look-back words (zeroed)
-    unsigned long long *ticket;         // zeroed
-    const unsigned long long *offsets;  // [257] exclusive bin offsets
-};
-
-// Unstable single-pass partition: ranks inside a tile come from shared-memory atomics (no match/ballot
-// ranking), the per-bin global offsets from a chained-scan look-back, and the tile is reordered in shared
-// memory so that every bin's rows leave as one contiguous run.
-template <int KW, int NV>
-__global__ void __launch_bounds__(PT, (NV <= 1 && KW == 4) ? 3 : 2) hk_part_kernel(const __grid_constant__ PartParams P) {
-    using KT = typename KRaw<KW>::T;
-    extern __shared__ __align__(16) unsigned char s_dyn[];
-    KT *s_key = reinterpret_cast<KT *>(s_dyn);
-    uint32_t *s_val = reinterpret_cast<uint32_t *>(s_dyn + (size_t)PTILE * KW); // [NV][PTILE]
-    __shared__ uint32_t s_hist[256];
-    __shared__ uint32_t s_binstart[256];
-    __shared__ uint64_t s_gbase[256];
-    __shared__ uint32_t s_wtot[8];
-    __shared__ long long s_tile;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const KT *keyp = reinterpret_cast<const KT *>(P.key_in);
-    const int nbins = P.f.nbins;
-
-    while (true) {
-        if (tid == 0) s_tile = (long long)atomicAdd(P.ticket, 1ull);
-        s_hist[tid] = 0;
-        __syncthreads();
-        const int64_t tile = s_tile;
-        if (tile >= P.num_tiles) break;
-        const int64_t tile_base = tile * PTILE;
-        const int count = (int)min((int64_t)PTILE, P.n - tile_base);
-        const bool full = count == PTILE;
-
-        // thread t owns rows (g*PT + t)*4 .. +3 of the tile, g = 0..3: 128-bit loads, all issued up front
-        KT key[PI];
-        uint32_t val[NV > 0 ? NV : 1][PI];
-        if (full) {
-#pragma unroll
-            for (int g = 0; g < PI / 4; g++) {
-                const int64_t r = tile_base + (int64_t)(g * PT + tid) * 4;
-                if constexpr (KW == 4) {
-                    const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(keyp + r));
-                    key[g * 4 + 0] = v.x; key[g * 4 + 1] = v.y; key[g * 4 + 2] = v.z; key[g * 4 + 3] = v.w;
-                } else {
-                    const ulonglong2 a = __ldcs(reinterpret_cast<const ulonglong2 *>(keyp + r));
-                    const ulonglong2 b = __ldcs(reinterpret_cast<const ulonglong2 *>(keyp + r + 2));
-                    key[g * 4 + 0] = a.x; key[g * 4 + 1] = a.y; key[g * 4 + 2] = b.x; key[g * 4 + 3] = b.y;
-                }
-            }
-#pragma unroll
-            for (int v = 0; v < NV; v++)
-#pragma unroll
-                for (int g = 0; g < PI / 4; g++) {
-                    const int64_t r = tile_base + (int64_t)(g * PT + tid) * 4;
-                    const uint4 x = __ldcs(reinterpret_cast<const uint4 *>(P.val_in[v] + r));
-                    val[v][g * 4 + 0] = x.x; val[v][g * 4 + 1] = x.y; val[v][g * 4 + 2] = x.z; val[v][g * 4 + 3] = x.w;
-                }
-        } else {
-#pragma unroll
-            for (int i = 0; i < PI; i++) {
-                const int idx = ((i >> 2) * PT + tid) * 4 + (i & 3);
-                key[i] = idx < count ? keyp[tile_base + idx] : (KT)0;
-#pragma unroll
-                for (int v = 0; v < NV; v++) val[v][i] = idx < count ? P.val_in[v][tile_base + idx] : 0u;
-            }
-        }
-        // rank inside the tile: one shared-memory atomic per row (packed: digit << 16 | rank)
-        uint32_t rd[PI];
-#pragma unroll
-        for (int i = 0; i < PI; i++) {
-            const int idx = ((i >> 2) * PT + tid) * 4 + (i & 3);
-            if (full || idx < count) {
-                const uint32_t d = part_digit<KW>(key[i], P.f);
-                rd[i] = (d << 16) | atomicAdd(&s_hist[d], 1u);
-            } else {
-                rd[i] = 0xffffffffu;
-            }
-        }
-        __syncthreads();
-
-        // thread b owns bin b: tile-local start, then the chained scan for the global start
-        {
-            const int b = tid;
-            const uint32_t sum = s_hist[b];
-            const uint32_t inc = hk_warp_incl_scan_u32(sum);
-            if (lane == 31) s_wtot[warp] = inc;
-            __syncthreads();
-            uint32_t woff = 0;
-            for (int w = 0; w < warp; w++) woff += s_wtot[w];
-            const uint32_t binstart = woff + inc - sum;
-            s_binstart[b] = binstart;
-            if (b < nbins) {
-                uint64_t *my = P.status + (size_t)tile * nbins + b;
-                uint64_t excl = 0;
-                if (tile == 0) {
-                    hk_st_relaxed_u64(my, HK_LB_INC | (uint64_t)sum);
-                } else {
-                    hk_st_relaxed_u64(my, HK_LB_AGG | (uint64_t)sum);
-                    int64_t t = tile - 1;
-                    while (true) {
-                        uint64_t v;
-                        do {
-                            v = hk_ld_relaxed_u64(P.status + (size_t)t * nbins + b);
-                        } while ((v >> 62) == 0);
-                        excl += v & HK_LB_VAL;
-                        if ((v >> 62) == 2) break;
-                        t--;
-                    }
-                    hk_st_relaxed_u64(my, HK_LB_INC | (excl + sum));
-                }
-                s_gbase[b] = (uint64_t)P.offsets[b] + excl - (uint64_t)binstart; // wraps; undone by + position
-            }
-        }
-        __syncthreads();
-
-        // tile-local reorder
-#pragma unroll
-        for (int i = 0; i < PI; i++) {
-            if (rd[i] != 0xffffffffu) {
-                const uint32_t pos = s_binstart[rd[i] >> 16] + (rd[i] & 0xffffu);
-                s_key[pos] = key[i];
-#pragma unroll
-                for (int v = 0; v < NV; v++) s_val[v * PTILE + pos] = val[v][i];
-            }
-        }
-        __syncthreads();
-        {
-            KT *ko = reinterpret_cast<KT *>(P.key_out);
-#pragma unroll 4
-            for (int j = tid; j < count; j += PT) {
-                const KT k = s_key[j];
-                const uint64_t g = s_gbase[part_digit<KW>(k, P.f)] + (uint64_t)j;
-                ko[g] = k;
-#pragma unroll
-                for (int v = 0; v < NV; v++) P.val_out[v][g] = s_val[v * PTILE + j];
-            }
-        }
-        // no trailing barrier: the next iteration's first barrier orders these reads before any rewrite
-    }
-}
-
-template <int KW, int NV>
-int launch_part(hark_ctx *ctx, const PartParams &P) {
-    const size_t smem = (size_t)PTILE * (KW + 4 * NV);
-    auto kern = hk_part_kernel<KW, NV>;
-    HK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    HK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PT, smem));
-    occ = std::max(1, occ);
-    const int64_t want = ctx->opt("part.ctas_per_sm", 0);
-    if (want > 0) occ = (int)std::min<int64_t>(occ, want);
-    const unsigned grid = (unsigned)std::min<int64_t>(P.num_tiles, (int64_t)ctx->num_sms * occ);
-    kern<<<grid, PT, smem, ctx->stream>>>(P);
-    HK_CHECK_LAUNCH(ctx);
-    ctx->count_launch();
-    return HARK_OK;
-}
+constexpr int PMAXV = 3; // value arrays the partition pass can carry (partition.cu)
 
 // ------------------------------------------------------------------------------------------------
 // K2 aggregation kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int AT = 512;    // threads per CTA (one CTA per SM: the table takes most of the shared memory)
+// threads per CTA (one CTA per SM: the table takes most of the shared memory)
+__host__ __device__ constexpr int dagg_threads(int nv) { return nv <= 1 ? 1024 : 512; }
 constexpr int AMAXACC = 12;
 
 enum AccKind {
@@ -383,48 +150,72 @@ __device__ __forceinline__ void smem_f64_update(unsigned long long *a, double v,
     } while (old != assumed);
 }
 
-// one row into the CTA's table
-__device__ __forceinline__ void acc_row(uint32_t *tab, uint32_t K, uint32_t idx, const DAcc &a, uint32_t x) {
-    uint32_t *w0 = tab + (size_t)a.word * K + idx;
-    switch (a.kind) {
-    case A_SUM32: atomicAdd(w0, x); break;
-    case A_SUM64S: {
+// one row into the CTA's table (KIND is a compile-time AccKind: the switch over kinds sits outside the row loops)
+template <int KIND>
+__device__ __forceinline__ void acc_row(uint32_t *tab, uint32_t K, uint32_t idx, int word, uint32_t x) {
+    uint32_t *w0 = tab + (size_t)word * K + idx;
+    if constexpr (KIND == A_SUM32) {
+        atomicAdd(w0, x);
+    } else if constexpr (KIND == A_SUM64S) {
         const uint32_t old = atomicAdd(w0, x);
         const int delta = (int)((uint32_t)(old + x) < old) - (int)((int32_t)x < 0);
         if (delta != 0) atomicAdd(reinterpret_cast<int *>(w0 + K), delta);
-        break;
-    }
-    case A_SUM64U: {
+    } else if constexpr (KIND == A_SUM64U) {
         const uint32_t old = atomicAdd(w0, x);
         if ((uint32_t)(old + x) < old) atomicAdd(w0 + K, 1u);
-        break;
-    }
-    case A_FSUM: smem_f64_update(reinterpret_cast<unsigned long long *>(tab + (size_t)a.word * K) + idx, (double)__uint_as_float(x), false); break;
-    case A_FPROD: smem_f64_update(reinterpret_cast<unsigned long long *>(tab + (size_t)a.word * K) + idx, (double)__uint_as_float(x), true); break;
-    case A_MINU: atomicMin(w0, x); break;
-    case A_MAXU: atomicMax(w0, x); break;
-    case A_MINS: atomicMin(reinterpret_cast<int *>(w0), (int)x); break;
-    case A_MAXS: atomicMax(reinterpret_cast<int *>(w0), (int)x); break;
-    case A_MINF:
-    case A_MAXF: {
+    } else if constexpr (KIND == A_FSUM || KIND == A_FPROD) {
+        smem_f64_update(reinterpret_cast<unsigned long long *>(tab + (size_t)word * K) + idx, (double)__uint_as_float(x), KIND == A_FPROD);
+    } else if constexpr (KIND == A_MINU) {
+        atomicMin(w0, x);
+    } else if constexpr (KIND == A_MAXU) {
+        atomicMax(w0, x);
+    } else if constexpr (KIND == A_MINS) {
+        atomicMin(reinterpret_cast<int *>(w0), (int)x);
+    } else if constexpr (KIND == A_MAXS) {
+        atomicMax(reinterpret_cast<int *>(w0), (int)x);
+    } else if constexpr (KIND == A_MINF || KIND == A_MAXF) {
         uint32_t old = *w0, assumed;
         do {
             assumed = old;
             const float cur = __uint_as_float(assumed);
-            const float nv = a.kind == A_MINF ? fminf(cur, __uint_as_float(x)) : fmaxf(cur, __uint_as_float(x));
+            const float nv = KIND == A_MINF ? fminf(cur, __uint_as_float(x)) : fmaxf(cur, __uint_as_float(x));
             if (__float_as_uint(nv) == assumed) break;
             old = atomicCAS(w0, assumed, __float_as_uint(nv));
         } while (old != assumed);
-        break;
-    }
-    default: { // A_PROD32
+    } else { // A_PROD32
         uint32_t old = *w0, assumed;
         do {
             assumed = old;
             old = atomicCAS(w0, assumed, assumed * x);
         } while (old != assumed);
-        break;
     }
+}
+
+template <int KIND, int U>
+__device__ __forceinline__ void acc_rows(uint32_t *tab, uint32_t K, const uint32_t (&idx)[U][4], int word, const uint32_t (&x)[U][4]) {
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+            if (idx[u][e] != 0xffffffffu) acc_row<KIND>(tab, K, idx[u][e], word, x[u][e]);
+}
+
+template <int U>
+__device__ __forceinline__ void acc_dispatch(uint32_t *tab, uint32_t K, const uint32_t (&idx)[U][4], int kind, int word,
+                                             const uint32_t (&x)[U][4]) {
+    switch (kind) {
+    case A_SUM32: acc_rows<A_SUM32, U>(tab, K, idx, word, x); break;
+    case A_SUM64S: acc_rows<A_SUM64S, U>(tab, K, idx, word, x); break;
+    case A_SUM64U: acc_rows<A_SUM64U, U>(tab, K, idx, word, x); break;
+    case A_FSUM: acc_rows<A_FSUM, U>(tab, K, idx, word, x); break;
+    case A_FPROD: acc_rows<A_FPROD, U>(tab, K, idx, word, x); break;
+    case A_MINU: acc_rows<A_MINU, U>(tab, K, idx, word, x); break;
+    case A_MAXU: acc_rows<A_MAXU, U>(tab, K, idx, word, x); break;
+    case A_MINS: acc_rows<A_MINS, U>(tab, K, idx, word, x); break;
+    case A_MAXS: acc_rows<A_MAXS, U>(tab, K, idx, word, x); break;
+    case A_MINF: acc_rows<A_MINF, U>(tab, K, idx, word, x); break;
+    case A_MAXF: acc_rows<A_MAXF, U>(tab, K, idx, word, x); break;
+    default: acc_rows<A_PROD32, U>(tab, K, idx, word, x); break;
     }
 }
 
@@ -514,10 +305,64 @@ __device__ __forceinline__ void load_keys4(const typename KRaw<KW>::T *p, int64_
     }
 }
 
-template <int KW, bool LUT, int NV>
-__global__ void __launch_bounds__(AT, 1) hk_dagg_kernel(const __grid_constant__ DAggParams P) {
+// One iteration of the row loop: U 4-row groups per thread.  CHECK = the groups may straddle [r0, r1).
+template <int KW, bool LUT, int NV, int U, bool CHECK>
+__device__ __forceinline__ void dagg_step(const DAggParams &P, uint32_t *tab, const typename KRaw<KW>::T *keyp, int64_t g0,
+                                          int64_t r0, int64_t r1, uint64_t slot0, int tid) {
     using KT = typename KRaw<KW>::T;
-    constexpr int U = NV <= 1 ? 4 : 2; // 4-row groups per thread and iteration (all their loads are in flight together)
+    constexpr int AT = dagg_threads(NV);
+    int64_t rr[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) rr[u] = g0 + (int64_t)(u * AT + tid) * 4;
+    KT k[U][4];
+    uint32_t x[NV > 0 ? NV : 1][U][4];
+#pragma unroll
+    for (int u = 0; u < U; u++)
+        if (!CHECK || rr[u] < r1) load_keys4<KW>(keyp, rr[u], k[u]);
+#pragma unroll
+    for (int v = 0; v < NV; v++)
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (!CHECK || rr[u] < r1) {
+                const uint4 q = __ldcs(reinterpret_cast<const uint4 *>(P.vals[v] + rr[u]));
+                x[v][u][0] = q.x; x[v][u][1] = q.y; x[v][u][2] = q.z; x[v][u][3] = q.w;
+            }
+    uint32_t idx[U][4];
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            idx[u][e] = 0xffffffffu;
+            if (!CHECK || (rr[u] + e >= r0 && rr[u] + e < r1)) {
+                if (LUT) {
+                    long long v;
+                    if constexpr (KW == 4) v = (P.key_dtype == HARK_U32 ? (long long)(uint32_t)k[u][e] : (long long)(int32_t)k[u][e]) - P.pk_min;
+                    else v = (long long)k[u][e] - P.pk_min;
+                    if (v >= 0 && v < P.pk_span) idx[u][e] = __ldg(P.lut + v) - 1u; // 0 (no match) -> 0xffffffff
+                } else {
+                    idx[u][e] = (uint32_t)(ordkey_of<KW>(k[u][e], P.key_dtype) - P.g_lo - slot0);
+                }
+            }
+        }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+            if ((!CHECK && !LUT) || idx[u][e] != 0xffffffffu) atomicAdd(&tab[idx[u][e]], 1u);
+#pragma unroll 1
+    for (int ai = 0; ai < P.nacc; ai++) {
+        const int kind = P.acc[ai].kind, word = P.acc[ai].word, vcol = P.acc[ai].vcol;
+#pragma unroll
+        for (int v = 0; v < NV; v++)
+            if (v == vcol) acc_dispatch<U>(tab, P.K, idx, kind, word, x[v]);
+    }
+}
+
+template <int KW, bool LUT, int NV>
+__global__ void __launch_bounds__(dagg_threads(NV), 1) hk_dagg_kernel(const __grid_constant__ DAggParams P) {
+    using KT = typename KRaw<KW>::T;
+    constexpr int AT = dagg_threads(NV);
+    constexpr int U = NV <= 1 ? 2 : 2; // 4-row groups per thread and iteration (all their loads are in flight together)
     extern __shared__ __align__(16) uint32_t tab[];
     __shared__ unsigned long long s_cpre[258]; // chunks before bucket b
     const int tid = threadIdx.x;
@@ -574,60 +419,10 @@ __global__ void __launch_bounds__(AT, 1) hk_dagg_kernel(const __grid_constant__ 
         const int64_t r0 = (int64_t)P.offsets[b] + (int64_t)(c - (long long)s_cpre[b]) * P.chunk;
         const int64_t r1 = min(r0 + P.chunk, (int64_t)P.offsets[b + 1]);
         const uint64_t slot0 = LUT ? 0ull : ((uint64_t)b << P.shift);
-        const int64_t a0 = r0 & ~(int64_t)3;
-        for (int64_t g0 = a0; g0 < r1; g0 += (int64_t)AT * 4 * U) {
-            int64_t rr[U];
-#pragma unroll
-            for (int u = 0; u < U; u++) rr[u] = g0 + (int64_t)(u * AT + tid) * 4;
-            KT k[U][4];
-            uint32_t x[NV > 0 ? NV : 1][U][4];
-#pragma unroll
-            for (int u = 0; u < U; u++)
-                if (rr[u] < r1) load_keys4<KW>(keyp, rr[u], k[u]);
-#pragma unroll
-            for (int v = 0; v < NV; v++)
-#pragma unroll
-                for (int u = 0; u < U; u++)
-                    if (rr[u] < r1) {
-                        const uint4 q = __ldcs(reinterpret_cast<const uint4 *>(P.vals[v] + rr[u]));
-                        x[v][u][0] = q.x; x[v][u][1] = q.y; x[v][u][2] = q.z; x[v][u][3] = q.w;
-                    }
-            uint32_t idx[U][4];
-#pragma unroll
-            for (int u = 0; u < U; u++)
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    const int64_t r = rr[u] + e;
-                    idx[u][e] = 0xffffffffu;
-                    if (r >= r0 && r < r1) {
-                        if (LUT) {
-                            long long v;
-                            if constexpr (KW == 4) v = (P.key_dtype == HARK_U32 ? (long long)(uint32_t)k[u][e] : (long long)(int32_t)k[u][e]) - P.pk_min;
-                            else v = (long long)k[u][e] - P.pk_min;
-                            if (v >= 0 && v < P.pk_span) idx[u][e] = __ldg(P.lut + v) - 1u; // 0 (no match) -> 0xffffffff
-                        } else {
-                            idx[u][e] = (uint32_t)(ordkey_of<KW>(k[u][e], P.key_dtype) - P.g_lo - slot0);
-                        }
-                    }
-                }
-#pragma unroll
-            for (int u = 0; u < U; u++)
-#pragma unroll
-                for (int e = 0; e < 4; e++)
-                    if (idx[u][e] != 0xffffffffu) atomicAdd(&tab[idx[u][e]], 1u);
-#pragma unroll 1
-            for (int ai = 0; ai < P.nacc; ai++) {
-                const DAcc a = P.acc[ai];
-#pragma unroll
-                for (int v = 0; v < NV; v++)
-                    if (v == a.vcol) {
-#pragma unroll
-                        for (int u = 0; u < U; u++)
-#pragma unroll
-                            for (int e = 0; e < 4; e++)
-                                if (idx[u][e] != 0xffffffffu) acc_row(tab, K, idx[u][e], a, x[v][u][e]);
-                    }
-            }
+        constexpr int64_t STEP = (int64_t)AT * 4 * U;
+        for (int64_t g0 = r0 & ~(int64_t)3; g0 < r1; g0 += STEP) {
+            if (g0 >= r0 && g0 + STEP <= r1) dagg_step<KW, LUT, NV, U, false>(P, tab, keyp, g0, r0, r1, slot0, tid);
+            else dagg_step<KW, LUT, NV, U, true>(P, tab, keyp, g0, r0, r1, slot0, tid);
         }
     }
     __syncthreads();
@@ -818,76 +613,6 @@ int hk_col_minmax(hark_ctx *ctx, const void *col, int32_t dtype, int64_t n, uint
     return HARK_OK;
 }
 
-int hk_partition_pass(hark_ctx *ctx, int64_t n, const void *key, int kw, const hk_part_spec &spec, int nv,
-                      const void *const *vals, void **key_out, void **vals_out, unsigned long long **d_offsets) {
-    if (nv > PMAXV || spec.nbins < 1 || spec.nbins > 256 || (kw != 4 && kw != 8))
-        return ctx->fail(HARK_ERR_UNSUPPORTED, "partition_pass: unsupported shape");
-    *key_out = nullptr;
-    *d_offsets = nullptr;
-    for (int v = 0; v < nv; v++) vals_out[v] = nullptr;
-    Bufs tmp(ctx);
-    unsigned long long *offs = nullptr;
-    HK_TRY(ctx->dalloc((void **)&offs, 257 * sizeof(unsigned long long)));
-    struct Owner { // frees the outputs unless released
-        hark_ctx *ctx;
-        std::vector<void *> v;
-        bool keep = false;
-        ~Owner() {
-            if (!keep)
-                for (void *p : v) ctx->dfree(p);
-        }
-    } own{ctx, {offs}};
-    HK_CUDA(ctx, cudaMemsetAsync(offs, 0, 257 * sizeof(unsigned long long), ctx->stream));
-    PartHistParams H;
-    H.f = spec;
-    H.key = key;
-    H.n = n;
-    H.hist = offs;
-    const unsigned hg = grid_for(ctx, (n + 3) / 4, 4);
-    if (kw == 4) hk_part_hist_kernel<4><<<hg, 256, 0, ctx->stream>>>(H);
-    else hk_part_hist_kernel<8><<<hg, 256, 0, ctx->stream>>>(H);
-    HK_CHECK_LAUNCH(ctx);
-    hk_part_scan_kernel<<<1, 256, 0, ctx->stream>>>(offs);
-    HK_CHECK_LAUNCH(ctx);
-    ctx->count_launch(2);
-
-    PartParams P;
-    memset(&P, 0, sizeof P);
-    P.f = spec;
-    P.key_in = key;
-    void *ko = nullptr;
-    HK_TRY(ctx->dalloc(&ko, (size_t)std::max<int64_t>(n, 1) * kw));
-    own.v.push_back(ko);
-    P.key_out = ko;
-    for (int v = 0; v < nv; v++) {
-        void *vo = nullptr;
-        HK_TRY(ctx->dalloc(&vo, (size_t)std::max<int64_t>(n, 1) * 4));
-        own.v.push_back(vo);
-        P.val_in[v] = (const uint32_t *)vals[v];
-        P.val_out[v] = (uint32_t *)vo;
-    }
-    P.n = n;
-    P.num_tiles = (n + PTILE - 1) / PTILE;
-    P.offsets = offs;
-    uint64_t *status = nullptr;
-    const size_t status_words = (size_t)P.num_tiles * spec.nbins + 1;
-    HK_TRY(tmp.alloc((void **)&status, status_words * sizeof(uint64_t)));
-    HK_CUDA(ctx, cudaMemsetAsync(status, 0, status_words * sizeof(uint64_t), ctx->stream));
-    P.status = status + 1;
-    P.ticket = (unsigned long long *)status;
-    if (n > 0) {
-        int rc;
-        if (kw == 4) rc = nv == 0 ? launch_part<4, 0>(ctx, P) : nv == 1 ? launch_part<4, 1>(ctx, P) : nv == 2 ? launch_part<4, 2>(ctx, P) : launch_part<4, 3>(ctx, P);
-        else rc = nv == 0 ? launch_part<8, 0>(ctx, P) : nv == 1 ? launch_part<8, 1>(ctx, P) : nv == 2 ? launch_part<8, 2>(ctx, P) : launch_part<8, 3>(ctx, P);
-        if (rc != HARK_OK) return rc;
-    }
-    own.keep = true;
-    *key_out = ko;
-    for (int v = 0; v < nv; v++) vals_out[v] = P.val_out[v];
-    *d_offsets = offs;
-    return HARK_OK;
-}
-
 int hk_dense_groupby(hark_ctx *ctx, hark_table **out, const hk_dense_req &rq, bool *handled) {
     *handled = false;
     const int64_t n = rq.n;
@@ -990,7 +715,7 @@ int hk_dense_groupby(hark_ctx *ctx, hark_table **out, const hk_dense_req &rq, bo
     // lut mode: slice the lookup so that the slice being probed stays L2-resident
     int lut_bins = 1, lut_shift = 0;
     if (lut_mode) {
-        const int64_t slice_bytes = ctx->opt("join.lut_slice_bytes", 32ll << 20);
+        const int64_t slice_bytes = ctx->opt("join.lut_slice_bytes", 16ll << 20);
         const uint64_t lut_bytes = (uint64_t)rq.pk_span * 4ull;
         if ((int64_t)lut_bytes > slice_bytes * 3 / 2 && rq.nvals <= PMAXV) {
             lut_shift = floor_log2_u64((uint64_t)slice_bytes / 4);
@@ -1096,7 +821,7 @@ int hk_dense_groupby(hark_ctx *ctx, hark_table **out, const hk_dense_req &rq, bo
         }
 #undef HK_DAGG_PICK
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) kern<<<grid, AT, smem, ctx->stream>>>(P);
+        if (e == cudaSuccess) kern<<<grid, dagg_threads(rq.nvals), smem, ctx->stream>>>(P);
         if (e == cudaSuccess) e = cudaGetLastError();
         if (e != cudaSuccess) return ctx->fail(HARK_ERR_CUDA, std::string("dense aggregate: ") + cudaGetErrorString(e));
         ctx->count_launch();

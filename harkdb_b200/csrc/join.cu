@@ -128,19 +128,33 @@ __global__ void __launch_bounds__(256) hk_lut_build_kernel(const void *pk, int p
 }
 
 // slot lookup for the fused probe + aggregate (dense_agg.cu, lut mode):
-// lut[pk - pk_min] = (ordkey(dim.g) - g_lo) + 1, 0 = no such key.  Duplicate pks raise dup_flag.
+// lut[pk - pk_min] = (ordkey(dim.g) - g_lo) + 1, 0 = no such key.  Plain scattered stores (no atomics: an atomic's
+// round trip to a lookup that does not fit L2 is what bounds this kernel); a duplicate pk then simply overwrites,
+// and is caught afterwards because the number of non-empty entries falls short of the dimension's row count.
 __global__ void __launch_bounds__(256) hk_slot_lut_build_kernel(const void *pk, int pk_dtype, const void *g, int g_dtype,
                                                                  int64_t n_dim, long long pk_min, unsigned long long g_lo,
-                                                                 uint32_t *lut, unsigned int *dup_flag) {
+                                                                 uint32_t *lut) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_dim; i += stride) {
         const long long v = load_int(pk, pk_dtype, i) - pk_min;
         unsigned long long ord;
         if (g_dtype == HARK_I64) ord = hk_ordkey64(reinterpret_cast<const unsigned long long *>(g)[i], g_dtype);
         else ord = hk_ordkey32(reinterpret_cast<const uint32_t *>(g)[i], g_dtype);
-        const uint32_t old = atomicExch(&lut[v], (uint32_t)(ord - g_lo) + 1u);
-        if (old != 0) *dup_flag = 1u;
+        lut[v] = (uint32_t)(ord - g_lo) + 1u;
     }
+}
+
+__global__ void __launch_bounds__(256) hk_count_nonzero_kernel(const uint32_t *__restrict__ a, int64_t n, unsigned long long *out) {
+    unsigned long long c = 0;
+    const int64_t nvec = n / 4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        const uint4 v = reinterpret_cast<const uint4 *>(a)[i];
+        c += (v.x != 0) + (v.y != 0) + (v.z != 0) + (v.w != 0);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(n - nvec * 4)) c += a[nvec * 4 + threadIdx.x] != 0;
+    c = hk_warp_sum_u64(c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
 // gkey[i] = dim.g[row(fk[i])] and hit[i] = 1 when fk[i] has a match, else hit[i] = 0.
@@ -366,15 +380,40 @@ int hk_join_groupby(hark_ctx *ctx, hark_table **out, const hark_table *fact, con
             if (eligible) {
                 HK_TRY(hk_col_minmax(ctx, dim->cols[g_col].ptr, g_dtype, nd, &rq.g_lo, &rq.g_hi));
                 if (rq.g_hi - rq.g_lo < (1ull << 20)) {
-                    HK_CUDA(ctx, cudaMemsetAsync(dup, 0, sizeof(unsigned int), ctx->stream));
+                    unsigned long long *nz = (unsigned long long *)d_mm;
+                    HK_CUDA(ctx, cudaMemsetAsync(nz, 0, sizeof(unsigned long long), ctx->stream));
+                    // a lookup much larger than L2: bring the dimension rows into lookup-slice order first, so the
+                    // scattered stores below complete whole sectors while the slice is still L2-resident
+                    const void *pk_src = dim->cols[pk_col].ptr, *g_src = dim->cols[g_col].ptr;
+                    const int pkw = hk_dtype_size(dim->cols[pk_col].dtype);
+                    if ((uint64_t)span * 4ull > (96ull << 20) && gw == 4) {
+                        hk_part_spec ps;
+                        ps.dtype = dim->cols[pk_col].dtype;
+                        ps.base = pkw == 4 ? (uint64_t)(ps.dtype == HARK_U32 ? (uint32_t)pk_min : ((uint32_t)(int32_t)pk_min ^ 0x80000000u))
+                                           : ((uint64_t)pk_min ^ 0x8000000000000000ull);
+                        ps.span = (uint64_t)span;
+                        ps.shift = 22; // 4 Mi entries = 16 MB of lookup per bin
+                        while ((((uint64_t)span - 1) >> ps.shift) + 1 > 256) ps.shift++;
+                        ps.nbins = (int)((((uint64_t)span - 1) >> ps.shift) + 1);
+                        void *pko = nullptr, *go[3] = {nullptr, nullptr, nullptr};
+                        unsigned long long *offs = nullptr;
+                        const void *gv[1] = {g_src};
+                        HK_TRY(hk_partition_pass(ctx, nd, pk_src, pkw, ps, 1, gv, &pko, go, &offs));
+                        bufs.adopt(pko);
+                        bufs.adopt(go[0]);
+                        bufs.adopt(offs);
+                        pk_src = pko;
+                        g_src = go[0];
+                    }
                     hk_slot_lut_build_kernel<<<grid_for(ctx, nd), 256, 0, ctx->stream>>>(
-                        dim->cols[pk_col].ptr, dim->cols[pk_col].dtype, dim->cols[g_col].ptr, g_dtype, nd, pk_min,
-                        (unsigned long long)rq.g_lo, lut, dup);
+                        pk_src, dim->cols[pk_col].dtype, g_src, g_dtype, nd, pk_min, (unsigned long long)rq.g_lo, lut);
                     HK_CHECK_LAUNCH(ctx);
-                    ctx->count_launch();
-                    HK_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, dup, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+                    hk_count_nonzero_kernel<<<grid_for(ctx, (int64_t)span / 4 + 1), 256, 0, ctx->stream>>>(lut, (int64_t)span, nz);
+                    HK_CHECK_LAUNCH(ctx);
+                    ctx->count_launch(2);
+                    HK_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, nz, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
                     HK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                    if (((unsigned int *)ctx->h_scalars)[0] != 0)
+                    if ((int64_t)ctx->h_scalars[0] != nd)
                         return ctx->fail(HARK_ERR_ARG, "join_groupby: dim.pk is not unique");
                     rq.lut = lut;
                     rq.pk_min = pk_min;

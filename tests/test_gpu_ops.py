@@ -317,6 +317,21 @@ def test_join_groupby_config5_shape(gb_impl):
     r.free(); dim.free(); fact.free()
 
 
+def test_join_groupby_duplicate_dim_key_and_misses(gb_impl):
+    env = get_env()
+    from harkdb_b200.hark_ffi import HarkError
+    dim = env.from_columns([np.array([5, 9, 5, 7], dtype=np.int32), np.array([1, 2, 3, 4], dtype=np.int32)])
+    fact = env.from_columns([np.array([5, 7, 9, 9, 100, -3], dtype=np.int32), np.array([1, 2, 3, 4, 5, 6], dtype=np.int32)])
+    with pytest.raises(HarkError, match="not unique"):
+        env.join_groupby(fact, dim, 0, 0, 1, [1], [NO.AGG_SUM])
+    dim2 = env.from_columns([np.array([5, 9, 7], dtype=np.int32), np.array([40, 40, -2], dtype=np.int32)])
+    r = env.join_groupby(fact, dim2, 0, 0, 1, [1, 1], [NO.AGG_SUM, NO.AGG_COUNT])      # fk 100 and -3 match nothing
+    k, s, c = r.columns()
+    assert k.tolist() == [-2, 40] and s.tolist() == [2, 8] and c.tolist() == [1, 3]
+    for x in (r, dim, dim2, fact):
+        x.free()
+
+
 # ---------------------------------------------------------------- SQL through FutharkContext
 def test_sql_groupby_orderby_join():
     import pandas as pd
