@@ -39,20 +39,25 @@ class FutharkContext:
         del self.tables[table_name]
 
     # ---- helpers ----
+    @staticmethod
+    def _is_table(t):
+        """A resident table handle (hark_ffi.DeviceTable, or a sharded.ShardTable) rather than a host array."""
+        return isinstance(t, DeviceTable) or (hasattr(t, "dtypes") and hasattr(t, "free"))
+
     def _is_int_col(self, t, col):
-        if isinstance(t, DeviceTable):
+        if self._is_table(t):
             return t.dtypes[col] in (I32, U32, I64)
         return np.asarray(t).dtype.kind in "iub"
 
     def _is_u32_compatible(self, t):
-        if isinstance(t, DeviceTable):
+        if self._is_table(t):
             return all(d in (I32, U32) for d in t.dtypes)
         a = np.asarray(t)
         return a.dtype.kind in "iub"
 
     def _as_device(self, t):
         """(device table, temporary?)"""
-        if isinstance(t, DeviceTable):
+        if self._is_table(t):
             return t, False
         from .table import entry_dtype
         return self.FutEnv.to_device(t, entry_dtype(np.asarray(t))), True

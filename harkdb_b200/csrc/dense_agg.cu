@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(1024) hk_dense_scan_kernel(const uint32_t *cou
     }
 }
 
-enum OutKind { O_COUNT = 0, O_COPY32, O_LOW32_OF_U64, O_AVG_S64, O_AVG_U64, O_AVG_F64, O_F32_OF_F64, O_F64 };
+enum OutKind { O_COUNT = 0, O_COPY32, O_LOW32_OF_U64, O_AVG_S64, O_AVG_U64, O_AVG_F64, O_F32_OF_F64, O_F64, O_F64_OF_S64, O_F64_OF_U64 };
 struct OutSpec {
     int kind;
     const void *src; // dense accumulator
@@ -536,6 +536,8 @@ __global__ void __launch_bounds__(CT) hk_dense_compact_kernel(const __grid_const
             case O_AVG_U64: reinterpret_cast<double *>(o.dst)[g] = (double)reinterpret_cast<const unsigned long long *>(o.src)[r] / (double)cnt[e]; break;
             case O_AVG_F64: reinterpret_cast<double *>(o.dst)[g] = reinterpret_cast<const double *>(o.src)[r] / (double)cnt[e]; break;
             case O_F32_OF_F64: reinterpret_cast<float *>(o.dst)[g] = (float)reinterpret_cast<const double *>(o.src)[r]; break;
+            case O_F64_OF_S64: reinterpret_cast<double *>(o.dst)[g] = (double)reinterpret_cast<const long long *>(o.src)[r]; break;
+            case O_F64_OF_U64: reinterpret_cast<double *>(o.dst)[g] = (double)reinterpret_cast<const unsigned long long *>(o.src)[r]; break;
             default: reinterpret_cast<double *>(o.dst)[g] = reinterpret_cast<const double *>(o.src)[r]; break;
             }
         }
@@ -639,7 +641,7 @@ int hk_dense_groupby(hark_ctx *ctx, hark_table **out, const hk_dense_req &rq, bo
     // exact 64-bit sums serve both SUM (low word) and AVG; if a column only needs SUM, a 32-bit sum is enough
     std::vector<bool> col_needs_avg((size_t)std::max(rq.nvals, 1), false);
     for (int j = 0; j < rq.c; j++)
-        if (rq.agg_code[j] == HARK_AGG_AVG && rq.agg_val[j] >= 0) col_needs_avg[rq.agg_val[j]] = true;
+        if ((rq.agg_code[j] == HARK_AGG_AVG || rq.agg_code[j] == HARK_AGG_SUMF64) && rq.agg_val[j] >= 0) col_needs_avg[rq.agg_val[j]] = true;
     struct OutPlan {
         int okind, acc;
         int32_t dtype;
@@ -663,6 +665,10 @@ int hk_dense_groupby(hark_ctx *ctx, hark_table **out, const hk_dense_req &rq, bo
         case HARK_AGG_AVG:
             if (is_f) outs.push_back({O_AVG_F64, acc_index(vi, A_FSUM, 2), HARK_F64});
             else outs.push_back({is_s ? O_AVG_S64 : O_AVG_U64, acc_index(vi, is_s ? A_SUM64S : A_SUM64U, 2), HARK_F64});
+            break;
+        case HARK_AGG_SUMF64:
+            if (is_f) outs.push_back({O_F64, acc_index(vi, A_FSUM, 2), HARK_F64});
+            else outs.push_back({is_s ? O_F64_OF_S64 : O_F64_OF_U64, acc_index(vi, is_s ? A_SUM64S : A_SUM64U, 2), HARK_F64});
             break;
         case HARK_AGG_PROD:
             if (is_f) outs.push_back({O_F32_OF_F64, acc_index(vi, A_FPROD, 2), HARK_F32});

@@ -454,7 +454,7 @@ int hk_segmented_aggregate(hark_ctx *ctx, hark_table **out, int64_t n, const voi
         const int code = aggs[j].second;
         const int32_t vdt = aggs[j].first >= 0 ? val_dtypes[aggs[j].first] : HARK_I64;
         if (code == HARK_AGG_COUNT) odt[1 + j] = HARK_I64;
-        else if (code == HARK_AGG_AVG) odt[1 + j] = HARK_F64;
+        else if (code == HARK_AGG_AVG || code == HARK_AGG_SUMF64) odt[1 + j] = HARK_F64;
         else odt[1 + j] = pinned_u32 ? HARK_U32 : vdt;
     }
     if (n == 0) return hk_table_alloc(ctx, out, 0, 0, odt.data(), 1 + c);
@@ -509,7 +509,7 @@ int hk_segmented_aggregate(hark_ctx *ctx, hark_table **out, int64_t n, const voi
             F.dst[j] = t->cols[1 + j].ptr;
             continue;
         }
-        if (code < HARK_AGG_PROD || code > HARK_AGG_AVG) code = HARK_AGG_MIN; // groupby.fut:41
+        if (code < HARK_AGG_PROD || code > HARK_AGG_SUMF64) code = HARK_AGG_MIN; // groupby.fut:41
         const int vi = aggs[j].first;
         const int32_t vdt = pinned_u32 ? HARK_U32 : val_dtypes[vi];
         AggSpec &ag = P.agg[nagg++];
@@ -518,10 +518,10 @@ int hk_segmented_aggregate(hark_ctx *ctx, hark_table **out, int64_t n, const voi
         const bool is_f = (vdt == HARK_F32 || vdt == HARK_F64);
         const bool is_signed = (vdt == HARK_I32 || vdt == HARK_I64);
         const int w = hk_dtype_size(vdt);
-        if (code == HARK_AGG_AVG || (is_f && (code == HARK_AGG_SUM || code == HARK_AGG_PROD))) {
+        if (code == HARK_AGG_AVG || code == HARK_AGG_SUMF64 || (is_f && (code == HARK_AGG_SUM || code == HARK_AGG_PROD))) {
             ag.cls = CLS_F64ACC;
             ag.op = code == HARK_AGG_PROD ? OP_PROD : OP_SUM;
-            if (code == HARK_AGG_AVG || vdt == HARK_F64) {
+            if (code == HARK_AGG_AVG || code == HARK_AGG_SUMF64 || vdt == HARK_F64) {
                 ag.acc = t->cols[1 + j].ptr; // f64 output column doubles as the accumulator
                 if (code == HARK_AGG_AVG) {
                     F.kind[j] = FIN_AVG;
@@ -612,7 +612,7 @@ int hk_groupby(hark_ctx *ctx, hark_table **out, const hark_table *db, int32_t g_
         for (int64_t j = 0; j < c && eligible; j++) {
             int code = ops[j];
             if (pinned_u32 && (code < HARK_AGG_PROD || code > HARK_AGG_MIN)) code = HARK_AGG_MIN; // groupby.fut:41
-            if (!pinned_u32 && (code < HARK_AGG_PROD || code > HARK_AGG_AVG)) code = HARK_AGG_MIN;
+            if (!pinned_u32 && (code < HARK_AGG_PROD || code > HARK_AGG_SUMF64)) code = HARK_AGG_MIN;
             rq.agg_code[j] = code;
             if (code == HARK_AGG_COUNT) {
                 rq.agg_val[j] = -1;

@@ -28,7 +28,7 @@ DTYPE_CODES = {v: k for k, v in NP_DTYPES.items()}
 GT, GE, LT, LE, EQ, NE = 0, 1, 2, 3, 4, 5
 CMP_CODES = {">": GT, ">=": GE, "<": LT, "<=": LE, "=": EQ, "==": EQ, "!=": NE, "<>": NE,
              "gt": GT, "gte": GE, "lt": LT, "lte": LE, "eq": EQ, "neq": NE}
-AGG_KEY, AGG_PROD, AGG_SUM, AGG_MAX, AGG_MIN, AGG_COUNT, AGG_AVG = 0, 1, 2, 3, 4, 5, 6
+AGG_KEY, AGG_PROD, AGG_SUM, AGG_MAX, AGG_MIN, AGG_COUNT, AGG_AVG, AGG_SUMF64 = 0, 1, 2, 3, 4, 5, 6, 7
 GEN_UNIFORM, GEN_AFFINE, GEN_CONST = 0, 1, 2
 
 STATUS = {0: "HARK_OK", 1: "HARK_ERR_ARG", 2: "HARK_ERR_CUDA", 3: "HARK_ERR_OOM", 4: "HARK_ERR_UNSUPPORTED"}
@@ -91,6 +91,11 @@ SIGNATURES = {
                                           C.c_int64]),
     "hark_table_sort_by": (C.c_int, [_P, C.POINTER(_P), _P, C.c_int32]),
     "hark_table_partition_by_hash": (C.c_int, [_P, C.POINTER(_P), _P, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
+    "hark_table_partition_by_splitters": (C.c_int, [_P, C.POINTER(_P), _P, _I32P, _I32P, C.c_int64,
+                                                    C.POINTER(C.c_uint64), C.c_int32, C.POINTER(C.c_int64)]),
+    "hark_table_sample_order_keys": (C.c_int, [_P, _P, _I32P, _I32P, C.c_int64, C.POINTER(C.c_int64), C.c_int64,
+                                               C.POINTER(C.c_uint64)]),
+    "hark_entry_groupby_finalize": (C.c_int, [_P, C.POINTER(_P), _P, _I32P, C.c_int64]),
     "hark_table_slice": (C.c_int, [_P, C.POINTER(_P), _P, C.c_int64, C.c_int64]),
     "hark_table_concat": (C.c_int, [_P, C.POINTER(_P), _P, _P]),
     "hark_stats_last": (C.c_int, [_P, C.POINTER(HarkStats)]),
@@ -443,6 +448,39 @@ class Futhark:
         self._check(self.lib.hark_table_partition_by_hash(self.ctx, C.byref(h), t.handle, int(key_col), nparts,
                                                           counts))
         return DeviceTable(self, h.value), [int(x) for x in counts]
+
+    def partition_by_splitters(self, t: DeviceTable, key_cols, desc, splitters: np.ndarray,
+                               nparts: int) -> Tuple[DeviceTable, List[int]]:
+        """Stable range partition: bucket of a row = number of splitter tuples <= its key tuple.
+        `splitters`: uint64 order keys [nparts-1][len(key_cols)], ascending (see sample_order_keys)."""
+        kc = _i32arr(key_cols)
+        d = _i32arr(desc if desc is not None else [0] * len(kc))
+        sp = np.ascontiguousarray(np.asarray(splitters, dtype=np.uint64).reshape(-1))
+        if sp.size != (nparts - 1) * len(kc):
+            raise HarkError(1, "partition_by_splitters: need (nparts-1) x nk splitter keys")
+        h = C.c_void_p()
+        counts = (C.c_int64 * nparts)()
+        self._check(self.lib.hark_table_partition_by_splitters(
+            self.ctx, C.byref(h), t.handle, _i32p(kc), _i32p(d), len(kc),
+            sp.ctypes.data_as(C.POINTER(C.c_uint64)) if sp.size else None, nparts, counts))
+        return DeviceTable(self, h.value), [int(x) for x in counts]
+
+    def sample_order_keys(self, t: DeviceTable, key_cols, desc, rows) -> np.ndarray:
+        """uint64 order keys [len(rows)][len(key_cols)] of the given rows (ORDER BY's key mapping)."""
+        kc = _i32arr(key_cols)
+        d = _i32arr(desc if desc is not None else [0] * len(kc))
+        r = np.ascontiguousarray(np.asarray(rows, dtype=np.int64).reshape(-1))
+        out = np.empty((len(r), len(kc)), dtype=np.uint64)
+        self._check(self.lib.hark_table_sample_order_keys(
+            self.ctx, t.handle, _i32p(kc), _i32p(d), len(kc), r.ctypes.data_as(C.POINTER(C.c_int64)), len(r),
+            out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out
+
+    def groupby_finalize(self, merged: DeviceTable, ops) -> DeviceTable:
+        o = _i32arr(ops)
+        h = C.c_void_p()
+        self._check(self.lib.hark_entry_groupby_finalize(self.ctx, C.byref(h), merged.handle, _i32p(o), len(o)))
+        return DeviceTable(self, h.value)
 
     def slice(self, t: DeviceTable, row0: int, nrows: int) -> DeviceTable:
         h = C.c_void_p()

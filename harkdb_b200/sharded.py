@@ -1,0 +1,474 @@
+"""Multi-GPU layer: one process per GPU, tables row-range partitioned, `torch.distributed` for the plumbing.
+
+The reference is single-process, single-context (FutharkContext.py:41); this layer is new.  It sits
+ABOVE the C-ABI: every rank owns one libhark context (one GPU) and the same SPMD program runs on all ranks.
+
+  filter / projection   shard-local, no collective; the global result is the concatenation in rank order, which
+                        is the single-GPU row order.
+  GROUP BY              shard-local partial aggregation (K2/K4) -> range repartition of the PARTIAL GROUPS by
+                        sampled key splitters (K8b + all-to-all) -> merge (same operators; AVG travels as an f64 sum
+                        and an i64 count) -> HAVING.  Rank r ends up with the r-th key range, locally key-ordered, so
+                        concatenation in rank order is the single-GPU output order.
+  ORDER BY              sampled splitters over the key tuples -> stable K8b partition -> all-to-all -> local stable
+                        K3 sort.  Equal key tuples all land on one rank and arrive in (source rank, row) order, so
+                        the global result is stable with respect to the global input row order, like one GPU.
+  JOIN + GROUP BY       the dimension table is all-gathered (dim << fact), every rank probes and pre-aggregates its
+                        own fact shard, partial groups merge as in GROUP BY.
+  JOIN                  both sides range-repartitioned by the join key with common splitters, joined locally.
+
+`ShardedEnv` exposes the same methods as `hark_ffi.Futhark`, so `FutharkContext.sql` runs unchanged on top of it
+(`ShardedFutharkContext`).  The local operator engine is pluggable: `HarkEngine` (libhark.so, CUDA tensors, NCCL) is
+the product; the CPU tests drive the identical host logic over `gloo` with a numpy stand-in engine.
+"""
+
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+I32, U32, I64, F32, F64 = 0, 1, 2, 3, 4
+AGG_KEY, AGG_PROD, AGG_SUM, AGG_MAX, AGG_MIN, AGG_COUNT, AGG_AVG, AGG_SUMF64 = 0, 1, 2, 3, 4, 5, 6, 7
+NP_DTYPES = {I32: np.dtype(np.int32), U32: np.dtype(np.uint32), I64: np.dtype(np.int64),
+             F32: np.dtype(np.float32), F64: np.dtype(np.float64)}
+
+
+def _torch_dtype(code):
+    import torch
+    return {I32: torch.int32, U32: torch.int32, I64: torch.int64, F32: torch.float32, F64: torch.float64}[code]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# host logic shared by every engine
+# ------------------------------------------------------------------------------------------------------------
+def expand_partial_ops(s_cols: Sequence[int], ops: Sequence[int], pinned_u32: bool = False):
+    """Aggregates of the query -> (columns, codes) of the shard-local partial aggregation.
+    AVG becomes an f64 sum and a count; every other aggregate is its own partial."""
+    p_s, p_ops = [], []
+    for c, op in zip(s_cols, ops):
+        op = int(op)
+        if pinned_u32:
+            op = op if op in (AGG_PROD, AGG_SUM, AGG_MAX, AGG_MIN) else AGG_MIN        # groupby.fut:41
+        elif op < AGG_PROD or op > AGG_SUMF64:
+            op = AGG_MIN
+        if op == AGG_AVG:
+            p_s += [c, c]
+            p_ops += [AGG_SUMF64, AGG_COUNT]
+        else:
+            p_s.append(c)
+            p_ops.append(op)
+    return p_s, p_ops
+
+
+def merge_ops_for(p_ops: Sequence[int]) -> List[int]:
+    """Operator that combines two partials of each partial column (counts and sums add)."""
+    return [AGG_SUM if op in (AGG_SUM, AGG_COUNT, AGG_SUMF64) else op for op in p_ops]
+
+
+def final_ops_for(ops: Sequence[int], pinned_u32: bool = False) -> List[int]:
+    out = []
+    for op in ops:
+        op = int(op)
+        if pinned_u32:
+            op = op if op in (AGG_PROD, AGG_SUM, AGG_MAX, AGG_MIN) else AGG_MIN
+        elif op < AGG_PROD or op > AGG_SUMF64:
+            op = AGG_MIN
+        out.append(op)
+    return out
+
+
+def sample_positions(n_local: int, nsamples: int) -> np.ndarray:
+    """Evenly spaced sample rows of a shard (deterministic)."""
+    if n_local <= 0:
+        return np.zeros(0, dtype=np.int64)
+    s = min(n_local, nsamples)
+    return ((np.arange(s, dtype=np.float64) + 0.5) * (n_local / s)).astype(np.int64).clip(0, n_local - 1)
+
+
+def pick_splitters(samples: Sequence[np.ndarray], weights: Sequence[float], nparts: int, nk: int) -> np.ndarray:
+    """Weighted quantiles of the gathered sample tuples -> (nparts-1, nk) uint64 splitters, ascending.
+    samples[r] is rank r's (s_r, nk) array of order keys, each row standing for weights[r] table rows."""
+    rows = [np.asarray(s, dtype=np.uint64).reshape(-1, nk) for s in samples]
+    allk = np.concatenate(rows, axis=0) if rows else np.zeros((0, nk), np.uint64)
+    w = np.concatenate([np.full(len(r), float(wt)) for r, wt in zip(rows, weights)]) if rows else np.zeros(0)
+    if len(allk) == 0:
+        return np.zeros((nparts - 1, nk), dtype=np.uint64)
+    order = np.lexsort(tuple(allk[:, j] for j in range(nk - 1, -1, -1)))
+    allk, w = allk[order], w[order]
+    cw = np.cumsum(w)
+    total = cw[-1]
+    out = np.empty((nparts - 1, nk), dtype=np.uint64)
+    for p in range(1, nparts):
+        i = int(np.searchsorted(cw, total * p / nparts, side="left"))
+        out[p - 1] = allk[min(i, len(allk) - 1)]
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# engines
+# ------------------------------------------------------------------------------------------------------------
+class _CAI:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+_TYPESTR = {I32: "<i4", U32: "<i4", I64: "<i8", F32: "<f4", F64: "<f8"}     # u32 travels as its i32 bit pattern
+
+
+class HarkEngine:
+    """The product engine: libhark.so on this rank's GPU; tables are hark_ffi.DeviceTable."""
+
+    def __init__(self, device: int = -1):
+        import torch
+        from . import hark_ffi
+        if device >= 0:
+            torch.cuda.set_device(device)
+        self.torch = torch
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        # one stream for torch collectives and libhark kernels: no cross-stream ordering to manage
+        self.env = hark_ffi.Futhark(device=self.device.index, stream=torch.cuda.current_stream().cuda_stream)
+
+    # ---- tables ----
+    def to_device(self, arr, dtype=None):
+        return self.env.to_device(arr, dtype)
+
+    def from_columns(self, cols):
+        return self.env.from_columns(cols)
+
+    def columns_torch(self, t):
+        n, m = t.shape
+        dts = t.dtypes
+        out = []
+        for c in range(m):
+            if n == 0:
+                out.append(self.torch.empty(0, dtype=_torch_dtype(dts[c]), device=self.device))
+            else:
+                out.append(self.torch.as_tensor(_CAI(t.column_ptr(c), n, _TYPESTR[dts[c]]), device=self.device))
+        return out
+
+    def from_torch(self, cols, dtypes):
+        n = int(cols[0].shape[0]) if cols else 0
+        cols = [c.contiguous() for c in cols]
+        if n == 0:
+            return self.env.from_columns([np.zeros(0, dtype=NP_DTYPES[d]) for d in dtypes])
+        t = self.env.from_device_pointers([int(c.data_ptr()) for c in cols], list(dtypes), n)
+        t._keepalive = cols          # the table borrows the tensors' memory
+        return t
+
+    def empty(self, n, dtype_code):
+        return self.torch.empty(n, dtype=_torch_dtype(dtype_code), device=self.device)
+
+    def to_numpy_columns(self, t):
+        return t.columns()
+
+    def sync(self):
+        self.env.sync()
+
+    def __getattr__(self, name):      # every operator entry is the local env's
+        return getattr(self.env, name)
+
+
+class ShardTable:
+    """A table whose rows are spread over the ranks; `local` is this rank's shard (an engine table)."""
+
+    def __init__(self, senv: "ShardedEnv", local):
+        self._senv = senv
+        self.local = local
+
+    @property
+    def dtypes(self):
+        return self.local.dtypes
+
+    @property
+    def shape(self):
+        return self.local.shape
+
+    def free(self):
+        if self.local is not None:
+            self.local.free()
+            self.local = None
+
+
+class ShardedEnv:
+    """Same call surface as hark_ffi.Futhark, over row-range shards (see module docstring)."""
+
+    def __init__(self, engine, group=None, oversample: int = 64):
+        import torch.distributed as dist
+        self.dist = dist
+        self.engine = engine
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.oversample = oversample
+
+    # ---- plumbing ----
+    def _wrap(self, local) -> ShardTable:
+        return ShardTable(self, local)
+
+    def _as_shard(self, db, dtype=None) -> Tuple[ShardTable, bool]:
+        if isinstance(db, ShardTable):
+            return db, False
+        return self.to_device(db, dtype), True
+
+    def to_device(self, arr, dtype=None) -> ShardTable:
+        """Every rank passes the SAME host array; rank r keeps rows [r*n/W, (r+1)*n/W)."""
+        arr = np.asarray(arr)
+        n = arr.shape[0]
+        lo, hi = self.rank * n // self.world, (self.rank + 1) * n // self.world
+        from .hark_ffi import convert_for_entry
+        if dtype is not None:
+            arr = convert_for_entry(arr, dtype, "table")     # range check on the whole table, like one GPU
+        return self._wrap(self.engine.to_device(np.ascontiguousarray(arr[lo:hi]), None))
+
+    def all_counts(self, n_local: int) -> List[int]:
+        if self.world == 1:
+            return [n_local]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, int(n_local), group=self.group)
+        return [int(x) for x in out]
+
+    def exchange(self, local, counts: Sequence[int]):
+        """Rows of `local` are grouped by destination (counts[d] rows for rank d, in order).  Returns the engine
+        table made of what every rank sent here, in source-rank order."""
+        import torch
+        eng, dist = self.engine, self.dist
+        dts = local.dtypes
+        cols = eng.columns_torch(local)
+        dev = cols[0].device if cols else "cpu"
+        send = torch.tensor(list(counts), dtype=torch.int64, device=dev)
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=self.group)
+        recv_l = [int(x) for x in recv.cpu().tolist()]
+        outs = []
+        for c, col in enumerate(cols):
+            out = torch.empty(sum(recv_l), dtype=col.dtype, device=dev)
+            dist.all_to_all_single(out, col.contiguous(), recv_l, list(counts), group=self.group)
+            outs.append(out)
+        return eng.from_torch(outs, dts)
+
+    def allgather_table(self, local):
+        """Every rank gets all shards, concatenated in rank order."""
+        import torch
+        eng, dist = self.engine, self.dist
+        if self.world == 1:
+            return local, False
+        dts = local.dtypes
+        cols = eng.columns_torch(local)
+        ns = self.all_counts(local.shape[0])
+        mx = max(ns + [1])
+        outs = []
+        for col in cols:
+            pad = torch.zeros(mx, dtype=col.dtype, device=col.device)
+            pad[: col.shape[0]] = col
+            parts = [torch.empty_like(pad) for _ in range(self.world)]
+            dist.all_gather(parts, pad, group=self.group)
+            outs.append(torch.cat([p[: ns[r]] for r, p in enumerate(parts)]))
+        return eng.from_torch(outs, dts), True
+
+    def choose_splitters(self, local, key_cols, desc) -> np.ndarray:
+        nk = len(key_cols)
+        n_local = local.shape[0]
+        pos = sample_positions(n_local, self.oversample * self.world)
+        mine = self.engine.sample_order_keys(local, key_cols, desc, pos) if len(pos) else np.zeros((0, nk), np.uint64)
+        gathered = [None] * self.world
+        self.dist.all_gather_object(gathered, (mine, n_local / max(len(pos), 1)), group=self.group)
+        return pick_splitters([g[0] for g in gathered], [g[1] for g in gathered], self.world, nk)
+
+    def repartition(self, local, key_cols, desc, splitters=None):
+        """Range-repartition a shard by key tuple; returns the rows this rank now owns (source-rank order)."""
+        if splitters is None:
+            splitters = self.choose_splitters(local, key_cols, desc)
+        part, counts = self.engine.partition_by_splitters(local, key_cols, desc, splitters, self.world)
+        try:
+            return self.exchange(part, counts)
+        finally:
+            part.free()
+
+    # ---- result collection ----
+    def from_futhark(self, t: ShardTable) -> np.ndarray:
+        """Global result as a row-major ndarray on every rank (FutharkContext.py:66,71 `from_futhark`)."""
+        full, tmp = self.allgather_table(t.local)
+        try:
+            cols = self.engine.to_numpy_columns(full)
+        finally:
+            if tmp:
+                full.free()
+        dts = t.dtypes
+        if not cols:
+            return np.empty((0, 0), dtype=np.int32)
+        if len(set(dts)) == 1:
+            return np.ascontiguousarray(np.stack(cols, axis=1))
+        return np.stack([c.astype(np.float64) for c in cols], axis=1)
+
+    def gather_columns(self, t: ShardTable) -> List[np.ndarray]:
+        full, tmp = self.allgather_table(t.local)
+        try:
+            return self.engine.to_numpy_columns(full)
+        finally:
+            if tmp:
+                full.free()
+
+    # ---- shard-local operators ----
+    def query_sel(self, db, cols) -> ShardTable:
+        t, tmp = self._as_shard(db, np.int32)
+        try:
+            return self._wrap(self.engine.query_sel(t.local, cols))
+        finally:
+            if tmp:
+                t.free()
+
+    def query_filter(self, db, cols, preds) -> ShardTable:
+        t, tmp = self._as_shard(db)
+        try:
+            return self._wrap(self.engine.query_filter(t.local, cols, preds))
+        finally:
+            if tmp:
+                t.free()
+
+    # ---- GROUP BY ----
+    def _merge_groups(self, part, ops, pinned_u32, having=()):
+        """part: shard-local partial groups [key, partials...] (consumed).  Returns this rank's final groups."""
+        eng = self.engine
+        p_ops = expand_partial_ops(list(range(len(ops))), ops, pinned_u32)[1]
+        if self.world > 1:
+            recv = self.repartition(part, [0], [0])
+            part.free()
+            m = recv.shape[1]
+            if pinned_u32:
+                merged = eng.query_groupby(recv, 0, list(range(1, m)), merge_ops_for(p_ops))
+            else:
+                merged = eng.query_groupby_ex(recv, 0, list(range(1, m)), merge_ops_for(p_ops))
+            recv.free()
+        else:
+            merged = part
+        if pinned_u32:
+            return merged
+        final = eng.groupby_finalize(merged, final_ops_for(ops))
+        merged.free()
+        if having:
+            f2 = eng.query_filter(final, list(range(final.shape[1])), list(having))
+            final.free()
+            final = f2
+        return final
+
+    def query_groupby(self, db, g_col, s_cols, t_cols) -> ShardTable:
+        """main.fut:9 semantics (u32, codes 0-4) over shards."""
+        t, tmp = self._as_shard(db, np.uint32)
+        try:
+            s_cols, t_cols = [int(x) for x in s_cols], [int(x) for x in t_cols]
+            if len(t_cols) < len(s_cols):
+                from .hark_ffi import HarkError
+                raise HarkError(1, "t_cols shorter than s_cols (groupby.fut:47)")
+            p_s, p_ops = expand_partial_ops(s_cols, t_cols[: len(s_cols)], pinned_u32=True)
+            part = self.engine.query_groupby(t.local, g_col, p_s, p_ops)
+            return self._wrap(self._merge_groups(part, t_cols[: len(s_cols)], True))
+        finally:
+            if tmp:
+                t.free()
+
+    def query_groupby_ex(self, db, g_col, s_cols, ops, having=()) -> ShardTable:
+        t, tmp = self._as_shard(db)
+        try:
+            p_s, p_ops = expand_partial_ops([int(x) for x in s_cols], ops)
+            part = self.engine.query_groupby_ex(t.local, g_col, p_s, p_ops)
+            return self._wrap(self._merge_groups(part, [int(x) for x in ops], False, having))
+        finally:
+            if tmp:
+                t.free()
+
+    # ---- ORDER BY ----
+    def query_orderby(self, db, cols, key_cols, desc=None) -> ShardTable:
+        t, tmp = self._as_shard(db)
+        try:
+            cols, key_cols = [int(x) for x in cols], [int(x) for x in key_cols]
+            desc = [int(x) for x in (desc if desc is not None else [0] * len(key_cols))]
+            if self.world == 1 or not key_cols:
+                return self._wrap(self.engine.query_orderby(t.local, cols, key_cols, desc))
+            need = list(dict.fromkeys(cols + key_cols))          # only these columns cross NVLink
+            m = t.shape[1]
+            proj = t.local if need == list(range(m)) else self.engine.query_filter(t.local, need, [])
+            try:
+                k2 = [need.index(k) for k in key_cols]
+                recv = self.repartition(proj, k2, desc)
+            finally:
+                if proj is not t.local:
+                    proj.free()
+            try:
+                return self._wrap(self.engine.query_orderby(recv, [need.index(c) for c in cols], k2, desc))
+            finally:
+                recv.free()
+        finally:
+            if tmp:
+                t.free()
+
+    # ---- JOIN ----
+    def join_groupby(self, fact, dim, fk_col, pk_col, g_col, s_cols, ops) -> ShardTable:
+        tf, tmpf = self._as_shard(fact)
+        td, tmpd = self._as_shard(dim)
+        try:
+            dim_full, dtmp = self.allgather_table(td.local)          # dim << fact: broadcast the build side
+            try:
+                p_s, p_ops = expand_partial_ops([int(x) for x in s_cols], ops)
+                part = self.engine.join_groupby(tf.local, dim_full, fk_col, pk_col, g_col, p_s, p_ops)
+            finally:
+                if dtmp:
+                    dim_full.free()
+            return self._wrap(self._merge_groups(part, [int(x) for x in ops], False))
+        finally:
+            if tmpf:
+                tf.free()
+            if tmpd:
+                td.free()
+
+    def join(self, db1, db2, col1, col2, cols1, cols2) -> ShardTable:
+        """join.fut:52 semantics over shards: both sides range-repartitioned by the key with common splitters."""
+        t1, tmp1 = self._as_shard(db1, np.uint32)
+        t2, tmp2 = self._as_shard(db2, np.uint32)
+        try:
+            if self.world == 1:
+                return self._wrap(self.engine.join(t1.local, t2.local, col1, col2, cols1, cols2))
+            for t, c in ((t1, col1), (t2, col2)):
+                if t.dtypes[c] != U32:
+                    from .hark_ffi import HarkError
+                    raise HarkError(1, "sharded join: key columns must be stored as u32 (the reference's key order)")
+            # splitters from both sides' keys, so neither side can overload a rank
+            nk = 1
+            s1 = self._samples(t1.local, [col1])
+            s2 = self._samples(t2.local, [col2])
+            gathered = [None] * self.world
+            self.dist.all_gather_object(gathered, (s1, s2), group=self.group)
+            sp = pick_splitters([g[0][0] for g in gathered] + [g[1][0] for g in gathered],
+                                [g[0][1] for g in gathered] + [g[1][1] for g in gathered], self.world, nk)
+            r1 = self.repartition(t1.local, [col1], [0], sp)
+            r2 = self.repartition(t2.local, [col2], [0], sp)
+            try:
+                return self._wrap(self.engine.join(r1, r2, col1, col2, cols1, cols2))
+            finally:
+                r1.free()
+                r2.free()
+        finally:
+            if tmp1:
+                t1.free()
+            if tmp2:
+                t2.free()
+
+    def _samples(self, local, key_cols):
+        n_local = local.shape[0]
+        pos = sample_positions(n_local, self.oversample * self.world)
+        k = self.engine.sample_order_keys(local, key_cols, [0] * len(key_cols), pos) if len(pos) else \
+            np.zeros((0, len(key_cols)), np.uint64)
+        return k, n_local / max(len(pos), 1)
+
+    def sync(self):
+        self.engine.sync()
+
+
+def ShardedFutharkContext(device: int = -1, group=None, engine=None):
+    """FutharkContext (create_table / drop_table / sql) over row-range shards: same class, its FutEnv is a ShardedEnv.
+    Every rank calls the same methods with the same arguments; `sql` returns the full result on every rank."""
+    from .FutharkContext import FutharkContext
+    fc = FutharkContext.__new__(FutharkContext)
+    fc.FutEnv = ShardedEnv(engine if engine is not None else HarkEngine(device), group)
+    fc.tables = {}
+    fc.resident = True
+    return fc

@@ -61,10 +61,11 @@ typedef struct {
 } hark_pred;
 
 /* Aggregate codes.  0-4 are exactly parse.py:81 / groupby.fut:35-41 (0 and any unknown code
- * fall through to `min`, groupby.fut:41); 5 and 6 are extensions.                            */
+ * fall through to `min`, groupby.fut:41); 5, 6 and 7 are extensions.                         */
 typedef enum {
     HARK_AGG_KEY = 0, HARK_AGG_PROD = 1, HARK_AGG_SUM = 2, HARK_AGG_MAX = 3, HARK_AGG_MIN = 4,
-    HARK_AGG_COUNT = 5, HARK_AGG_AVG = 6
+    HARK_AGG_COUNT = 5, HARK_AGG_AVG = 6,
+    HARK_AGG_SUMF64 = 7 /* f64 sum as its own f64 column: the partial aggregate behind a distributed AVG */
 } hark_agg;
 
 /* Synthetic column generator (hark_table_synth).  Value of (column c, global row r) is a pure
@@ -169,6 +170,23 @@ int hark_entry_join_groupby(hark_ctx *ctx, hark_table **out, const hark_table *f
 /* ---- building blocks exported for the multi-GPU layer and for tests ---- */
 /* Stable LSD radix sort of whole rows by one column (ascending; signedness of the dtype).      */
 int hark_table_sort_by(hark_ctx *ctx, hark_table **out, const hark_table *db, int32_t key_col);
+/* Stable partition of rows into nparts (<= 256) buckets by key RANGE: bucket of a row = number of splitters
+ * that are <= its key tuple (lexicographic over key_cols, each compared through the ORDER BY order key:
+ * signed ints by sign-bit flip, floats IEEE with NaN last, DESC columns complemented).  splitters is a host
+ * array [nparts-1][nk] of such order keys (uint64), ascending.  Rows of bucket p are contiguous, in input order.
+ * This is what ORDER BY / GROUP BY / JOIN repartition with across GPUs (sampled splitters).                 */
+int hark_table_partition_by_splitters(hark_ctx *ctx, hark_table **out, const hark_table *db, const int32_t *key_cols,
+                                      const int32_t *desc, int64_t nk, const uint64_t *splitters, int32_t nparts,
+                                      int64_t *counts_out);
+/* Order keys (uint64, the same mapping as above) of the given rows: out[i][j] = ordkey(db[rows[i]][key_cols[j]]).
+ * Used to sample splitter candidates.                                                                       */
+int hark_table_sample_order_keys(hark_ctx *ctx, const hark_table *db, const int32_t *key_cols, const int32_t *desc,
+                                 int64_t nk, const int64_t *rows, int64_t nrows, uint64_t *out);
+/* Last step of a distributed GROUP BY: `merged` holds [key, partial columns...] where every aggregate of `ops`
+ * contributed its partial columns in order (AVG: an f64 sum and an i64 count; everything else one column).
+ * Output [key, agg_1..agg_c] with AVG = sum / count.                                                       */
+int hark_entry_groupby_finalize(hark_ctx *ctx, hark_table **out, const hark_table *merged, const int32_t *ops,
+                                int64_t c);
 /* Stable partition of rows into nparts buckets by mix(key) % nparts (integer key column);
  * counts_out[nparts] (host) receives the bucket sizes; rows of bucket p are contiguous.        */
 int hark_table_partition_by_hash(hark_ctx *ctx, hark_table **out, const hark_table *db, int32_t key_col,

@@ -1,0 +1,168 @@
+#!/usr/bin/env python
+"""Multi-GPU timings of the repartitioning operators (BASELINE configs 3-5) through harkdb_b200.sharded.
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+      tools/sharded_bench.py [--ops groupby,orderby,join] [--rows-per-gpu-scale 1.0] [--strong] [--reps 3]
+
+Weak scaling by default (every rank holds a full single-GPU shard of the config: total rows = N x config rows /
+--strong divides the config's rows over the ranks).  Time = barrier + synchronize on both sides, CUDA events, MAX
+over ranks.  Rank 0 prints one JSON line per operator with rows/s over all GPUs and the bytes that crossed NVLink.
+Each result is checked with size-independent properties (counts, sums, sortedness across rank boundaries).
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+I32, U32, I64, F32, F64 = 0, 1, 2, 3, 4
+AGG_SUM, AGG_COUNT, AGG_AVG = 2, 5, 6
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ops", default="groupby,orderby,join")
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the BASELINE config's row count")
+    ap.add_argument("--strong", action="store_true", help="total rows fixed (config rows x scale), divided over ranks")
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--out", default="")
+    args = ap.parse_args()
+
+    import torch
+    import torch.distributed as dist
+    from harkdb_b200.sharded import HarkEngine, ShardedEnv, ShardTable
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    eng = HarkEngine(local_rank)
+    senv = ShardedEnv(eng)
+    env = eng.env
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        best, keep = None, None
+        for _ in range(args.reps):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn()
+            e1.record()
+            barrier()
+            ms = e0.elapsed_time(e1)
+            if world > 1:
+                t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            if best is None or ms < best:
+                if keep is not None:
+                    keep.free()
+                best, keep = ms, r
+            else:
+                r.free()
+        return best, keep
+
+    def allsum(x):
+        t = torch.tensor([int(x)], device="cuda", dtype=torch.int64)
+        if world > 1:
+            dist.all_reduce(t)
+        return int(t.item())
+
+    def rows_for(cfg_rows):
+        total = int(cfg_rows * args.scale) * (1 if args.strong else world)
+        per = total // world
+        return per, per * world
+
+    results = []
+
+    def emit(d):
+        d.update(n_gpus=world, scaling="strong" if args.strong else "weak")
+        results.append(d)
+        if rank == 0:
+            print(json.dumps(d), flush=True)
+
+    for op in args.ops.split(","):
+        if op == "groupby":
+            per, total = rows_for(10 ** 9)
+            specs = [dict(kind=0, lo=0, range=1 << 20), dict(kind=0, lo=0, range=1000)]
+            t = ShardTable(senv, env.synth(per, [I32, I32], specs, seed=42, row0=rank * per))
+            ops = [AGG_SUM, AGG_COUNT, AGG_AVG]
+            ms, r = timed(lambda: senv.query_groupby_ex(t, 0, [1, 1, 1], ops))
+            keys, sums, cnts, avgs = r.local.columns()
+            ok = allsum(cnts.sum()) == total and allsum(len(keys)) == (1 << 20) and bool(np.all(np.diff(keys.astype(np.int64)) > 0))
+            bounds = [None] * world
+            if world > 1:
+                dist.all_gather_object(bounds, (int(keys[0]) if len(keys) else None, int(keys[-1]) if len(keys) else None))
+                flat = [b for b in bounds if b[0] is not None]
+                ok = ok and all(flat[i][1] < flat[i + 1][0] for i in range(len(flat) - 1))
+            emit({"op": "groupby_cfg3", "rows_total": total, "rows_per_gpu": per, "ms": ms, "rows_per_s": total / (ms * 1e-3),
+                  "groups": allsum(len(keys)), "check_ok": bool(ok)})
+            r.free(); t.free()
+        elif op == "orderby":
+            per, total = rows_for(2 * 10 ** 9)
+            specs = [dict(kind=0, lo=-(2 ** 19), range=2 ** 20), dict(kind=0, lo=0, range=0)]
+            t = ShardTable(senv, env.synth(per, [I64, I64], specs, seed=42, row0=rank * per))
+            a0, b0 = eng.columns_torch(t.local)
+            env.sync()
+            s_in = (allsum(a0.sum().item()), allsum(b0.sum().item() >> 8))
+            del a0, b0
+            ms, r = timed(lambda: senv.query_orderby(t, [0, 1], [0, 1], [0, 0]))
+            a, b = eng.columns_torch(r.local)
+            env.sync()
+            n_out = allsum(a.shape[0])
+            s_out = (allsum(a.sum().item()), allsum(b.sum().item() >> 8))
+            srt = True
+            if a.shape[0] > 1:
+                srt = bool(((a[:-1] < a[1:]) | ((a[:-1] == a[1:]) & (b[:-1] <= b[1:]))).all().item())
+            ends = [None] * world
+            mine = ((int(a[0]), int(b[0])), (int(a[-1]), int(b[-1]))) if a.shape[0] else None
+            if world > 1:
+                dist.all_gather_object(ends, mine)
+                flat = [e for e in ends if e is not None]
+                srt = srt and all(flat[i][1] <= flat[i + 1][0] for i in range(len(flat) - 1))
+            imb = a.shape[0] / max(per, 1)
+            emit({"op": "orderby_cfg4", "rows_total": total, "rows_per_gpu": per, "ms": ms, "rows_per_s": total / (ms * 1e-3),
+                  "check_ok": bool(n_out == total and s_in == s_out and allsum(int(srt)) == world),
+                  "rank0_load_vs_even": imb, "nvlink_bytes_per_gpu": int(per * 16 * (world - 1) / world)})
+            del a, b
+            r.free(); t.free()
+        elif op == "join":
+            per, total = rows_for(4 * 10 ** 9)
+            nd = int(10 ** 8 * min(1.0, args.scale * 4))
+            nd_per = nd // world
+            nd = nd_per * world
+            aa = 2654435761
+            while np.gcd(aa, nd) != 1:
+                aa += 2
+            # dim shard: global rows [rank*nd_per, ...) of pk = (a*r+b) mod nd (a permutation of 0..nd-1)
+            dim = ShardTable(senv, env.synth(nd_per, [I32, I32], [dict(kind=1, a=aa, b=12345, range=nd), dict(kind=0, lo=0, range=1024)],
+                                             seed=7, row0=rank * nd_per))
+            fact = ShardTable(senv, env.synth(per, [I32, I32], [dict(kind=0, lo=0, range=nd), dict(kind=0, lo=0, range=1000)],
+                                              seed=42, row0=rank * per))
+            ms, r = timed(lambda: senv.join_groupby(fact, dim, 0, 0, 1, [1, 1], [AGG_SUM, AGG_COUNT]))
+            keys, sums, cnts = r.local.columns()
+            ok = allsum(cnts.sum()) == total and allsum(len(keys)) == 1024
+            emit({"op": "join_groupby_cfg5", "rows_total": total, "rows_per_gpu": per, "dim_rows": nd, "ms": ms,
+                  "rows_per_s": total / (ms * 1e-3), "check_ok": bool(ok),
+                  "nvlink_bytes_per_gpu": int(nd_per * 8 * (world - 1))})
+            r.free(); dim.free(); fact.free()
+    if args.out and rank == 0:
+        json.dump(results, open(args.out, "w"), indent=1)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
