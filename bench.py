@@ -186,8 +186,7 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
 
     from harkdb_b200 import hark_ffi
-    stream = torch.cuda.current_stream().cuda_stream
-    env = hark_ffi.Futhark(device=local_rank, stream=stream)
+    env = hark_ffi.Futhark(device=local_rank, stream=hark_ffi.torch_stream_handle())   # torch events see libhark's kernels
     if args.filter_ctas_per_sm:
         env.set_option("filter.ctas_per_sm", args.filter_ctas_per_sm)
     if args.filter_impl:

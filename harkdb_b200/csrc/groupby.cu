@@ -681,7 +681,7 @@ int hk_groupby(hark_ctx *ctx, hark_table **out, const hark_table *db, int32_t g_
         arrays.push_back(a);
     }
     if ((int)arrays.size() > HK_SORT_MAX_ARRAYS)
-        return ctx->fail(HARK_ERR_UNSUPPORTED, "query_groupby: more than 9 distinct aggregated columns");
+        return ctx->fail(HARK_ERR_UNSUPPORTED, "query_groupby: more than 19 distinct aggregated columns");
     std::vector<hk_sort_keyspec> keys{hk_sort_keyspec{0, key_dtype, 0}};
     hk_sort_info info;
     HK_TRY(hk_radix_sort(ctx, n, keys, arrays, 0, nullptr, &info));

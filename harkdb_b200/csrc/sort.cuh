@@ -4,7 +4,7 @@
 
 #include "hark_internal.cuh"
 
-#define HK_SORT_MAX_ARRAYS 10
+#define HK_SORT_MAX_ARRAYS 20
 
 struct hk_sort_keyspec {
     int array;     // index into the carried arrays

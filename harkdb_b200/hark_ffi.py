@@ -107,6 +107,16 @@ SIGNATURES = {
 
 _LIB: Optional[C.CDLL] = None
 
+LEGACY_DEFAULT_STREAM = 1   # cudaStreamLegacy: CUDA's handle for "the default stream" that is not the NULL pointer
+
+
+def torch_stream_handle() -> int:
+    """cudaStream_t of torch's current stream, usable as `Futhark(stream=...)`.  torch's default stream has handle
+    0, which this ABI reads as "create your own stream", so it is passed as cudaStreamLegacy instead: libhark's
+    kernels are then ordered with torch's kernels and with the collectives torch.distributed launches."""
+    import torch
+    return int(torch.cuda.current_stream().cuda_stream) or LEGACY_DEFAULT_STREAM
+
 
 def load_library(path: str = LIB_PATH) -> C.CDLL:
     """dlopen libhark.so and type every exported symbol.  Raises if the library was not built."""

@@ -126,7 +126,7 @@ class HarkEngine:
         self.torch = torch
         self.device = torch.device("cuda", torch.cuda.current_device())
         # one stream for torch collectives and libhark kernels: no cross-stream ordering to manage
-        self.env = hark_ffi.Futhark(device=self.device.index, stream=torch.cuda.current_stream().cuda_stream)
+        self.env = hark_ffi.Futhark(device=self.device.index, stream=hark_ffi.torch_stream_handle())
 
     # ---- tables ----
     def to_device(self, arr, dtype=None):

@@ -102,7 +102,8 @@ typedef struct {
 /* ---- context (replaces futhark_context_config_new / futhark_context_new, FutharkContext.py:41) ---- */
 int hark_abi_version(void);
 /* device: CUDA ordinal, -1 = the calling thread's current device.
- * stream: a cudaStream_t to launch on (borrowed), or NULL for a stream the context owns.     */
+ * stream: a cudaStream_t to launch on (borrowed; cudaStreamLegacy / cudaStreamPerThread are accepted), or NULL
+ *         for a non-blocking stream the context owns.                                                            */
 hark_ctx *hark_context_new(int device, void *stream);
 void hark_context_free(hark_ctx *ctx);
 int hark_context_sync(hark_ctx *ctx);

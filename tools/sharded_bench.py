@@ -80,6 +80,12 @@ def main():
             dist.all_reduce(t)
         return int(t.item())
 
+    def wrapsum(t):      # sum over ranks of an int64 scalar tensor, wrapping mod 2^64 like the local sums do
+        t = t.reshape(1).clone()
+        if world > 1:
+            dist.all_reduce(t)
+        return int(t.item())
+
     def rows_for(cfg_rows):
         total = int(cfg_rows * args.scale) * (1 if args.strong else world)
         per = total // world
@@ -116,13 +122,13 @@ def main():
             t = ShardTable(senv, env.synth(per, [I64, I64], specs, seed=42, row0=rank * per))
             a0, b0 = eng.columns_torch(t.local)
             env.sync()
-            s_in = (allsum(a0.sum().item()), allsum(b0.sum().item() >> 8))
+            s_in = (wrapsum(a0.sum()), wrapsum(b0.sum()))
             del a0, b0
             ms, r = timed(lambda: senv.query_orderby(t, [0, 1], [0, 1], [0, 0]))
             a, b = eng.columns_torch(r.local)
             env.sync()
             n_out = allsum(a.shape[0])
-            s_out = (allsum(a.sum().item()), allsum(b.sum().item() >> 8))
+            s_out = (wrapsum(a.sum()), wrapsum(b.sum()))
             srt = True
             if a.shape[0] > 1:
                 srt = bool(((a[:-1] < a[1:]) | ((a[:-1] == a[1:]) & (b[:-1] <= b[1:]))).all().item())
