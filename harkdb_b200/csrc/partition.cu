@@ -78,10 +78,10 @@ struct PartParams {
 };
 
 template <int KW>
-__global__ void __launch_bounds__(256) hk_part_hist_kernel(const __grid_constant__ PartParams P) {
+__global__ void __launch_bounds__(1024) hk_part_hist_kernel(const __grid_constant__ PartParams P) {
     using T = typename KRaw<KW>::T;
     __shared__ uint32_t sh[256];
-    sh[threadIdx.x] = 0;
+    if (threadIdx.x < 256) sh[threadIdx.x] = 0;
     __syncthreads();
     const T *p = reinterpret_cast<const T *>(P.key_in);
     constexpr int V = 16 / KW;
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) hk_part_hist_kernel(const __grid_constant
     const int64_t nvec = (r1 - r0) / V;
     const T *q = p + r0;
 #pragma unroll 4
-    for (int64_t i = threadIdx.x; i < nvec; i += 256) {
+    for (int64_t i = threadIdx.x; i < nvec; i += 1024) {
         T x[V];
         if constexpr (KW == 4) {
             const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(q) + i);
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256) hk_part_hist_kernel(const __grid_constant
     }
     if (threadIdx.x < (int)((r1 - r0) - nvec * V)) atomicAdd(&sh[part_digit<KW>(q[nvec * V + threadIdx.x], P.f)], 1u);
     __syncthreads();
-    P.chunk_counts[(size_t)blockIdx.x * 256 + threadIdx.x] = sh[threadIdx.x];
+    if (threadIdx.x < 256) P.chunk_counts[(size_t)blockIdx.x * 256 + threadIdx.x] = sh[threadIdx.x];
 }
 
 // one CTA of 1024 threads: thread (q, b) scans quarter q of the chunks of bin b
@@ -380,8 +380,8 @@ int hk_partition_pass(hark_ctx *ctx, int64_t n, const void *key, int kw, const h
         P.val_in[v] = (const uint32_t *)vals[v];
         P.val_out[v] = (uint32_t *)vo;
     }
-    if (kw == 4) hk_part_hist_kernel<4><<<(unsigned)P.num_chunks, 256, 0, ctx->stream>>>(P);
-    else hk_part_hist_kernel<8><<<(unsigned)P.num_chunks, 256, 0, ctx->stream>>>(P);
+    if (kw == 4) hk_part_hist_kernel<4><<<(unsigned)P.num_chunks, 1024, 0, ctx->stream>>>(P);
+    else hk_part_hist_kernel<8><<<(unsigned)P.num_chunks, 1024, 0, ctx->stream>>>(P);
     HK_CHECK_LAUNCH(ctx);
     hk_part_scan_kernel<<<1, 1024, 0, ctx->stream>>>(P);
     HK_CHECK_LAUNCH(ctx);

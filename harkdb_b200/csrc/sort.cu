@@ -308,6 +308,334 @@ __global__ void __launch_bounds__(ST, 2) hk_onesweep_kernel(const __grid_constan
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// K3 v2 — chunked stable pass (default).  Same contract as one onesweep pass (stable scatter of all carried arrays
+// by one 8-bit digit), different inter-CTA protocol: instead of a chained-scan look-back per (tile, bin), a
+// histogram kernel first counts every CHUNK's rows per bin (one extra streaming read of the pass's key column), a
+// one-CTA scan turns that into each chunk's start offset per bin, and the scatter kernel walks its chunk tile by
+// tile with running offsets in shared memory — no global atomics, no spinning, and the next tile's keys are loaded
+// while the current tile is written out.  Stability: chunks, tiles, warps, items and lanes are all visited in
+// row order (warp-striped items ranked with match.any ballots).
+// ------------------------------------------------------------------------------------------------
+constexpr int LT = 512;          // threads per CTA
+constexpr int LI = 8;            // rows per thread
+constexpr int LTILE = LT * LI;   // rows per tile (4096)
+constexpr int LWARPS = LT / 32;
+
+struct LsdParams {
+    DigitFn f;
+    int na;      // carried arrays; array `ka` is the key column of this pass
+    int ka;
+    const void *in[MAXA];
+    void *out[MAXA];
+    int width[MAXA];
+    int64_t n;
+    int64_t num_tiles;
+    int64_t tiles_per_chunk;
+    int num_chunks;
+    uint32_t *chunk_counts;           // [num_chunks][256]
+    unsigned long long *chunk_base;   // [num_chunks][256]
+    unsigned long long *offsets;      // [257]
+};
+
+template <int KW>
+__global__ void __launch_bounds__(1024) hk_lsd_hist_kernel(const __grid_constant__ LsdParams P) {
+    using T = typename KeyRaw<KW>::T;
+    __shared__ uint32_t sh[256];
+    if (threadIdx.x < 256) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const T *p = reinterpret_cast<const T *>(P.in[P.ka]);
+    constexpr int V = 16 / KW;
+    const int64_t r0 = (int64_t)blockIdx.x * P.tiles_per_chunk * LTILE;
+    const int64_t r1 = min(P.n, r0 + P.tiles_per_chunk * LTILE);
+    const int64_t nvec = r1 > r0 ? (r1 - r0) / V : 0;
+    const T *q = p + r0;
+#pragma unroll 4
+    for (int64_t i = threadIdx.x; i < nvec; i += 1024) {
+        T x[V];
+        if constexpr (KW == 4) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(q) + i);
+            x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+        } else {
+            const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(q) + i);
+            x[0] = v.x; x[1] = v.y;
+        }
+#pragma unroll
+        for (int e = 0; e < V; e++) atomicAdd(&sh[digit_of<KW>(x[e], P.f)], 1u);
+    }
+    if (r1 > r0 && threadIdx.x < (int)((r1 - r0) - nvec * V)) atomicAdd(&sh[digit_of<KW>(q[nvec * V + threadIdx.x], P.f)], 1u);
+    __syncthreads();
+    if (threadIdx.x < 256) P.chunk_counts[(size_t)blockIdx.x * 256 + threadIdx.x] = sh[threadIdx.x];
+}
+
+// one CTA of 1024 threads: thread (q, b) scans quarter q of the chunks of bin b
+__global__ void __launch_bounds__(1024) hk_lsd_scan_kernel(const __grid_constant__ LsdParams P) {
+    __shared__ unsigned long long s_q[4][256];
+    __shared__ unsigned long long wtot[8];
+    const int b = threadIdx.x & 255, q = threadIdx.x >> 8;
+    const int per = (P.num_chunks + 3) / 4;
+    const int c0 = min(P.num_chunks, q * per), c1 = min(P.num_chunks, c0 + per);
+    unsigned long long sum = 0;
+#pragma unroll 8
+    for (int c = c0; c < c1; c++) sum += P.chunk_counts[(size_t)c * 256 + b];
+    s_q[q][b] = sum;
+    __syncthreads();
+    const unsigned long long total = s_q[0][b] + s_q[1][b] + s_q[2][b] + s_q[3][b];
+    const int lane = b & 31, warp = b >> 5;
+    unsigned long long inc = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(HK_FULL_MASK, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (q == 0 && lane == 31) wtot[warp] = inc;
+    __syncthreads();
+    if (q == 0) {
+        unsigned long long off = 0;
+        for (int w = 0; w < warp; w++) off += wtot[w];
+        const unsigned long long st = off + inc - total;
+        P.offsets[b] = st;
+        if (b == 255) P.offsets[256] = off + inc;
+        const unsigned long long q0 = sum, q1 = s_q[1][b], q2 = s_q[2][b];
+        s_q[0][b] = st;
+        s_q[1][b] = st + q0;
+        s_q[2][b] = st + q0 + q1;
+        s_q[3][b] = st + q0 + q1 + q2;
+    }
+    __syncthreads();
+    unsigned long long run = s_q[q][b];
+#pragma unroll 8
+    for (int c = c0; c < c1; c++) {
+        P.chunk_base[(size_t)c * 256 + b] = run;
+        run += P.chunk_counts[(size_t)c * 256 + b];
+    }
+}
+
+template <int KW>
+__device__ __forceinline__ void lsd_load_keys(const typename KeyRaw<KW>::T *keyp, int64_t tile_base, int count, int warp, int lane,
+                                              typename KeyRaw<KW>::T (&key)[LI]) {
+    using KT = typename KeyRaw<KW>::T;
+#pragma unroll
+    for (int i = 0; i < LI; i++) {
+        const int idx = warp * (LI * 32) + i * 32 + lane;
+        key[i] = idx < count ? keyp[tile_base + idx] : (KT)0;
+    }
+}
+
+// values of one carried array for this thread's items (warp-striped), widened to 64 bits
+__device__ __forceinline__ void lsd_load_vals(const void *src, int width, int64_t tile_base, int count, int warp, int lane,
+                                              uint64_t (&v)[LI]) {
+    if (width == 4) {
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(src) + tile_base;
+#pragma unroll
+        for (int i = 0; i < LI; i++) {
+            const int idx = warp * (LI * 32) + i * 32 + lane;
+            v[i] = idx < count ? (uint64_t)p[idx] : 0ull;
+        }
+    } else {
+        const uint64_t *p = reinterpret_cast<const uint64_t *>(src) + tile_base;
+#pragma unroll
+        for (int i = 0; i < LI; i++) {
+            const int idx = warp * (LI * 32) + i * 32 + lane;
+            v[i] = idx < count ? p[idx] : 0ull;
+        }
+    }
+}
+
+// staged tile -> global, bin runs contiguous; fixed trip count for full tiles so the shared-memory look-ups pipeline
+template <typename OT>
+__device__ __forceinline__ void lsd_write_out(OT *o, const uint64_t *stage, const uint8_t *s_digit, const uint64_t *s_gbase,
+                                              int count, int tid) {
+    if (count == LTILE) {
+#pragma unroll
+        for (int i = 0; i < LI; i++) {
+            const int j = i * LT + tid;
+            o[s_gbase[s_digit[j]] + (uint64_t)j] = (OT)stage[j];
+        }
+    } else {
+        for (int j = tid; j < count; j += LT) o[s_gbase[s_digit[j]] + (uint64_t)j] = (OT)stage[j];
+    }
+}
+
+// RANK: 0 = match.any, 1 = eight ballots (register-only multisplit)
+template <int KW, int RANK>
+__global__ void __launch_bounds__(LT, 2) hk_lsd_scatter_kernel(const __grid_constant__ LsdParams P) {
+    using KT = typename KeyRaw<KW>::T;
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    uint64_t *stage = reinterpret_cast<uint64_t *>(s_dyn); // LTILE slots of 8 bytes
+    __shared__ uint32_t wh[LWARPS][256];
+    __shared__ uint32_t s_binstart[256];
+    __shared__ uint64_t s_gbase[256];
+    __shared__ uint64_t s_run[256];
+    __shared__ uint8_t s_digit[LTILE];
+    __shared__ uint32_t s_wtot[8];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const KT *keyp = reinterpret_cast<const KT *>(P.in[P.ka]);
+    const int64_t t0 = (int64_t)blockIdx.x * P.tiles_per_chunk;
+    const int64_t t1 = min(P.num_tiles, t0 + P.tiles_per_chunk);
+    if (tid < 256) s_run[tid] = P.chunk_base[(size_t)blockIdx.x * 256 + tid];
+    for (int i = tid; i < LWARPS * 256; i += LT) (&wh[0][0])[i] = 0;
+    if (t0 >= t1) return;
+    const int first_other = P.ka == 0 ? (P.na > 1 ? 1 : -1) : 0;
+
+    KT key[LI];
+    int count = (int)min((int64_t)LTILE, P.n - t0 * LTILE);
+    lsd_load_keys<KW>(keyp, t0 * LTILE, count, warp, lane, key);
+    __syncthreads();
+
+    for (int64_t tile = t0; tile < t1; tile++) {
+        const int64_t tile_base = tile * LTILE;
+        const int cur_count = count;
+        // the first carried array's values are requested now and arrive while the keys are being ranked
+        uint64_t v[LI];
+        if (first_other >= 0) lsd_load_vals(P.in[first_other], P.width[first_other], tile_base, cur_count, warp, lane, v);
+        // ---- stable rank of every key among the keys of its warp with the same digit ----
+        uint32_t rank[LI];
+#pragma unroll
+        for (int i = 0; i < LI; i++) {
+            const int idx = warp * (LI * 32) + i * 32 + lane;
+            const bool valid = idx < cur_count;
+            const uint32_t d = valid ? digit_of<KW>(key[i], P.f) : 256u;
+            uint32_t peers;
+            if constexpr (RANK == 0) {
+                peers = __match_any_sync(HK_FULL_MASK, d);
+            } else {
+                peers = __ballot_sync(HK_FULL_MASK, valid);
+                if (!valid) peers = ~peers;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const uint32_t b = __ballot_sync(HK_FULL_MASK, (d >> k) & 1u);
+                    peers &= ((d >> k) & 1u) ? b : ~b;
+                }
+            }
+            const int leader = __ffs(peers) - 1;
+            uint32_t old = 0;
+            if (valid && lane == leader) {
+                old = wh[warp][d];
+                wh[warp][d] = old + __popc(peers);
+            }
+            old = __shfl_sync(HK_FULL_MASK, old, leader);
+            rank[i] = (valid ? (d << 16) : 0xffff0000u) | (old + __popc(peers & lt_mask));
+            __syncwarp();
+        }
+        __syncthreads();
+        // ---- thread b owns bin b: offsets of the warps inside the bin, bin start inside the tile, global base ----
+        {
+            uint32_t sum = 0;
+            if (tid < 256) {
+#pragma unroll
+                for (int w = 0; w < LWARPS; w++) {
+                    const uint32_t c = wh[w][tid];
+                    wh[w][tid] = sum;
+                    sum += c;
+                }
+            }
+            const uint32_t inc = hk_warp_incl_scan_u32(sum);
+            if (lane == 31 && warp < 8) s_wtot[warp] = inc;
+            __syncthreads();
+            if (tid < 256) {
+                uint32_t woff = 0;
+                for (int w = 0; w < warp; w++) woff += s_wtot[w];
+                const uint32_t binstart = woff + inc - sum;
+                s_binstart[tid] = binstart;
+                const uint64_t run = s_run[tid];
+                s_gbase[tid] = run - (uint64_t)binstart; // wraps; undone by + position
+                s_run[tid] = run + sum;
+            }
+        }
+        __syncthreads();
+        // ---- tile-local reorder of the keys; every item remembers its slot ----
+#pragma unroll
+        for (int i = 0; i < LI; i++) {
+            const uint32_t d = rank[i] >> 16;
+            if (d < 256u) {
+                const uint32_t pos = s_binstart[d] + wh[warp][d] + (rank[i] & 0xffffu);
+                rank[i] = pos;
+                stage[pos] = (uint64_t)key[i];
+                s_digit[pos] = (uint8_t)d;
+            }
+        }
+        // the key registers are free: load the next tile's keys now, they arrive while this tile is written out
+        if (tile + 1 < t1) {
+            count = (int)min((int64_t)LTILE, P.n - (tile + 1) * LTILE);
+            lsd_load_keys<KW>(keyp, (tile + 1) * LTILE, count, warp, lane, key);
+        }
+        __syncthreads();
+        for (int i = tid; i < LWARPS * 256; i += LT) (&wh[0][0])[i] = 0; // last read above; next written after >= 1 barrier
+        lsd_write_out<KT>(reinterpret_cast<KT *>(P.out[P.ka]), stage, s_digit, s_gbase, cur_count, tid);
+        // ---- the other carried arrays ride the same permutation; array a+1 is loaded while array a is written ----
+        for (int a = first_other; a >= 0 && a < P.na;) {
+            __syncthreads(); // everyone has read the previous array out of `stage`
+#pragma unroll
+            for (int i = 0; i < LI; i++) {
+                const int idx = warp * (LI * 32) + i * 32 + lane;
+                if (idx < cur_count) stage[rank[i]] = v[i];
+            }
+            int nxt = a + 1;
+            if (nxt == P.ka) nxt++;
+            if (nxt < P.na) lsd_load_vals(P.in[nxt], P.width[nxt], tile_base, cur_count, warp, lane, v);
+            __syncthreads();
+            if (P.width[a] == 4) lsd_write_out<uint32_t>(reinterpret_cast<uint32_t *>(P.out[a]), stage, s_digit, s_gbase, cur_count, tid);
+            else lsd_write_out<uint64_t>(reinterpret_cast<uint64_t *>(P.out[a]), stage, s_digit, s_gbase, cur_count, tid);
+            a = nxt;
+        }
+        __syncthreads(); // stage / s_digit are rewritten by the next tile
+    }
+}
+
+// One stable pass over all carried arrays with the chunked protocol.  d_offsets_out (optional) receives the device
+// pointer of the 257 exclusive bin offsets (caller frees).
+int lsd_pass(hark_ctx *ctx, LsdParams &P, int kw, unsigned long long **d_offsets_out) {
+    P.num_tiles = (P.n + LTILE - 1) / LTILE;
+    const size_t smem = (size_t)LTILE * 8;
+    int occ = 1;
+    const bool ballots = ctx->opt("sort.rank", 1) == 1;
+    void (*scatter)(const LsdParams) = kw == 4 ? (ballots ? hk_lsd_scatter_kernel<4, 1> : hk_lsd_scatter_kernel<4, 0>)
+                                               : (ballots ? hk_lsd_scatter_kernel<8, 1> : hk_lsd_scatter_kernel<8, 0>);
+    cudaError_t e = cudaFuncSetAttribute(scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scatter, LT, smem);
+    if (e != cudaSuccess) return ctx->fail(HARK_ERR_CUDA, std::string("sort(pass setup): ") + cudaGetErrorString(e));
+    occ = std::max(1, occ);
+    const int64_t want = ctx->opt("sort.ctas_per_sm", 0);
+    if (want > 0) occ = (int)std::min<int64_t>(occ, want);
+    const int64_t max_chunks = (int64_t)ctx->num_sms * occ;
+    P.tiles_per_chunk = std::max<int64_t>(1, (P.num_tiles + max_chunks - 1) / max_chunks);
+    P.num_chunks = (int)std::max<int64_t>(1, (P.num_tiles + P.tiles_per_chunk - 1) / P.tiles_per_chunk);
+    void *cc = nullptr, *cb = nullptr, *off = nullptr;
+    HK_TRY(ctx->dalloc(&cc, (size_t)P.num_chunks * 256 * sizeof(uint32_t)));
+    int rc = ctx->dalloc(&cb, (size_t)P.num_chunks * 256 * sizeof(unsigned long long));
+    if (rc == HARK_OK) rc = ctx->dalloc(&off, 257 * sizeof(unsigned long long));
+    if (rc != HARK_OK) {
+        ctx->dfree(cc);
+        ctx->dfree(cb);
+        return rc;
+    }
+    P.chunk_counts = (uint32_t *)cc;
+    P.chunk_base = (unsigned long long *)cb;
+    P.offsets = (unsigned long long *)off;
+    if (kw == 4) hk_lsd_hist_kernel<4><<<(unsigned)P.num_chunks, 1024, 0, ctx->stream>>>(P);
+    else hk_lsd_hist_kernel<8><<<(unsigned)P.num_chunks, 1024, 0, ctx->stream>>>(P);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) {
+        hk_lsd_scan_kernel<<<1, 1024, 0, ctx->stream>>>(P);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) {
+        scatter<<<(unsigned)P.num_chunks, LT, smem, ctx->stream>>>(P);
+        e = cudaGetLastError();
+    }
+    ctx->count_launch(3);
+    ctx->dfree(cc);
+    ctx->dfree(cb);
+    if (d_offsets_out) *d_offsets_out = (unsigned long long *)off;
+    else ctx->dfree(off);
+    if (e != cudaSuccess) return ctx->fail(HARK_ERR_CUDA, std::string("sort(pass): ") + cudaGetErrorString(e));
+    return HARK_OK;
+}
+
 template <typename IT>
 __global__ void __launch_bounds__(256) hk_iota_kernel(IT *out, int64_t n) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -463,98 +791,136 @@ int hk_radix_sort(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec> &
         return HARK_OK;
     }
 
+    const bool chunked = ctx->opt("sort.impl", 0) != 1;
+    if (chunked) {
+        // ---- K3 v2: every pass = chunk histogram + scan + stable scatter (see hk_lsd_scatter_kernel) ----
+        std::vector<const void *> cur(na);
+        for (int a = 0; a < na; a++) cur[a] = arrays[a].in;
+        for (int p = 0; p < npass; p++) {
+            const int ob = p & 1;
+            for (int a = 0; a < na && rc == HARK_OK; a++)
+                if (!arrays[a].buf[ob]) rc = ctx->dalloc(&arrays[a].buf[ob], (size_t)n * arrays[a].width);
+            if (rc != HARK_OK) return cleanup_fail(rc, "");
+            LsdParams P;
+            memset(&P, 0, sizeof P);
+            P.f = passes[p].f;
+            P.na = na;
+            P.ka = keys[passes[p].key].array;
+            for (int a = 0; a < na; a++) {
+                P.in[a] = cur[a];
+                P.out[a] = arrays[a].buf[ob];
+                P.width[a] = arrays[a].width;
+            }
+            P.n = n;
+            unsigned long long *d_off = nullptr;
+            if (p == 0) ctx->kernel_begin();
+            rc = lsd_pass(ctx, P, arrays[P.ka].width, hash_counts ? &d_off : nullptr);
+            if (p == npass - 1) ctx->kernel_end();
+            if (rc != HARK_OK) return cleanup_fail(rc, "");
+            if (hash_counts) { // bucket sizes for the caller
+                e = cudaMemcpyAsync(ctx->h_scalars, d_off, sizeof(uint64_t) * 256, cudaMemcpyDeviceToHost, ctx->stream);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+                ctx->dfree(d_off);
+                if (e != cudaSuccess) return cleanup_fail(HARK_ERR_CUDA, std::string("sort(counts): ") + cudaGetErrorString(e));
+                for (int i = 0; i < hash_nparts; i++)
+                    hash_counts[i] = (int64_t)((i + 1 < 256 ? ctx->h_scalars[i + 1] : (uint64_t)n) - ctx->h_scalars[i]);
+            }
+            for (int a = 0; a < na; a++) cur[a] = arrays[a].buf[ob];
+        }
+    } else {
     // ---- 3. all digit histograms up front (one read per key column), then their exclusive scans ----
-    rc = ctx->dalloc((void **)&d_hist, sizeof(unsigned long long) * 256 * npass);
-    if (rc != HARK_OK) return cleanup_fail(rc, "");
-    e = cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * 256 * npass, ctx->stream);
-    for (int p0 = 0; p0 < npass && e == cudaSuccess;) {
-        int p1 = p0;
-        while (p1 < npass && passes[p1].key == passes[p0].key && p1 - p0 < MAXPASS) p1++;
-        HistParams H;
-        memset(&H, 0, sizeof H);
-        const hk_sort_array &ka = arrays[keys[passes[p0].key].array];
-        H.key = ka.in;
-        H.n = n;
-        H.npass = p1 - p0;
-        for (int q = p0; q < p1; q++) H.f[q - p0] = passes[q].f;
-        H.hist = d_hist + (size_t)256 * p0;
-        const unsigned g = grid_for(ctx, n, 4);
-        if (ka.width == 4) hk_hist_kernel<4><<<g, 256, 0, ctx->stream>>>(H);
-        else hk_hist_kernel<8><<<g, 256, 0, ctx->stream>>>(H);
-        e = cudaGetLastError();
-        ctx->count_launch();
-        p0 = p1;
-    }
-    if (e == cudaSuccess && hash_counts) { // bucket sizes for the caller (before the scan overwrites them)
-        e = cudaMemcpyAsync(ctx->h_scalars, d_hist, sizeof(uint64_t) * 256, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e == cudaSuccess)
-            for (int i = 0; i < hash_nparts; i++) hash_counts[i] = (int64_t)ctx->h_scalars[i];
-    }
-    if (e == cudaSuccess) {
-        hk_hist_scan_kernel<<<npass, 256, 0, ctx->stream>>>(d_hist);
-        e = cudaGetLastError();
-        ctx->count_launch();
-    }
-    if (e != cudaSuccess) return cleanup_fail(HARK_ERR_CUDA, std::string("sort(hist): ") + cudaGetErrorString(e));
-
-    // ---- 4. the passes ----
-    const int64_t num_tiles = (n + STILE - 1) / STILE;
-    uint64_t *d_status = nullptr; // [0] ticket per pass x npass ... then [num_tiles][256]
-    const size_t status_words = (size_t)num_tiles * 256;
-    rc = ctx->dalloc((void **)&d_status, sizeof(uint64_t) * (status_words + (size_t)npass));
-    if (rc != HARK_OK) return cleanup_fail(rc, "");
-    e = cudaMemsetAsync(d_status, 0, sizeof(uint64_t) * (status_words + (size_t)npass), ctx->stream);
-    int occ4 = 0, occ8 = 0;
-    const size_t smem = (size_t)STILE * 8;
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(hk_onesweep_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(hk_onesweep_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4, hk_onesweep_kernel<4>, ST, smem);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ8, hk_onesweep_kernel<8>, ST, smem);
-    const int64_t want_occ = ctx->opt("sort.ctas_per_sm", 0);
-
-    std::vector<const void *> cur(na);
-    for (int a = 0; a < na; a++) cur[a] = arrays[a].in;
-    for (int p = 0; p < npass && e == cudaSuccess; p++) {
-        if (p > 0 && p % 255 == 0) // tags wrap: start over with a clean status array
-            e = cudaMemsetAsync(d_status + npass, 0, sizeof(uint64_t) * status_words, ctx->stream);
-        const int ob = p & 1;
-        for (int a = 0; a < na && rc == HARK_OK; a++)
-            if (!arrays[a].buf[ob]) rc = ctx->dalloc(&arrays[a].buf[ob], (size_t)n * arrays[a].width);
-        if (rc != HARK_OK) {
-            ctx->dfree(d_status);
-            return cleanup_fail(rc, "");
+        rc = ctx->dalloc((void **)&d_hist, sizeof(unsigned long long) * 256 * npass);
+        if (rc != HARK_OK) return cleanup_fail(rc, "");
+        e = cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * 256 * npass, ctx->stream);
+        for (int p0 = 0; p0 < npass && e == cudaSuccess;) {
+            int p1 = p0;
+            while (p1 < npass && passes[p1].key == passes[p0].key && p1 - p0 < MAXPASS) p1++;
+            HistParams H;
+            memset(&H, 0, sizeof H);
+            const hk_sort_array &ka = arrays[keys[passes[p0].key].array];
+            H.key = ka.in;
+            H.n = n;
+            H.npass = p1 - p0;
+            for (int q = p0; q < p1; q++) H.f[q - p0] = passes[q].f;
+            H.hist = d_hist + (size_t)256 * p0;
+            const unsigned g = grid_for(ctx, n, 4);
+            if (ka.width == 4) hk_hist_kernel<4><<<g, 256, 0, ctx->stream>>>(H);
+            else hk_hist_kernel<8><<<g, 256, 0, ctx->stream>>>(H);
+            e = cudaGetLastError();
+            ctx->count_launch();
+            p0 = p1;
         }
-        PassParams P;
-        memset(&P, 0, sizeof P);
-        P.f = passes[p].f;
-        P.na = na;
-        P.ka = keys[passes[p].key].array;
-        for (int a = 0; a < na; a++) {
-            P.in[a] = cur[a];
-            P.out[a] = arrays[a].buf[ob];
-            P.width[a] = arrays[a].width;
+        if (e == cudaSuccess && hash_counts) { // bucket sizes for the caller (before the scan overwrites them)
+            e = cudaMemcpyAsync(ctx->h_scalars, d_hist, sizeof(uint64_t) * 256, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e == cudaSuccess)
+                for (int i = 0; i < hash_nparts; i++) hash_counts[i] = (int64_t)ctx->h_scalars[i];
         }
-        P.n = n;
-        P.num_tiles = num_tiles;
-        P.status = d_status + npass;
-        P.ticket = (unsigned long long *)(d_status + p);
-        P.pass_offsets = d_hist + (size_t)256 * passes[p].hist_slot;
-        P.tag = (uint32_t)(p % 255) + 1;
-        const int kw = arrays[P.ka].width;
-        int occ = std::max(1, kw == 4 ? occ4 : occ8);
-        if (want_occ > 0) occ = (int)std::min<int64_t>(occ, want_occ);
-        const unsigned grid = (unsigned)std::min<int64_t>(num_tiles, (int64_t)ctx->num_sms * occ);
-        if (p == 0) ctx->kernel_begin();
-        if (kw == 4) hk_onesweep_kernel<4><<<grid, ST, smem, ctx->stream>>>(P);
-        else hk_onesweep_kernel<8><<<grid, ST, smem, ctx->stream>>>(P);
-        e = cudaGetLastError();
-        ctx->count_launch();
-        if (p == npass - 1) ctx->kernel_end();
-        for (int a = 0; a < na; a++) cur[a] = arrays[a].buf[ob];
+        if (e == cudaSuccess) {
+            hk_hist_scan_kernel<<<npass, 256, 0, ctx->stream>>>(d_hist);
+            e = cudaGetLastError();
+            ctx->count_launch();
+        }
+        if (e != cudaSuccess) return cleanup_fail(HARK_ERR_CUDA, std::string("sort(hist): ") + cudaGetErrorString(e));
+    
+        // ---- 4. the passes ----
+        const int64_t num_tiles = (n + STILE - 1) / STILE;
+        uint64_t *d_status = nullptr; // [0] ticket per pass x npass ... then [num_tiles][256]
+        const size_t status_words = (size_t)num_tiles * 256;
+        rc = ctx->dalloc((void **)&d_status, sizeof(uint64_t) * (status_words + (size_t)npass));
+        if (rc != HARK_OK) return cleanup_fail(rc, "");
+        e = cudaMemsetAsync(d_status, 0, sizeof(uint64_t) * (status_words + (size_t)npass), ctx->stream);
+        int occ4 = 0, occ8 = 0;
+        const size_t smem = (size_t)STILE * 8;
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(hk_onesweep_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(hk_onesweep_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4, hk_onesweep_kernel<4>, ST, smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ8, hk_onesweep_kernel<8>, ST, smem);
+        const int64_t want_occ = ctx->opt("sort.ctas_per_sm", 0);
+    
+        std::vector<const void *> cur(na);
+        for (int a = 0; a < na; a++) cur[a] = arrays[a].in;
+        for (int p = 0; p < npass && e == cudaSuccess; p++) {
+            if (p > 0 && p % 255 == 0) // tags wrap: start over with a clean status array
+                e = cudaMemsetAsync(d_status + npass, 0, sizeof(uint64_t) * status_words, ctx->stream);
+            const int ob = p & 1;
+            for (int a = 0; a < na && rc == HARK_OK; a++)
+                if (!arrays[a].buf[ob]) rc = ctx->dalloc(&arrays[a].buf[ob], (size_t)n * arrays[a].width);
+            if (rc != HARK_OK) {
+                ctx->dfree(d_status);
+                return cleanup_fail(rc, "");
+            }
+            PassParams P;
+            memset(&P, 0, sizeof P);
+            P.f = passes[p].f;
+            P.na = na;
+            P.ka = keys[passes[p].key].array;
+            for (int a = 0; a < na; a++) {
+                P.in[a] = cur[a];
+                P.out[a] = arrays[a].buf[ob];
+                P.width[a] = arrays[a].width;
+            }
+            P.n = n;
+            P.num_tiles = num_tiles;
+            P.status = d_status + npass;
+            P.ticket = (unsigned long long *)(d_status + p);
+            P.pass_offsets = d_hist + (size_t)256 * passes[p].hist_slot;
+            P.tag = (uint32_t)(p % 255) + 1;
+            const int kw = arrays[P.ka].width;
+            int occ = std::max(1, kw == 4 ? occ4 : occ8);
+            if (want_occ > 0) occ = (int)std::min<int64_t>(occ, want_occ);
+            const unsigned grid = (unsigned)std::min<int64_t>(num_tiles, (int64_t)ctx->num_sms * occ);
+            if (p == 0) ctx->kernel_begin();
+            if (kw == 4) hk_onesweep_kernel<4><<<grid, ST, smem, ctx->stream>>>(P);
+            else hk_onesweep_kernel<8><<<grid, ST, smem, ctx->stream>>>(P);
+            e = cudaGetLastError();
+            ctx->count_launch();
+            if (p == npass - 1) ctx->kernel_end();
+            for (int a = 0; a < na; a++) cur[a] = arrays[a].buf[ob];
+        }
+        ctx->dfree(d_status);
+        if (e != cudaSuccess) return cleanup_fail(HARK_ERR_CUDA, std::string("sort(pass): ") + cudaGetErrorString(e));
     }
-    ctx->dfree(d_status);
-    if (e != cudaSuccess) return cleanup_fail(HARK_ERR_CUDA, std::string("sort(pass): ") + cudaGetErrorString(e));
     const int fb = (npass - 1) & 1;
     for (auto &a : arrays) {
         a.result = a.buf[fb];

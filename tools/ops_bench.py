@@ -43,9 +43,14 @@ def peak():
 
 
 def timed(env, fn, reps):
+    """One untimed warm-up (grows the context's memory pool, loads the kernels), then `reps` timed runs; every
+    result but the last is freed before the next run so that the pool never has to grow inside a timed run."""
     import torch
-    out = []
-    for _ in range(reps):
+    fn().free()
+    best, r = None, None
+    for i in range(reps):
+        if r is not None:
+            r.free()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         r = fn()
@@ -53,12 +58,9 @@ def timed(env, fn, reps):
         wall = (time.perf_counter() - t0) * 1e3
         st = env.stats()
         st["wall_ms"] = wall
-        out.append((st, r))
-    best = min(out, key=lambda x: x[0]["total_ms"])
-    for st, r in out:
-        if r is not best[1]:
-            r.free()
-    return best
+        if best is None or st["total_ms"] < best["total_ms"]:
+            best = st
+    return best, r
 
 
 def line(name, n, st, extra=None):
