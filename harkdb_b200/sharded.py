@@ -104,6 +104,19 @@ def pick_splitters(samples: Sequence[np.ndarray], weights: Sequence[float], npar
     return out
 
 
+def splitters_to_int64(sp_ordkeys: np.ndarray, dtype_code: int) -> np.ndarray:
+    """Order keys (uint64) of an INTEGER column back to values whose int64 order is the column's order
+    (i32: value; u32: value as a non-negative int64; i64: value)."""
+    sp = np.asarray(sp_ordkeys, dtype=np.uint64)
+    if dtype_code == I32:
+        return (sp.astype(np.int64) - (1 << 31)).astype(np.int64)
+    if dtype_code == U32:
+        return sp.astype(np.int64)
+    if dtype_code == I64:
+        return (sp ^ np.uint64(1 << 63)).view(np.int64)
+    raise ValueError("split_sorted: integer key columns only")
+
+
 # ------------------------------------------------------------------------------------------------------------
 # engines
 # ------------------------------------------------------------------------------------------------------------
@@ -158,6 +171,23 @@ class HarkEngine:
     def empty(self, n, dtype_code):
         return self.torch.empty(n, dtype=_torch_dtype(dtype_code), device=self.device)
 
+    def split_sorted(self, t, key_col, splitters):
+        """Rows per destination of a table already sorted ascending by the integer column key_col:
+        destination of a row = number of splitters <= its key (partition_by_splitters' rule), found by a
+        boundary search instead of a partition pass."""
+        torch = self.torch
+        n = t.shape[0]
+        dt = t.dtypes[key_col]
+        sp = splitters_to_int64(np.asarray(splitters, dtype=np.uint64).reshape(-1), dt)
+        if n == 0:
+            return [0] * (len(sp) + 1)
+        k = self.columns_torch(t)[key_col]
+        if dt == U32:
+            k = k.to(torch.int64) & 0xFFFFFFFF
+        b = torch.searchsorted(k, torch.from_numpy(sp).to(k.device).to(k.dtype), right=False).cpu().tolist()
+        edges = [0] + [int(x) for x in b] + [n]
+        return [edges[i + 1] - edges[i] for i in range(len(edges) - 1)]
+
     def to_numpy_columns(self, t):
         return t.columns()
 
@@ -192,7 +222,8 @@ class ShardTable:
 class ShardedEnv:
     """Same call surface as hark_ffi.Futhark, over row-range shards (see module docstring)."""
 
-    def __init__(self, engine, group=None, oversample: int = 64):
+    def __init__(self, engine, group=None, oversample: int = 64, trace: Optional[bool] = None):
+        import os
         import torch.distributed as dist
         self.dist = dist
         self.engine = engine
@@ -200,6 +231,34 @@ class ShardedEnv:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.oversample = oversample
+        # phase tracing (HARK_SHARD_TRACE=1): host wall time per phase with a device sync on both sides
+        self.trace_on = bool(int(os.environ.get("HARK_SHARD_TRACE", "0"))) if trace is None else trace
+        self.trace = {}
+
+    class _Phase:
+        def __init__(self, senv, name):
+            self.senv, self.name = senv, name
+
+        def __enter__(self):
+            if self.senv.trace_on:
+                import time
+                self.senv.engine.sync()
+                self.t0 = time.perf_counter()
+
+        def __exit__(self, *exc):
+            if self.senv.trace_on:
+                import time
+                self.senv.engine.sync()
+                tr = self.senv.trace
+                tr[self.name] = tr.get(self.name, 0.0) + (time.perf_counter() - self.t0) * 1e3
+            return False
+
+    def phase(self, name):
+        return ShardedEnv._Phase(self, name)
+
+    def pop_trace(self):
+        t, self.trace = self.trace, {}
+        return t
 
     # ---- plumbing ----
     def _wrap(self, local) -> ShardTable:
@@ -265,22 +324,55 @@ class ShardedEnv:
             outs.append(torch.cat([p[: ns[r]] for r, p in enumerate(parts)]))
         return eng.from_torch(outs, dts), True
 
+    def _gather_samples(self, mine: np.ndarray, n_local: int, nk: int):
+        """All ranks' sample tuples and weights with ONE pair of tensor all-gathers (fixed-size, padded)."""
+        import torch
+        S = self.oversample * self.world
+        if self.world == 1:
+            return [mine], [n_local / max(len(mine), 1)]
+        buf = np.zeros((S + 1, nk), dtype=np.uint64)
+        buf[: len(mine)] = mine
+        buf[S, 0] = len(mine)
+        dev = self.engine.device
+        t = torch.from_numpy(buf.view(np.int64)).to(dev)
+        w = torch.tensor([float(n_local)], dtype=torch.float64, device=dev)
+        outs = [torch.empty_like(t) for _ in range(self.world)]
+        ws = [torch.empty_like(w) for _ in range(self.world)]
+        self.dist.all_gather(outs, t, group=self.group)
+        self.dist.all_gather(ws, w, group=self.group)
+        samples, weights = [], []
+        for o, wt in zip(outs, ws):
+            a = o.cpu().numpy().view(np.uint64)
+            cnt = int(a[S, 0])
+            samples.append(a[:cnt].copy())
+            weights.append(float(wt.item()) / max(cnt, 1))
+        return samples, weights
+
     def choose_splitters(self, local, key_cols, desc) -> np.ndarray:
         nk = len(key_cols)
         n_local = local.shape[0]
-        pos = sample_positions(n_local, self.oversample * self.world)
-        mine = self.engine.sample_order_keys(local, key_cols, desc, pos) if len(pos) else np.zeros((0, nk), np.uint64)
-        gathered = [None] * self.world
-        self.dist.all_gather_object(gathered, (mine, n_local / max(len(pos), 1)), group=self.group)
-        return pick_splitters([g[0] for g in gathered], [g[1] for g in gathered], self.world, nk)
+        with self.phase("sample"):
+            pos = sample_positions(n_local, self.oversample * self.world)
+            mine = self.engine.sample_order_keys(local, key_cols, desc, pos) if len(pos) else np.zeros((0, nk), np.uint64)
+            samples, weights = self._gather_samples(mine, n_local, nk)
+        return pick_splitters(samples, weights, self.world, nk)
 
-    def repartition(self, local, key_cols, desc, splitters=None):
-        """Range-repartition a shard by key tuple; returns the rows this rank now owns (source-rank order)."""
+    def repartition(self, local, key_cols, desc, splitters=None, sorted_by_key: bool = False):
+        """Range-repartition a shard by key tuple; returns the rows this rank now owns (source-rank order).
+        sorted_by_key: the shard is already ascending in its single integer key column (a GROUP BY result), so the
+        destinations are contiguous slices and no partition pass is needed."""
         if splitters is None:
             splitters = self.choose_splitters(local, key_cols, desc)
-        part, counts = self.engine.partition_by_splitters(local, key_cols, desc, splitters, self.world)
+        if sorted_by_key and len(key_cols) == 1 and not desc[0]:
+            with self.phase("split_sorted"):
+                counts = self.engine.split_sorted(local, key_cols[0], splitters)
+            with self.phase("exchange"):
+                return self.exchange(local, counts)
+        with self.phase("partition"):
+            part, counts = self.engine.partition_by_splitters(local, key_cols, desc, splitters, self.world)
         try:
-            return self.exchange(part, counts)
+            with self.phase("exchange"):
+                return self.exchange(part, counts)
         finally:
             part.free()
 
@@ -331,24 +423,26 @@ class ShardedEnv:
         eng = self.engine
         p_ops = expand_partial_ops(list(range(len(ops))), ops, pinned_u32)[1]
         if self.world > 1:
-            recv = self.repartition(part, [0], [0])
+            recv = self.repartition(part, [0], [0], sorted_by_key=True)     # partial groups come out key-ordered
             part.free()
             m = recv.shape[1]
-            if pinned_u32:
-                merged = eng.query_groupby(recv, 0, list(range(1, m)), merge_ops_for(p_ops))
-            else:
-                merged = eng.query_groupby_ex(recv, 0, list(range(1, m)), merge_ops_for(p_ops))
+            with self.phase("merge"):
+                if pinned_u32:
+                    merged = eng.query_groupby(recv, 0, list(range(1, m)), merge_ops_for(p_ops))
+                else:
+                    merged = eng.query_groupby_ex(recv, 0, list(range(1, m)), merge_ops_for(p_ops))
             recv.free()
         else:
             merged = part
         if pinned_u32:
             return merged
-        final = eng.groupby_finalize(merged, final_ops_for(ops))
-        merged.free()
-        if having:
-            f2 = eng.query_filter(final, list(range(final.shape[1])), list(having))
-            final.free()
-            final = f2
+        with self.phase("finalize"):
+            final = eng.groupby_finalize(merged, final_ops_for(ops))
+            merged.free()
+            if having:
+                f2 = eng.query_filter(final, list(range(final.shape[1])), list(having))
+                final.free()
+                final = f2
         return final
 
     def query_groupby(self, db, g_col, s_cols, t_cols) -> ShardTable:
@@ -370,7 +464,8 @@ class ShardedEnv:
         t, tmp = self._as_shard(db)
         try:
             p_s, p_ops = expand_partial_ops([int(x) for x in s_cols], ops)
-            part = self.engine.query_groupby_ex(t.local, g_col, p_s, p_ops)
+            with self.phase("local"):
+                part = self.engine.query_groupby_ex(t.local, g_col, p_s, p_ops)
             return self._wrap(self._merge_groups(part, [int(x) for x in ops], False, having))
         finally:
             if tmp:
@@ -394,7 +489,8 @@ class ShardedEnv:
                 if proj is not t.local:
                     proj.free()
             try:
-                return self._wrap(self.engine.query_orderby(recv, [need.index(c) for c in cols], k2, desc))
+                with self.phase("local"):
+                    return self._wrap(self.engine.query_orderby(recv, [need.index(c) for c in cols], k2, desc))
             finally:
                 recv.free()
         finally:
@@ -406,10 +502,12 @@ class ShardedEnv:
         tf, tmpf = self._as_shard(fact)
         td, tmpd = self._as_shard(dim)
         try:
-            dim_full, dtmp = self.allgather_table(td.local)          # dim << fact: broadcast the build side
+            with self.phase("allgather_dim"):
+                dim_full, dtmp = self.allgather_table(td.local)      # dim << fact: broadcast the build side
             try:
                 p_s, p_ops = expand_partial_ops([int(x) for x in s_cols], ops)
-                part = self.engine.join_groupby(tf.local, dim_full, fk_col, pk_col, g_col, p_s, p_ops)
+                with self.phase("local"):
+                    part = self.engine.join_groupby(tf.local, dim_full, fk_col, pk_col, g_col, p_s, p_ops)
             finally:
                 if dtmp:
                     dim_full.free()
@@ -432,13 +530,9 @@ class ShardedEnv:
                     from .hark_ffi import HarkError
                     raise HarkError(1, "sharded join: key columns must be stored as u32 (the reference's key order)")
             # splitters from both sides' keys, so neither side can overload a rank
-            nk = 1
-            s1 = self._samples(t1.local, [col1])
-            s2 = self._samples(t2.local, [col2])
-            gathered = [None] * self.world
-            self.dist.all_gather_object(gathered, (s1, s2), group=self.group)
-            sp = pick_splitters([g[0][0] for g in gathered] + [g[1][0] for g in gathered],
-                                [g[0][1] for g in gathered] + [g[1][1] for g in gathered], self.world, nk)
+            s1, w1 = self._samples(t1.local, [col1])
+            s2, w2 = self._samples(t2.local, [col2])
+            sp = pick_splitters(s1 + s2, w1 + w2, self.world, 1)
             r1 = self.repartition(t1.local, [col1], [0], sp)
             r2 = self.repartition(t2.local, [col2], [0], sp)
             try:
@@ -457,7 +551,7 @@ class ShardedEnv:
         pos = sample_positions(n_local, self.oversample * self.world)
         k = self.engine.sample_order_keys(local, key_cols, [0] * len(key_cols), pos) if len(pos) else \
             np.zeros((0, len(key_cols)), np.uint64)
-        return k, n_local / max(len(pos), 1)
+        return self._gather_samples(k, n_local, len(key_cols))
 
     def sync(self):
         self.engine.sync()

@@ -113,6 +113,14 @@ class OracleEngine:
         rows = np.asarray(rows, dtype=np.int64)
         return np.stack([_ordkey64(t.cols[int(k)][rows], bool(d)) for k, d in zip(key_cols, desc)], axis=1)
 
+    def split_sorted(self, t, key_col, splitters):
+        from harkdb_b200.sharded import splitters_to_int64
+        k = t.cols[int(key_col)]
+        sp = splitters_to_int64(np.asarray(splitters, dtype=np.uint64).reshape(-1), NO.dtype_code(k))
+        b = np.searchsorted(k.astype(np.int64), sp, side="left")
+        edges = [0] + [int(x) for x in b] + [len(k)]
+        return [edges[i + 1] - edges[i] for i in range(len(edges) - 1)]
+
     def partition_by_splitters(self, t, key_cols, desc, splitters, nparts):
         n = t.shape[0]
         sp = np.asarray(splitters, dtype=np.uint64).reshape(nparts - 1, len(key_cols))

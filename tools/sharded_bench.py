@@ -95,6 +95,8 @@ def main():
 
     def emit(d):
         d.update(n_gpus=world, scaling="strong" if args.strong else "weak")
+        if senv.trace_on:      # HARK_SHARD_TRACE=1: phase times include a device sync each, so they sum to more than `ms`
+            d["trace_ms_rank0"] = {k: round(v / (args.reps + 0), 3) for k, v in senv.pop_trace().items()}
         results.append(d)
         if rank == 0:
             print(json.dumps(d), flush=True)
