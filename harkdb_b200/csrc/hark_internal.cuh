@@ -49,6 +49,7 @@ struct hark_ctx {
     int64_t total_launches = 0;
     int64_t entry_launches = 0;
     std::map<std::string, int64_t> opts;
+    struct hk_peer_state *peer = nullptr; // K8c: receive arena + the other ranks' arenas (repartition.cu)
 
     int fail(int code, const std::string &msg) {
         err = msg;
@@ -111,6 +112,8 @@ struct hark_ctx {
 static inline int hk_dtype_size(int dt) { return (dt == HARK_I64 || dt == HARK_F64) ? 8 : 4; }
 static inline bool hk_dtype_ok(int dt) { return dt >= HARK_I32 && dt <= HARK_F64; }
 static inline bool hk_dtype_int(int dt) { return dt == HARK_I32 || dt == HARK_U32 || dt == HARK_I64; }
+
+void hk_peer_destroy(hark_ctx *ctx); // repartition.cu
 
 // new table with m owned columns of capacity cap rows (uninitialised)
 int hk_table_alloc(hark_ctx *ctx, hark_table **out, int64_t n, int64_t cap, const int32_t *dtypes, int64_t m);

@@ -337,6 +337,9 @@ struct LsdParams {
     uint32_t *chunk_counts;           // [num_chunks][256]
     unsigned long long *chunk_base;   // [num_chunks][256]
     unsigned long long *offsets;      // [257]
+    // peer mode (K8c): digit = destination GPU; peer_out[a * HK_PEER_MAX + d] = byte address such that element
+    // (chunk_base + position) of array a lands at its final slot in GPU d's receive arena (NVLink stores)
+    const unsigned long long *peer_out;
 };
 
 template <int KW>
@@ -458,8 +461,28 @@ __device__ __forceinline__ void lsd_write_out(OT *o, const uint64_t *stage, cons
     }
 }
 
-// RANK: 0 = match.any, 1 = eight ballots (register-only multisplit)
-template <int KW, int RANK>
+// peer mode: the base pointer depends on the digit (= destination GPU); s_peer = this array's HK_PEER_MAX addresses
+template <typename OT>
+__device__ __forceinline__ void lsd_write_out_peer(const unsigned long long *s_peer, const uint64_t *stage, const uint8_t *s_digit,
+                                                   const uint64_t *s_gbase, int count, int tid) {
+    if (count == LTILE) {
+#pragma unroll
+        for (int i = 0; i < LI; i++) {
+            const int j = i * LT + tid;
+            const int d = s_digit[j];
+            reinterpret_cast<OT *>(s_peer[d])[s_gbase[d] + (uint64_t)j] = (OT)stage[j];
+        }
+    } else {
+        for (int j = tid; j < count; j += LT) {
+            const int d = s_digit[j];
+            reinterpret_cast<OT *>(s_peer[d])[s_gbase[d] + (uint64_t)j] = (OT)stage[j];
+        }
+    }
+}
+
+// RANK: 0 = match.any, 1 = eight ballots (register-only multisplit).  PEER: outputs go to per-digit base addresses
+// (other GPUs' arenas) and the key array itself (the destination digit) is not written anywhere.
+template <int KW, int RANK, bool PEER = false>
 __global__ void __launch_bounds__(LT, 2) hk_lsd_scatter_kernel(const __grid_constant__ LsdParams P) {
     using KT = typename KeyRaw<KW>::T;
     extern __shared__ __align__(16) unsigned char s_dyn[];
@@ -470,6 +493,7 @@ __global__ void __launch_bounds__(LT, 2) hk_lsd_scatter_kernel(const __grid_cons
     __shared__ uint64_t s_run[256];
     __shared__ uint8_t s_digit[LTILE];
     __shared__ uint32_t s_wtot[8];
+    __shared__ unsigned long long s_peer[PEER ? MAXA * HK_PEER_MAX : 1];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -478,6 +502,8 @@ __global__ void __launch_bounds__(LT, 2) hk_lsd_scatter_kernel(const __grid_cons
     const int64_t t1 = min(P.num_tiles, t0 + P.tiles_per_chunk);
     if (tid < 256) s_run[tid] = P.chunk_base[(size_t)blockIdx.x * 256 + tid];
     for (int i = tid; i < LWARPS * 256; i += LT) (&wh[0][0])[i] = 0;
+    if constexpr (PEER)
+        for (int i = tid; i < P.na * HK_PEER_MAX; i += LT) s_peer[i] = P.peer_out[i];
     if (t0 >= t1) return;
     const int first_other = P.ka == 0 ? (P.na > 1 ? 1 : -1) : 0;
 
@@ -565,7 +591,7 @@ __global__ void __launch_bounds__(LT, 2) hk_lsd_scatter_kernel(const __grid_cons
         }
         __syncthreads();
         for (int i = tid; i < LWARPS * 256; i += LT) (&wh[0][0])[i] = 0; // last read above; next written after >= 1 barrier
-        lsd_write_out<KT>(reinterpret_cast<KT *>(P.out[P.ka]), stage, s_digit, s_gbase, cur_count, tid);
+        if constexpr (!PEER) lsd_write_out<KT>(reinterpret_cast<KT *>(P.out[P.ka]), stage, s_digit, s_gbase, cur_count, tid);
         // ---- the other carried arrays ride the same permutation; array a+1 is loaded while array a is written ----
         for (int a = first_other; a >= 0 && a < P.na;) {
             __syncthreads(); // everyone has read the previous array out of `stage`
@@ -578,8 +604,13 @@ __global__ void __launch_bounds__(LT, 2) hk_lsd_scatter_kernel(const __grid_cons
             if (nxt == P.ka) nxt++;
             if (nxt < P.na) lsd_load_vals(P.in[nxt], P.width[nxt], tile_base, cur_count, warp, lane, v);
             __syncthreads();
-            if (P.width[a] == 4) lsd_write_out<uint32_t>(reinterpret_cast<uint32_t *>(P.out[a]), stage, s_digit, s_gbase, cur_count, tid);
-            else lsd_write_out<uint64_t>(reinterpret_cast<uint64_t *>(P.out[a]), stage, s_digit, s_gbase, cur_count, tid);
+            if constexpr (PEER) {
+                if (P.width[a] == 4) lsd_write_out_peer<uint32_t>(s_peer + a * HK_PEER_MAX, stage, s_digit, s_gbase, cur_count, tid);
+                else lsd_write_out_peer<uint64_t>(s_peer + a * HK_PEER_MAX, stage, s_digit, s_gbase, cur_count, tid);
+            } else {
+                if (P.width[a] == 4) lsd_write_out<uint32_t>(reinterpret_cast<uint32_t *>(P.out[a]), stage, s_digit, s_gbase, cur_count, tid);
+                else lsd_write_out<uint64_t>(reinterpret_cast<uint64_t *>(P.out[a]), stage, s_digit, s_gbase, cur_count, tid);
+            }
             a = nxt;
         }
         __syncthreads(); // stage / s_digit are rewritten by the next tile
@@ -595,6 +626,7 @@ int lsd_pass(hark_ctx *ctx, LsdParams &P, int kw, unsigned long long **d_offsets
     const bool ballots = ctx->opt("sort.rank", 1) == 1;
     void (*scatter)(const LsdParams) = kw == 4 ? (ballots ? hk_lsd_scatter_kernel<4, 1> : hk_lsd_scatter_kernel<4, 0>)
                                                : (ballots ? hk_lsd_scatter_kernel<8, 1> : hk_lsd_scatter_kernel<8, 0>);
+    if (P.peer_out) scatter = hk_lsd_scatter_kernel<4, 1, true>; // the key is the 4-byte destination digit
     cudaError_t e = cudaFuncSetAttribute(scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scatter, LT, smem);
     if (e != cudaSuccess) return ctx->fail(HARK_ERR_CUDA, std::string("sort(pass setup): ") + cudaGetErrorString(e));
@@ -663,6 +695,29 @@ int bit_width_u64(uint64_t v) {
 }
 
 } // namespace
+
+// K8c: one stable pass keyed on a u32 destination digit (< HK_PEER_MAX) whose outputs are peer addresses.
+// cols/widths: the carried table columns; d_peer_out: device array [(1 + ncols) * HK_PEER_MAX] of byte addresses
+// (row 0, the digit array's, is unused).
+int hk_peer_scatter_pass(hark_ctx *ctx, int64_t n, const void *digit, const void *const *cols, const int *widths, int ncols,
+                         const unsigned long long *d_peer_out) {
+    if (ncols + 1 > MAXA) return ctx->fail(HARK_ERR_UNSUPPORTED, "peer scatter: too many columns");
+    if (n == 0) return HARK_OK;
+    LsdParams P;
+    memset(&P, 0, sizeof P);
+    P.f = DigitFn{HARK_U32, 0, 0, 0, 0xffu, 0, 0};
+    P.na = ncols + 1;
+    P.ka = 0;
+    P.in[0] = digit;
+    P.width[0] = 4;
+    for (int c = 0; c < ncols; c++) {
+        P.in[1 + c] = cols[c];
+        P.width[1 + c] = widths[c];
+    }
+    P.n = n;
+    P.peer_out = d_peer_out;
+    return lsd_pass(ctx, P, 4, nullptr);
+}
 
 int hk_iota(hark_ctx *ctx, void *out, int64_t n, int width) {
     if (n == 0) return HARK_OK;

@@ -5,6 +5,7 @@
 #include "hark_internal.cuh"
 
 #define HK_SORT_MAX_ARRAYS 20
+#define HK_PEER_MAX 16 // GPUs a peer scatter can address (one NVSwitch domain)
 
 struct hk_sort_keyspec {
     int array;     // index into the carried arrays
@@ -31,3 +32,5 @@ int hk_radix_sort(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec> &
 int hk_iota(hark_ctx *ctx, void *out, int64_t n, int width);
 int hk_gather(hark_ctx *ctx, void *dst, const void *src, int vwidth, const void *perm, int pwidth, int64_t n);
 int hk_copy_bytes(hark_ctx *ctx, void *dst, const void *src, int64_t bytes);
+int hk_peer_scatter_pass(hark_ctx *ctx, int64_t n, const void *digit, const void *const *cols, const int *widths, int ncols,
+                         const unsigned long long *d_peer_out);

@@ -96,6 +96,13 @@ SIGNATURES = {
     "hark_table_sample_order_keys": (C.c_int, [_P, _P, _I32P, _I32P, C.c_int64, C.POINTER(C.c_int64), C.c_int64,
                                                C.POINTER(C.c_uint64)]),
     "hark_entry_groupby_finalize": (C.c_int, [_P, C.POINTER(_P), _P, _I32P, C.c_int64]),
+    "hark_peer_arena_create": (C.c_int, [_P, C.c_int64, _P]),
+    "hark_peer_arena_open": (C.c_int, [_P, _P, C.c_int32, C.c_int32]),
+    "hark_peer_arena_close": (C.c_int, [_P]),
+    "hark_peer_arena_bytes_needed": (C.c_int64, [_P, _P, C.c_int64]),
+    "hark_peer_scatter_count": (C.c_int, [_P, _P, _I32P, _I32P, C.c_int64, C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]),
+    "hark_peer_scatter_run": (C.c_int, [_P, _P, C.POINTER(C.c_int64)]),
+    "hark_peer_scatter_result": (C.c_int, [_P, C.POINTER(_P)]),
     "hark_table_slice": (C.c_int, [_P, C.POINTER(_P), _P, C.c_int64, C.c_int64]),
     "hark_table_concat": (C.c_int, [_P, C.POINTER(_P), _P, _P]),
     "hark_stats_last": (C.c_int, [_P, C.POINTER(HarkStats)]),
@@ -485,6 +492,42 @@ class Futhark:
             self.ctx, t.handle, _i32p(kc), _i32p(d), len(kc), r.ctypes.data_as(C.POINTER(C.c_int64)), len(r),
             out.ctypes.data_as(C.POINTER(C.c_uint64))))
         return out
+
+    # ---- K8c: partition fused with the exchange over NVLink peer memory ----
+    def peer_arena_create(self, nbytes: int) -> bytes:
+        """Allocates this rank's receive arena; returns its 64-byte CUDA IPC handle (to be all-gathered)."""
+        buf = C.create_string_buffer(64)
+        self._check(self.lib.hark_peer_arena_create(self.ctx, int(nbytes), buf))
+        return buf.raw
+
+    def peer_arena_open(self, handles: Sequence[bytes], my_rank: int):
+        blob = b"".join(handles)
+        self._check(self.lib.hark_peer_arena_open(self.ctx, C.c_char_p(blob), len(handles), my_rank))
+
+    def peer_arena_close(self):
+        self._check(self.lib.hark_peer_arena_close(self.ctx))
+
+    def peer_arena_bytes_needed(self, t: DeviceTable, rows: int) -> int:
+        return int(self.lib.hark_peer_arena_bytes_needed(self.ctx, t.handle, int(rows)))
+
+    def peer_scatter_count(self, t: DeviceTable, key_cols, desc, splitters: np.ndarray, world: int) -> List[int]:
+        kc = _i32arr(key_cols)
+        d = _i32arr(desc if desc is not None else [0] * len(kc))
+        sp = np.ascontiguousarray(np.asarray(splitters, dtype=np.uint64).reshape(-1))
+        counts = (C.c_int64 * world)()
+        self._check(self.lib.hark_peer_scatter_count(
+            self.ctx, t.handle, _i32p(kc), _i32p(d), len(kc),
+            sp.ctypes.data_as(C.POINTER(C.c_uint64)) if sp.size else None, counts))
+        return [int(x) for x in counts]
+
+    def peer_scatter_run(self, t: DeviceTable, counts_matrix: np.ndarray):
+        cm = np.ascontiguousarray(np.asarray(counts_matrix, dtype=np.int64))
+        self._check(self.lib.hark_peer_scatter_run(self.ctx, t.handle, cm.ctypes.data_as(C.POINTER(C.c_int64))))
+
+    def peer_scatter_result(self) -> DeviceTable:
+        h = C.c_void_p()
+        self._check(self.lib.hark_peer_scatter_result(self.ctx, C.byref(h)))
+        return DeviceTable(self, h.value)
 
     def groupby_finalize(self, merged: DeviceTable, ops) -> DeviceTable:
         o = _i32arr(ops)

@@ -171,6 +171,59 @@ class HarkEngine:
     def empty(self, n, dtype_code):
         return self.torch.empty(n, dtype=_torch_dtype(dtype_code), device=self.device)
 
+    # ---- K8c: partition fused with the exchange (NVLink peer stores into the destination's arena) ----
+    def peer_setup(self, senv, arena_bytes: int) -> bool:
+        """Creates this rank's receive arena and maps everybody else's.  Collective; False on every rank if any rank
+        cannot (no CUDA IPC in this environment, allocation failure): the NCCL path is used instead."""
+        from .hark_ffi import HarkError
+        ok, handle = 1, b""
+        try:
+            handle = self.env.peer_arena_create(arena_bytes)
+        except HarkError:
+            ok = 0
+        got = [None] * senv.world
+        senv.dist.all_gather_object(got, (ok, handle), group=senv.group)
+        if not all(g[0] for g in got):
+            self._peer_close_quietly()
+            return False
+        try:
+            self.env.peer_arena_open([g[1] for g in got], senv.rank)
+        except HarkError:
+            ok = 0
+        flags = [None] * senv.world
+        senv.dist.all_gather_object(flags, ok, group=senv.group)
+        if not all(flags):
+            self._peer_close_quietly()
+            return False
+        self.peer_bytes = int(arena_bytes)
+        return True
+
+    def _peer_close_quietly(self):
+        try:
+            self.env.peer_arena_close()
+        except Exception:
+            pass
+
+    def peer_repartition(self, senv, local, key_cols, desc, splitters):
+        """Returns the rows this rank owns after the exchange (a view of its arena), or None when the rows of some
+        destination would not fit its arena (decided identically on every rank from the all-gathered counts)."""
+        torch = self.torch
+        world = senv.world
+        with senv.phase("peer_count"):
+            mine = self.env.peer_scatter_count(local, key_cols, desc, splitters, world)
+            t = torch.tensor(mine, dtype=torch.int64, device=self.device)
+            rows = [torch.empty_like(t) for _ in range(world)]
+            senv.dist.all_gather(rows, t, group=senv.group)
+            cm = torch.stack(rows).cpu().numpy()                       # [src][dst]
+        need = max(self.env.peer_arena_bytes_needed(local, int(cm[:, d].sum())) for d in range(world))
+        if need > self.peer_bytes:
+            return None
+        with senv.phase("peer_scatter"):
+            self.env.peer_scatter_run(local, cm)
+            # "every rank's stores into my arena have landed": one stream-ordered collective after the scatter
+            senv.dist.all_reduce(torch.zeros(1, device=self.device), group=senv.group)
+        return self.env.peer_scatter_result()
+
     def split_sorted(self, t, key_col, splitters):
         """Rows per destination of a table already sorted ascending by the integer column key_col:
         destination of a row = number of splitters <= its key (partition_by_splitters' rule), found by a
@@ -234,6 +287,12 @@ class ShardedEnv:
         # phase tracing (HARK_SHARD_TRACE=1): host wall time per phase with a device sync on both sides
         self.trace_on = bool(int(os.environ.get("HARK_SHARD_TRACE", "0"))) if trace is None else trace
         self.trace = {}
+        # K8c peer-memory exchange: on when the engine offers it and CUDA IPC works (HARK_PEER=0 forces NCCL;
+        # HARK_PEER_ARENA_GB sizes the receive arena, default 24)
+        self.peer = False
+        if self.world > 1 and hasattr(engine, "peer_setup") and os.environ.get("HARK_PEER", "1") != "0":
+            gb = float(os.environ.get("HARK_PEER_ARENA_GB", "24"))
+            self.peer = bool(engine.peer_setup(self, int(gb * (1 << 30))))
 
     class _Phase:
         def __init__(self, senv, name):
@@ -368,6 +427,10 @@ class ShardedEnv:
                 counts = self.engine.split_sorted(local, key_cols[0], splitters)
             with self.phase("exchange"):
                 return self.exchange(local, counts)
+        if self.peer:
+            got = self.engine.peer_repartition(self, local, key_cols, desc, splitters)
+            if got is not None:
+                return got
         with self.phase("partition"):
             part, counts = self.engine.partition_by_splitters(local, key_cols, desc, splitters, self.world)
         try:
@@ -534,6 +597,10 @@ class ShardedEnv:
             s2, w2 = self._samples(t2.local, [col2])
             sp = pick_splitters(s1 + s2, w1 + w2, self.world, 1)
             r1 = self.repartition(t1.local, [col1], [0], sp)
+            if self.peer:   # r1 may be a view of the receive arena, which the next exchange overwrites
+                keep = self.engine.query_filter(r1, list(range(r1.shape[1])), [])
+                r1.free()
+                r1 = keep
             r2 = self.repartition(t2.local, [col2], [0], sp)
             try:
                 return self._wrap(self.engine.join(r1, r2, col1, col2, cols1, cols2))

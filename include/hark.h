@@ -188,6 +188,23 @@ int hark_table_sample_order_keys(hark_ctx *ctx, const hark_table *db, const int3
  * Output [key, agg_1..agg_c] with AVG = sum / count.                                                       */
 int hark_entry_groupby_finalize(hark_ctx *ctx, hark_table **out, const hark_table *merged, const int32_t *ops,
                                 int64_t c);
+/* ---- K8c: partition fused with the exchange over NVLink peer memory (one process per GPU, CUDA IPC) ----
+ * Every rank creates a receive arena and passes its 64-byte IPC handle around (any transport; the Python layer
+ * uses torch.distributed); after hark_peer_arena_open the scatter below stores rows directly into the destination
+ * GPUs' arenas.  Protocol per exchange: count -> (ranks all-gather counts) -> run -> (one stream-ordered
+ * collective) -> result.  The result table is a view of this rank's arena, valid until the next exchange.       */
+int hark_peer_arena_create(hark_ctx *ctx, int64_t bytes, void *ipc_handle_out /* 64 bytes */);
+int hark_peer_arena_open(hark_ctx *ctx, const void *handles /* world x 64 bytes, rank order */, int32_t world,
+                         int32_t my_rank);
+int hark_peer_arena_close(hark_ctx *ctx);
+/* arena bytes a rank needs to receive `rows` rows of db's schema */
+int64_t hark_peer_arena_bytes_needed(hark_ctx *ctx, const hark_table *db, int64_t rows);
+/* destination of a row = number of splitters <= its key tuple (as hark_table_partition_by_splitters, nparts = world) */
+int hark_peer_scatter_count(hark_ctx *ctx, const hark_table *db, const int32_t *key_cols, const int32_t *desc, int64_t nk,
+                            const uint64_t *splitters, int64_t *counts_out /* [world] */);
+int hark_peer_scatter_run(hark_ctx *ctx, const hark_table *db, const int64_t *counts_matrix /* [src][dst], world x world */);
+int hark_peer_scatter_result(hark_ctx *ctx, hark_table **out);
+
 /* Stable partition of rows into nparts buckets by mix(key) % nparts (integer key column);
  * counts_out[nparts] (host) receives the bucket sizes; rows of bucket p are contiguous.        */
 int hark_table_partition_by_hash(hark_ctx *ctx, hark_table **out, const hark_table *db, int32_t key_col,
