@@ -44,6 +44,22 @@ PREDS = [(1, GT, 0, T_CONST), (4, LT, 0, U_CONST)]
 SEED = 42
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one hk_filter2_kernel launch of THIS workload, from the committed
+    `ncu --set full` capture (profiles/r01_filter_v2_final_ncu.txt; bench.py never runs under a profiler)."""
+    try:
+        rd = wr = None
+        for line in open(os.path.join(ROOT, "profiles", "r01_filter_v2_final_ncu.txt")):
+            line = line.strip()
+            if line.startswith("dram__bytes_read.sum") and rd is None:
+                rd = float(line.split("=")[1].split()[0]) * 1e9
+            if line.startswith("dram__bytes_write.sum") and wr is None:
+                wr = float(line.split("=")[1].split()[0]) * 1e9
+        return int(rd + wr) if rd is not None and wr is not None else None
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -315,7 +331,9 @@ def run_gpu_arm(args):
                    "l2_policy": f"inputs larger than L2 ({rows * 16 / 1e9:.1f} GB read per step vs 126 MB L2)",
                    "parallelism": f"row-range shards x{world}, no collective"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "hk_filter2_kernel<4,2,2>" if args.filter_impl in (0, 3) else "hk_filter_kernel<4,2,2>", "kernel_ms": k_ms,
+                     "traffic": ncu_traffic_bytes() if rows == 10 ** 9 else None,
+                     "traffic_source": "profiles/r01_filter_v2_final_ncu.txt (ncu --set full, same workload, per launch)",
+                     "kernel": "hk_filter2_kernel<4,2,2>" if args.filter_impl in (0, 3) else "hk_filter_kernel<4,2,2>", "kernel_ms": k_ms,
                      "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                      "frac_of_nominal_8TBs": achieved / 8000.0,
                      "kernel_share_of_step": k_ms / (elapsed_ms / args.steps)},

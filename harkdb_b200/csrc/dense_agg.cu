@@ -615,6 +615,22 @@ int hk_col_minmax(hark_ctx *ctx, const void *col, int32_t dtype, int64_t n, uint
     return HARK_OK;
 }
 
+int hk_column_minmax(hark_ctx *ctx, const hark_col &col, int64_t n, int32_t dtype, uint64_t *lo, uint64_t *hi) {
+    const bool cacheable = dtype == col.dtype && ctx->opt("stats.cache", 1) != 0;
+    if (cacheable && col.mm_valid) {
+        *lo = col.mm_lo;
+        *hi = col.mm_hi;
+        return HARK_OK;
+    }
+    HK_TRY(hk_col_minmax(ctx, col.ptr, dtype, n, lo, hi));
+    if (cacheable) {
+        col.mm_lo = *lo;
+        col.mm_hi = *hi;
+        col.mm_valid = true;
+    }
+    return HARK_OK;
+}
+
 int hk_dense_groupby(hark_ctx *ctx, hark_table **out, const hk_dense_req &rq, bool *handled) {
     *handled = false;
     const int64_t n = rq.n;

@@ -43,5 +43,7 @@ struct hk_dense_req {
 // 8-byte value columns, ...): the caller then takes the sort path.
 int hk_dense_groupby(hark_ctx *ctx, hark_table **out, const hk_dense_req &rq, bool *handled);
 
-// min / max order key of a column (cached nowhere: one streaming read)
+// min / max order key of a raw column (one streaming read)
 int hk_col_minmax(hark_ctx *ctx, const void *col, int32_t dtype, int64_t n, uint64_t *lo, uint64_t *hi);
+// same for a table column, through the column's cached statistics when `dtype` is the column's own dtype
+int hk_column_minmax(hark_ctx *ctx, const hark_col &col, int64_t n, int32_t dtype, uint64_t *lo, uint64_t *hi);

@@ -632,7 +632,7 @@ int hk_groupby(hark_ctx *ctx, hark_table **out, const hark_table *db, int32_t g_
             rq.agg_val[j] = val_of_col[col];
         }
         if (eligible) {
-            HK_TRY(hk_col_minmax(ctx, rq.key, key_dtype, n, &rq.g_lo, &rq.g_hi));
+            HK_TRY(hk_column_minmax(ctx, db->cols[g_col], n, key_dtype, &rq.g_lo, &rq.g_hi));
             bool handled = false;
             hark_table *t = nullptr;
             HK_TRY(hk_dense_groupby(ctx, &t, rq, &handled));

@@ -24,6 +24,10 @@ struct hark_col {
     void *ptr = nullptr;
     int32_t dtype = HARK_I32;
     bool owned = true;
+    // column statistics (zone map): min / max order key, computed by the first operator that needs them and kept
+    // with the column (columns are immutable once built)
+    mutable bool mm_valid = false;
+    mutable uint64_t mm_lo = 0, mm_hi = 0;
 };
 
 struct hark_table {

@@ -378,7 +378,7 @@ int hk_join_groupby(hark_ctx *ctx, hark_table **out, const hark_table *fact, con
                 rq.agg_val[j] = val_of_col[col];
             }
             if (eligible) {
-                HK_TRY(hk_col_minmax(ctx, dim->cols[g_col].ptr, g_dtype, nd, &rq.g_lo, &rq.g_hi));
+                HK_TRY(hk_column_minmax(ctx, dim->cols[g_col], nd, g_dtype, &rq.g_lo, &rq.g_hi));
                 if (rq.g_hi - rq.g_lo < (1ull << 20)) {
                     unsigned long long *nz = (unsigned long long *)d_mm;
                     HK_CUDA(ctx, cudaMemsetAsync(nz, 0, sizeof(unsigned long long), ctx->stream));
