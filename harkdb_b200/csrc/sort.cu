@@ -38,6 +38,9 @@ struct DigitFn {
     uint32_t mask;
     uint32_t nparts;
     uint64_t base;  // min ordkey (asc) / max ordkey (desc)
+    // integer keys in radix mode skip the generic order-key switch: order key = raw ^ xmask
+    int fast;       // 0 generic, 1 integer ascending, 2 integer descending
+    uint64_t xmask;
 };
 
 template <int KW> struct KeyRaw;
@@ -54,6 +57,17 @@ __device__ __forceinline__ uint64_t norm_key(typename KeyRaw<KW>::T raw, const D
 
 template <int KW>
 __device__ __forceinline__ uint32_t digit_of(typename KeyRaw<KW>::T raw, const DigitFn &f) {
+    if (f.fast) {
+        if constexpr (KW == 4) {
+            const uint32_t u = raw ^ (uint32_t)f.xmask;
+            const uint32_t t = f.fast == 1 ? u - (uint32_t)f.base : (uint32_t)f.base - u;
+            return (t >> f.shift) & f.mask;
+        } else {
+            const uint64_t u = raw ^ f.xmask;
+            const uint64_t t = f.fast == 1 ? u - f.base : f.base - u;
+            return (uint32_t)(t >> f.shift) & f.mask;
+        }
+    }
     if (f.mode == 1) return (uint32_t)(hk_mix64(0x68617368ull, 0, (uint64_t)raw) % f.nparts);
     return (uint32_t)(norm_key<KW>(raw, f) >> f.shift) & f.mask;
 }
@@ -519,6 +533,8 @@ __global__ void __launch_bounds__(LT, 2) hk_lsd_scatter_kernel(const __grid_cons
         uint64_t v[LI];
         if (first_other >= 0) lsd_load_vals(P.in[first_other], P.width[first_other], tile_base, cur_count, warp, lane, v);
         // ---- stable rank of every key among the keys of its warp with the same digit ----
+        // (issuing the 8 counter updates as back-to-back atomics and reading the results after the loop was tried:
+        //  the extra live registers spill under the 64-register cap and the pass got 7 % slower)
         uint32_t rank[LI];
 #pragma unroll
         for (int i = 0; i < LI; i++) {
@@ -705,7 +721,7 @@ int hk_peer_scatter_pass(hark_ctx *ctx, int64_t n, const void *digit, const void
     if (n == 0) return HARK_OK;
     LsdParams P;
     memset(&P, 0, sizeof P);
-    P.f = DigitFn{HARK_U32, 0, 0, 0, 0xffu, 0, 0};
+    P.f = DigitFn{HARK_U32, 0, 0, 0, 0xffu, 0, 0, 1, 0};
     P.na = ncols + 1;
     P.ka = 0;
     P.in[0] = digit;
@@ -815,6 +831,8 @@ int hk_radix_sort(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec> &
                 p.f.mask = (bits - sh >= 8) ? 0xffu : ((1u << (bits - sh)) - 1u);
                 p.f.nparts = 0;
                 p.f.base = keys[k].desc ? hi : lo;
+                p.f.fast = hk_dtype_int(keys[k].dtype) ? (keys[k].desc ? 2 : 1) : 0;
+                p.f.xmask = keys[k].dtype == HARK_I32 ? 0x80000000ull : keys[k].dtype == HARK_I64 ? 0x8000000000000000ull : 0ull;
                 p.hist_slot = (int)passes.size();
                 passes.push_back(p);
             }
@@ -822,7 +840,7 @@ int hk_radix_sort(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec> &
     } else if (n > 0 && hash_nparts > 0) {
         Pass p;
         p.key = 0;
-        p.f = DigitFn{keys[0].dtype, 0, 1, 0, 0xffu, (uint32_t)hash_nparts, 0};
+        p.f = DigitFn{keys[0].dtype, 0, 1, 0, 0xffu, (uint32_t)hash_nparts, 0, 0, 0};
         p.hist_slot = 0;
         passes.push_back(p);
     }
