@@ -381,6 +381,40 @@ def test_groupby_full_size_properties():
         x.free()
 
 
+def test_join_groupby_full_size_properties():
+    """Config 5 (4e9-row fact x 1e8-row dim when memory allows): every fact row matches exactly one dim row, so the
+    group counts add up to the fact rows, the sums to the value column's sum (mod 2^32 per group), and the 1024
+    attribute values come out ascending."""
+    import torch
+    env = get_env()
+    big = free_gb() > 120
+    nf, nd = (4 * 10 ** 9, 10 ** 8) if big else (1 << 27, 1 << 22)
+    a = 2654435761
+    while np.gcd(a, nd) != 1:
+        a += 2
+    dim = env.synth(nd, [NO.I32, NO.I32], [dict(kind=NO.GEN_AFFINE, a=a, b=12345, range=nd), dict(kind=NO.GEN_UNIFORM, lo=0, range=1024)], seed=7)
+    fact = env.synth(nf, [NO.I32, NO.I32], [dict(kind=NO.GEN_UNIFORM, lo=0, range=nd), dict(kind=NO.GEN_UNIFORM, lo=0, range=1000)], seed=42)
+    r = env.join_groupby(fact, dim, 0, 0, 1, [1, 1, 1], [NO.AGG_SUM, NO.AGG_COUNT, NO.AGG_AVG])
+    st = env.stats()
+    keys, sums, cnts, avgs = r.columns()
+    assert np.array_equal(keys, np.arange(1024, dtype=np.int32)) and int(cnts.sum()) == nf
+    total = int(as_torch(fact, 1).sum(dtype=torch.int64).item())
+    assert (int(sums.view(np.uint32).astype(np.uint64).sum()) - total) % (1 << 32) == 0
+    assert abs(float((avgs * cnts).sum()) - total) <= 1e-9 * total            # AVG = exact sum / count
+    # a prefix the oracle can redo: the first 2^20 fact rows against the whole dimension
+    from oracle import c_oracle as CO
+    n0 = 1 << 20
+    fcols = [CO.synth_column(NO.I32, dict(kind=NO.GEN_UNIFORM, lo=0, range=nd), 42, 0, 0, n0),
+             CO.synth_column(NO.I32, dict(kind=NO.GEN_UNIFORM, lo=0, range=1000), 42, 1, 0, n0)]
+    head = env.slice(fact, 0, n0)
+    r0 = env.join_groupby(head, dim, 0, 0, 1, [1, 1], [NO.AGG_SUM, NO.AGG_COUNT])
+    dcols = dim.columns()
+    _check_cols(r0.columns(), NO.join_groupby(fcols, dcols, 0, 0, 1, [1, 1], [NO.AGG_SUM, NO.AGG_COUNT]))
+    print(f"join+groupby {nf} x {nd} rows: {st['total_ms']:.2f} ms")
+    for x in (r0, head, r, fact, dim):
+        x.free()
+
+
 def test_orderby_full_size_properties():
     """Config 4 (2e9 x {i64,i64} when memory allows): sortedness and multiset preservation, checked on device."""
     import torch
