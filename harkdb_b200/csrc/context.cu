@@ -551,6 +551,15 @@ __global__ void __launch_bounds__(256) hk_synth_kernel(void *__restrict__ out, i
             iv = v;
             fv = (double)v;
             ffv = (float)v;
+        } else if (spec.kind == HARK_GEN_LOGUNIFORM) {
+            const uint64_t range = spec.range < 2 ? 2 : spec.range;
+            const int nb = 63 - __clzll((long long)range); // floor(log2 range) >= 1
+            const uint64_t e = __umul64hi(hk_mix64(seed, (uint64_t)col, r), (uint64_t)nb);
+            const uint64_t h2 = hk_mix64(seed ^ 0x5851F42D4C957F2DULL, (uint64_t)col, r);
+            const uint64_t k = ((1ull << e) + (h2 & ((1ull << e) - 1ull)) - 1ull) % range;
+            iv = (uint64_t)spec.lo + k;
+            fv = (double)(long long)iv;
+            ffv = (float)(long long)iv;
         } else {
             iv = (uint64_t)spec.lo;
             fv = spec.flo;
@@ -573,7 +582,7 @@ extern "C" int hark_table_synth(hark_ctx *ctx, hark_table **out, int64_t n, int6
     HK_ARG(ctx, out && n >= 0 && m >= 0 && (m == 0 || (dtypes && specs)), "table_synth: bad argument");
     for (int64_t c = 0; c < m; c++) {
         HK_ARG(ctx, hk_dtype_ok(dtypes[c]), "table_synth: bad dtype");
-        HK_ARG(ctx, specs[c].kind >= HARK_GEN_UNIFORM && specs[c].kind <= HARK_GEN_CONST, "table_synth: bad kind");
+        HK_ARG(ctx, specs[c].kind >= HARK_GEN_UNIFORM && specs[c].kind <= HARK_GEN_LOGUNIFORM, "table_synth: bad kind");
     }
     hark_table *t = nullptr;
     HK_TRY(hk_table_alloc(ctx, &t, n, n, dtypes, m));

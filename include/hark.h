@@ -77,7 +77,11 @@ typedef enum {
                              f64: fma (u53, fhi-flo, flo), u53 = (h>>11)*2^-53               */
     HARK_GEN_AFFINE = 1,  /* ((a*r + b) mod 2^64) mod range (range 0: no mod) — unique keys when
                              gcd(a, range) = 1 and a*r+b does not wrap                       */
-    HARK_GEN_CONST = 2    /* lo (ints) / flo (floats)                                         */
+    HARK_GEN_CONST = 2,   /* lo (ints) / flo (floats)                                         */
+    HARK_GEN_LOGUNIFORM = 3 /* skewed keys, integer arithmetic only: octave e = mulhi64(h, floor(log2 range))
+                             uniform, then uniform inside the octave: k = 2^e + (h2 & (2^e - 1)) - 1, value =
+                             lo + k mod range, h2 = hark_mix64(seed ^ 0x5851F42D4C957F2D, c, r).  P(k) ~ 1/(k+1):
+                             a piecewise-constant Zipf(1.0) — key 0 holds 1/floor(log2 range) of all rows       */
 } hark_gen_kind;
 
 typedef struct {

@@ -31,7 +31,7 @@ DTYPE_CODES = {np.dtype(v): k for k, v in NP_DTYPES.items()}
 
 GT, GE, LT, LE, EQ, NE = 0, 1, 2, 3, 4, 5
 AGG_KEY, AGG_PROD, AGG_SUM, AGG_MAX, AGG_MIN, AGG_COUNT, AGG_AVG, AGG_SUMF64 = 0, 1, 2, 3, 4, 5, 6, 7
-GEN_UNIFORM, GEN_AFFINE, GEN_CONST = 0, 1, 2
+GEN_UNIFORM, GEN_AFFINE, GEN_CONST, GEN_LOGUNIFORM = 0, 1, 2, 3
 
 Pred = Tuple[int, int, int, float]  # (col, op, ival, fval) — include/hark.h hark_pred
 
@@ -102,6 +102,16 @@ def synth_column(dtype: int, spec: dict, seed: int, col: int, row0: int, n: int)
                 v = v % np.uint64(rng)
             if dtype in (F32, F64):
                 return v.astype(npdt)
+        elif kind == GEN_LOGUNIFORM:
+            r2 = max(rng, 2)
+            nb = r2.bit_length() - 1
+            e = _mulhi64(mix64(seed, col, rows), nb)
+            h2 = mix64(seed ^ 0x5851F42D4C957F2D, col, rows)
+            one = np.uint64(1)
+            k = ((one << e) + (h2 & ((one << e) - one)) - one) % np.uint64(r2)
+            v = np.uint64(lo & 0xFFFFFFFFFFFFFFFF) + k
+            if dtype in (F32, F64):
+                return v.view(np.int64).astype(npdt)
         else:
             if dtype in (F32, F64):
                 return np.full(n, flo, dtype=npdt)

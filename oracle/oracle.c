@@ -459,6 +459,15 @@ int oracle_synth_column(int32_t dtype, const hark_colspec *spec, uint64_t seed, 
             iv = v; fv = (double)v; ffv = (float)v;
             break;
         }
+        case HARK_GEN_LOGUNIFORM: {
+            uint64_t range = spec->range < 2 ? 2 : spec->range;
+            int nb = 63 - __builtin_clzll(range);
+            uint64_t e = mulhi64(oracle_mix64(seed, (uint64_t)col, r), (uint64_t)nb);
+            uint64_t h2 = oracle_mix64(seed ^ 0x5851F42D4C957F2DULL, (uint64_t)col, r);
+            uint64_t k = ((1ull << e) + (h2 & ((1ull << e) - 1ull)) - 1ull) % range;
+            iv = (uint64_t)spec->lo + k; fv = (double)(int64_t)iv; ffv = (float)(int64_t)iv;
+            break;
+        }
         default:
             iv = (uint64_t)spec->lo; fv = spec->flo; ffv = (float)spec->flo;
             break;

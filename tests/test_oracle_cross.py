@@ -115,7 +115,8 @@ def test_generator_c_vs_numpy(dtype):
              dict(kind=NO.GEN_UNIFORM, lo=0, range=0, flo=-2.0, fhi=3.0),
              dict(kind=NO.GEN_UNIFORM, lo=-(2 ** 19), range=2 ** 20),
              dict(kind=NO.GEN_AFFINE, a=7, b=3, range=1000),
-             dict(kind=NO.GEN_CONST, lo=42, flo=4.25)]
+             dict(kind=NO.GEN_CONST, lo=42, flo=4.25), dict(kind=NO.GEN_LOGUNIFORM, lo=-3, range=1 << 20),
+             dict(kind=NO.GEN_LOGUNIFORM, lo=5, range=1000)]
     for col, spec in enumerate(specs):
         a = CO.synth_column(dtype, spec, 42, col, 10 ** 9 - 5, 300)
         b = NO.synth_column(dtype, spec, 42, col, 10 ** 9 - 5, 300)

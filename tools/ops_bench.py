@@ -133,6 +133,48 @@ def run_groupby(env, scale, reps):
     return d
 
 
+def run_groupby_zipf(env, scale, reps):
+    """Config 3 with skewed keys (HARK_GEN_LOGUNIFORM: P(k) ~ 1/(k+1), key 0 holds 5 % of the rows)."""
+    import torch
+    n = int(10 ** 9 * scale)
+    specs = [dict(kind=3, lo=0, range=1 << 20), dict(kind=0, lo=0, range=1000)]
+    t = env.synth(n, [I32, I32], specs, seed=42)
+    ops = [AGG_SUM, AGG_COUNT, AGG_AVG]
+    st, r = timed(env, lambda: env.query_groupby_ex(t, 0, [1, 1, 1], ops), reps)
+    keys, sums, cnts, avgs = r.columns()
+    total = int(as_torch(t, 1).sum(dtype=torch.int64).item())
+    ok = (bool(np.all(np.diff(keys.astype(np.int64)) > 0)) and int(cnts.sum()) == n
+          and (int(sums.view(np.uint32).astype(np.uint64).sum()) - total) % (1 << 32) == 0)
+    env.set_option("groupby.impl", 1)
+    st_sort, r_sort = timed(env, lambda: env.query_groupby_ex(t, 0, [1, 1, 1], ops), 1)
+    env.set_option("groupby.impl", 0)
+    ok = ok and all(np.array_equal(a, b) for a, b in zip(r.columns(), r_sort.columns()))   # K2 == sort path, bit for bit
+    d = line("groupby_cfg3_zipf", n, st, {"groups": len(keys), "check_ok": bool(ok), "max_group_rows": int(cnts.max()),
+                                          "sort_path_total_ms": st_sort["total_ms"]})
+    r.free(); r_sort.free(); t.free()
+    return d
+
+
+def run_filter_sweep(env, scale, reps):
+    """Config 2 at selectivities 1 / 10 / 25 / 50 / 90 %: col2 > t AND col5 < u, (1 - t) * u = sigma."""
+    n = int(10 ** 9 * scale)
+    t = env.synth(n, [F32] * 8, [dict(kind=0)] * 8, seed=42)
+    out = []
+    for sigma in (0.01, 0.10, 0.25, 0.50, 0.90):
+        u = sigma ** 0.5
+        preds = [(1, GT, 0, 1.0 - u), (4, 2, 0, u)]
+        st, r = timed(env, lambda: env.query_filter(t, [0, 2], preds), reps)
+        got = r.shape[0] / n
+        gbs = st["alg_bytes"] / (st["kernel_ms"] * 1e-3) / 1e9
+        out.append({"sigma_target": sigma, "sigma": got, "kernel_ms": st["kernel_ms"], "alg_bytes": st["alg_bytes"],
+                    "alg_gbs": gbs, "frac_of_measured_peak": gbs / peak()})
+        r.free()
+    d = {"op": "filter_sweep_cfg2", "rows": n, "sweep": out, "check_ok": all(abs(x["sigma"] - x["sigma_target"]) < 0.01 for x in out)}
+    print(json.dumps(d), flush=True)
+    t.free()
+    return d
+
+
 def run_orderby(env, scale, reps):
     import torch
     n = int(2 * 10 ** 9 * scale)
@@ -203,9 +245,13 @@ def main():
                 res.append(run_groupby(env, args.scale, args.reps))
             elif op == "orderby":
                 res.append(run_orderby(env, args.scale, args.reps))
+            elif op == "groupby_zipf":
+                res.append(run_groupby_zipf(env, args.scale, args.reps))
+            elif op == "filter_sweep":
+                res.append(run_filter_sweep(env, args.scale, args.reps))
             elif op == "join":
                 res.append(run_join(env, args.join_scale or args.scale, args.reps))
-            if args.cpu_rows > 0 and "error" not in res[-1]:
+            if args.cpu_rows > 0 and "error" not in res[-1] and op in ("groupby", "orderby", "join"):
                 res[-1]["cpu_baseline"] = cpu_leg(op, args.cpu_rows)
                 print(json.dumps({"op": op, "cpu_baseline": res[-1]["cpu_baseline"]}), flush=True)
         except Exception as e:  # keep going: one OOM must not hide the other operators' numbers
