@@ -181,13 +181,22 @@ extern "C" int hark_context_set_option(hark_ctx *ctx, const char *key, int64_t v
     if (!ctx || !key) return HARK_ERR_ARG;
     static const char *known[] = {"filter.impl", "filter.ctas_per_sm", "sort.ctas_per_sm", "groupby.impl",
                                   "join.impl",   "upload.chunk_mb",    "dense.log2_slots",  "dense.smem_bytes",
-                                  "part.ctas_per_sm", "part.threads", "join.lut_slice_bytes", "sort.impl", "sort.rank", "stats.cache", nullptr};
+                                  "part.ctas_per_sm", "part.threads", "join.lut_slice_bytes", "sort.impl", "sort.rank", "stats.cache",
+                                  "sort.trunc", "sort.trunc_slack", nullptr};
     for (int i = 0; known[i]; i++)
         if (!strcmp(known[i], key)) {
             ctx->opts[key] = value;
             return HARK_OK;
         }
     return ctx->fail(HARK_ERR_ARG, std::string("unknown option: ") + key);
+}
+
+extern "C" int hark_context_get_option(hark_ctx *ctx, const char *key, int64_t *value) {
+    if (!ctx || !key || !value) return HARK_ERR_ARG;
+    auto it = ctx->opts.find(key);
+    if (it == ctx->opts.end()) return ctx->fail(HARK_ERR_ARG, std::string("option not set: ") + key);
+    *value = it->second;
+    return HARK_OK;
 }
 
 extern "C" int hark_stats_last(hark_ctx *ctx, hark_stats *out) {

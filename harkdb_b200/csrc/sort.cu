@@ -697,6 +697,193 @@ __global__ void __launch_bounds__(256) hk_gather_kernel(VT *__restrict__ dst, co
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[perm[i]];
 }
 
+// ------------------------------------------------------------------------------------------------
+// K3t — truncated LSD + tie repair.  When the composite key has many more significant bits than log2(n), the LSD
+// passes over its LOW bits are almost always wasted work: after a stable sort by the top T >= log2(n) + slack bits
+// only a small fraction of the rows still share their T-bit prefix with a neighbour.  hk_radix_sort then runs the
+// passes of the top T bits only (config 4: 5 passes instead of 11) and repairs the rest here:
+//   hk_sort_fix_find_kernel  — one streaming read of the sorted key columns; a row whose predecessor has the same
+//                              prefix but a LARGER suffix is an inversion; the thread at the FIRST inversion of a
+//                              run of equal prefixes records (run start, run length) in a work list;
+//   hk_sort_fix_apply_kernel — one thread per recorded run: stable insertion sort of the run by the suffix, then
+//                              every carried array that can differ inside a run is permuted in place.
+// Runs of fully equal keys (duplicates) contain no inversion and cost nothing.  A run longer than FIX_LMAX that
+// needs repair, or a work list overflow, raises a flag and the caller redoes the sort with all passes; a sample of
+// the keys taken before the passes keeps that from happening on clustered data (see plan_truncation).
+// Find and apply are separate launches because apply rewrites the key columns that find reads.
+// ------------------------------------------------------------------------------------------------
+constexpr int FIX_MAXK = 8;  // key columns the repair can compare
+constexpr int FIX_LMAX = 32; // longest run of equal prefixes repaired in place
+constexpr int FIX_T = 256;
+constexpr int FIX_I = 4;     // rows per thread and iteration
+
+struct FixKey {
+    const void *ptr;
+    int width;
+    int dtype;
+    int desc;
+    uint64_t base;
+};
+
+struct FixParams {
+    int nk;    // keys, most significant first
+    int kstar; // last key with sorted digits; its bits below `shift` and all later keys are unsorted
+    int shift;
+    FixKey key[FIX_MAXK];
+    int na;
+    void *arr[MAXA];
+    int width[MAXA];
+    int moves[MAXA];
+    int64_t n;
+    unsigned long long *work; // [cap] : run start << 8 | run length
+    unsigned long long cap;
+    unsigned long long *count; // [0] runs recorded, [1] flag: redo with all passes
+};
+
+__device__ __forceinline__ uint64_t fix_key(const FixKey &k, int64_t r) {
+    uint64_t u;
+    if (k.width == 4) u = hk_ordkey32(reinterpret_cast<const uint32_t *>(k.ptr)[r], k.dtype);
+    else u = hk_ordkey64(reinterpret_cast<const uint64_t *>(k.ptr)[r], k.dtype);
+    return k.desc ? (k.base - u) : (u - k.base);
+}
+
+__device__ bool fix_same_prefix(const FixParams &P, int64_t a, int64_t b) {
+    if ((fix_key(P.key[P.kstar], a) >> P.shift) != (fix_key(P.key[P.kstar], b) >> P.shift)) return false;
+    for (int k = P.kstar - 1; k >= 0; k--)
+        if (fix_key(P.key[k], a) != fix_key(P.key[k], b)) return false;
+    return true;
+}
+
+// order of rows a and b by the keys from kstar on (meaningful when their prefixes are equal)
+__device__ int fix_cmp_suffix(const FixParams &P, int64_t a, int64_t b) {
+    for (int k = P.kstar; k < P.nk; k++) {
+        const uint64_t x = fix_key(P.key[k], a), y = fix_key(P.key[k], b);
+        if (x != y) return x < y ? -1 : 1;
+    }
+    return 0;
+}
+
+// row i is an inversion (checked by the caller).  Returns start << 8 | length of its run when i is the run's FIRST
+// inversion and the run fits FIX_LMAX; 0 when another thread owns the run; ~0 when the run is too long.
+__device__ unsigned long long fix_claim_run(const FixParams &P, int64_t i) {
+    int64_t s = i - 1;
+    while (s > 0 && fix_same_prefix(P, s - 1, s)) {
+        if (fix_cmp_suffix(P, s - 1, s) > 0) return 0ull; // an earlier inversion owns this run
+        s--;
+        if (i - s >= FIX_LMAX) return ~0ull;
+    }
+    int64_t e = i + 1;
+    while (e < P.n && fix_same_prefix(P, e - 1, e)) {
+        e++;
+        if (e - s > FIX_LMAX) return ~0ull;
+    }
+    return ((unsigned long long)s << 8) | (unsigned long long)(e - s);
+}
+
+__global__ void __launch_bounds__(FIX_T) hk_sort_fix_find_kernel(const __grid_constant__ FixParams P) {
+    __shared__ unsigned long long s_list[FIX_T * FIX_I];
+    __shared__ unsigned int s_cnt;
+    __shared__ unsigned long long s_base;
+    const FixKey &ks = P.key[P.kstar];
+    const int64_t per_iter = (int64_t)FIX_T * FIX_I;
+    const int64_t iters = (P.n + per_iter - 1) / per_iter;
+    for (int64_t it = blockIdx.x; it < iters; it += gridDim.x) {
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        const int64_t r0 = it * per_iter + threadIdx.x;
+        uint64_t ta[FIX_I], tb[FIX_I];
+#pragma unroll
+        for (int j = 0; j < FIX_I; j++) {
+            const int64_t i = r0 + (int64_t)j * FIX_T;
+            const bool ok = i >= 1 && i < P.n;
+            ta[j] = ok ? fix_key(ks, i - 1) : 0ull;
+            tb[j] = ok ? fix_key(ks, i) : ~0ull;
+        }
+#pragma unroll
+        for (int j = 0; j < FIX_I; j++) {
+            const int64_t i = r0 + (int64_t)j * FIX_T;
+            if ((ta[j] >> P.shift) != (tb[j] >> P.shift) || ta[j] < tb[j]) continue; // other prefix, or in order
+            if (!(i >= 1 && i < P.n)) continue;
+            bool same = true;
+            for (int k = P.kstar - 1; k >= 0 && same; k--) same = fix_key(P.key[k], i - 1) == fix_key(P.key[k], i);
+            if (!same) continue;
+            if (ta[j] == tb[j]) { // tie on the truncated key: the later keys decide
+                int c = 0;
+                for (int k = P.kstar + 1; k < P.nk && c == 0; k++) {
+                    const uint64_t x = fix_key(P.key[k], i - 1), y = fix_key(P.key[k], i);
+                    c = x < y ? -1 : (x > y ? 1 : 0);
+                }
+                if (c <= 0) continue;
+            }
+            const unsigned long long w = fix_claim_run(P, i);
+            if (w == ~0ull) atomicExch(P.count + 1, 1ull);
+            else if (w) s_list[atomicAdd(&s_cnt, 1u)] = w;
+        }
+        __syncthreads();
+        const unsigned int c = s_cnt;
+        if (c) {
+            if (threadIdx.x == 0) s_base = atomicAdd(P.count, (unsigned long long)c);
+            __syncthreads();
+            const unsigned long long base = s_base;
+            if (base + c > P.cap) {
+                if (threadIdx.x == 0) atomicExch(P.count + 1, 1ull);
+            } else {
+                for (unsigned int j = threadIdx.x; j < c; j += FIX_T) P.work[base + j] = s_list[j];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(128) hk_sort_fix_apply_kernel(const __grid_constant__ FixParams P) {
+    if (P.count[1]) return; // the caller redoes the sort
+    const unsigned long long runs = min(P.count[0], P.cap);
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < runs; w += stride) {
+        const unsigned long long e = P.work[w];
+        const int64_t s = (int64_t)(e >> 8);
+        const int len = (int)(e & 0xff);
+        uint8_t idx[FIX_LMAX];
+        for (int j = 0; j < len; j++) { // stable insertion sort of the run's row offsets by the suffix
+            int p = j;
+            while (p > 0 && fix_cmp_suffix(P, s + idx[p - 1], s + j) > 0) {
+                idx[p] = idx[p - 1];
+                p--;
+            }
+            idx[p] = (uint8_t)j;
+        }
+        uint64_t tmp[FIX_LMAX];
+        for (int a = 0; a < P.na; a++) {
+            if (!P.moves[a]) continue;
+            if (P.width[a] == 4) {
+                uint32_t *q = reinterpret_cast<uint32_t *>(P.arr[a]) + s;
+                for (int j = 0; j < len; j++) tmp[j] = q[idx[j]];
+                for (int j = 0; j < len; j++) q[j] = (uint32_t)tmp[j];
+            } else {
+                uint64_t *q = reinterpret_cast<uint64_t *>(P.arr[a]) + s;
+                for (int j = 0; j < len; j++) tmp[j] = q[idx[j]];
+                for (int j = 0; j < len; j++) q[j] = tmp[j];
+            }
+        }
+    }
+}
+
+// evenly spaced sample of the normalised key tuples: out[k * S + s] = key k of row floor(s * n / S)
+struct SampleParams {
+    int nk;
+    FixKey key[FIX_MAXK];
+    int64_t n;
+    int S;
+    uint64_t *out;
+};
+
+__global__ void __launch_bounds__(256) hk_sort_sample_kernel(const __grid_constant__ SampleParams P) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.S) return;
+    const int64_t r = (int64_t)(((unsigned __int128)(uint64_t)s * (uint64_t)P.n) / (uint64_t)P.S);
+    for (int k = 0; k < P.nk; k++) P.out[(size_t)k * P.S + s] = fix_key(P.key[k], r);
+}
+
 unsigned grid_for(hark_ctx *ctx, int64_t n, int per_sm = 8) {
     return (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx->num_sms * per_sm));
 }
@@ -708,6 +895,205 @@ int bit_width_u64(uint64_t v) {
         v >>= 1;
     }
     return b;
+}
+
+struct Pass {
+    int key;      // index into keys
+    DigitFn f;
+    int hist_slot;
+};
+
+struct KeyRange {
+    uint64_t lo = 0, hi = 0; // min / max order key of the column
+    int bits = 0;            // significant bits of (hi - lo)
+};
+
+struct TruncPlan {
+    bool on = false;
+    int kstar = 0; // last key with sorted digits
+    int q = 0;     // its top q digits are sorted (0: all of it)
+    int shift = 0; // its bits below `shift` are unsorted
+};
+
+// Pass list (least significant first) that sorts keys 0..kstar, key kstar by its top q 8-bit digits only (q == 0 or
+// 8q >= bits: all of it).  Returns the number of passes; *low_shift = lowest sorted bit of key kstar.
+int build_passes(const std::vector<hk_sort_keyspec> &keys, const std::vector<KeyRange> &ranges, int kstar, int q,
+                 std::vector<Pass> &passes, int *low_shift = nullptr) {
+    passes.clear();
+    if (low_shift) *low_shift = 0;
+    for (int k = kstar; k >= 0; k--) {
+        const int bits = ranges[k].bits;
+        int sh0 = 0;
+        if (k == kstar && q > 0 && 8 * q < bits) sh0 = bits - 8 * q;
+        if (k == kstar && low_shift) *low_shift = sh0;
+        for (int sh = sh0; sh < bits; sh += 8) {
+            Pass p;
+            p.key = k;
+            p.f.dtype = keys[k].dtype;
+            p.f.desc = keys[k].desc;
+            p.f.mode = 0;
+            p.f.shift = sh;
+            p.f.mask = (bits - sh >= 8) ? 0xffu : ((1u << (bits - sh)) - 1u);
+            p.f.nparts = 0;
+            p.f.base = keys[k].desc ? ranges[k].hi : ranges[k].lo;
+            p.f.fast = hk_dtype_int(keys[k].dtype) ? (keys[k].desc ? 2 : 1) : 0;
+            p.f.xmask = keys[k].dtype == HARK_I32 ? 0x80000000ull : keys[k].dtype == HARK_I64 ? 0x8000000000000000ull : 0ull;
+            p.hist_slot = (int)passes.size();
+            passes.push_back(p);
+        }
+    }
+    return (int)passes.size();
+}
+
+FixKey make_fix_key(const hk_sort_keyspec &ks, const KeyRange &r, const void *ptr, int width) {
+    FixKey f;
+    f.ptr = ptr;
+    f.width = width;
+    f.dtype = ks.dtype;
+    f.desc = ks.desc;
+    f.base = ks.desc ? r.hi : r.lo;
+    return f;
+}
+
+// Decides how many of the top bits of the composite key the LSD passes must cover.  T starts at ceil(log2 n) + slack
+// (a uniform key then leaves < 2^-slack of the rows tied with a neighbour) and grows by one digit at a time while an
+// evenly spaced sample of the key tuples still shows prefix ties between DIFFERENT tuples — clustered keys (floats
+// around one exponent, ids with a common high part) keep all their passes, duplicates cost nothing.
+int plan_truncation(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec> &keys, const std::vector<hk_sort_array> &arrays,
+                    const std::vector<KeyRange> &ranges, int full_passes, TruncPlan *out) {
+    const int nk = (int)keys.size();
+    out->on = false;
+    int total_bits = 0;
+    for (int k = 0; k < nk; k++) total_bits += ranges[k].bits;
+    const int slack = (int)std::max<int64_t>(0, ctx->opt("sort.trunc_slack", 4));
+    int T = bit_width_u64((uint64_t)(n - 1)) + slack;
+    if (T + 8 > total_bits) return HARK_OK; // nothing to save
+    // ---- sample, sorted by the full tuple; per adjacent pair: first differing key and its highest differing bit ----
+    const int S = (int)std::min<int64_t>(n, 32768);
+    uint64_t *d_sample = nullptr;
+    HK_TRY(ctx->dalloc((void **)&d_sample, sizeof(uint64_t) * (size_t)S * nk));
+    SampleParams SP;
+    memset(&SP, 0, sizeof SP);
+    SP.nk = nk;
+    for (int k = 0; k < nk; k++) SP.key[k] = make_fix_key(keys[k], ranges[k], arrays[keys[k].array].in, arrays[keys[k].array].width);
+    SP.n = n;
+    SP.S = S;
+    SP.out = d_sample;
+    hk_sort_sample_kernel<<<(S + 255) / 256, 256, 0, ctx->stream>>>(SP);
+    cudaError_t e = cudaGetLastError();
+    ctx->count_launch();
+    std::vector<uint64_t> col((size_t)S * nk), row((size_t)S * nk);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(col.data(), d_sample, sizeof(uint64_t) * col.size(), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    ctx->dfree(d_sample);
+    if (e != cudaSuccess) return ctx->fail(HARK_ERR_CUDA, std::string("sort(sample): ") + cudaGetErrorString(e));
+    for (int s = 0; s < S; s++)
+        for (int k = 0; k < nk; k++) row[(size_t)s * nk + k] = col[(size_t)k * S + s];
+    std::vector<int> order(S);
+    for (int s = 0; s < S; s++) order[s] = s;
+    std::sort(order.begin(), order.end(), [&](int a, int b) {
+        const uint64_t *x = &row[(size_t)a * nk], *y = &row[(size_t)b * nk];
+        for (int k = 0; k < nk; k++)
+            if (x[k] != y[k]) return x[k] < y[k];
+        return false;
+    });
+    std::vector<std::pair<int, int>> diff; // (first differing key, bit width of the xor) of adjacent distinct tuples
+    diff.reserve(S);
+    for (int s = 1; s < S; s++) {
+        const uint64_t *x = &row[(size_t)order[s - 1] * nk], *y = &row[(size_t)order[s] * nk];
+        for (int k = 0; k < nk; k++)
+            if (x[k] != y[k]) {
+                diff.emplace_back(k, bit_width_u64(x[k] ^ y[k]));
+                break;
+            }
+    }
+    const double expect = 2.0 * (double)S * (double)S / (double)n; // ties a sample of harmless short runs would show
+    const int64_t thr = (int64_t)std::min<double>(std::max(4.0, expect), S / 8.0);
+    // ---- smallest digit-aligned prefix whose sample ties stay under the threshold ----
+    for (;; T += 8) {
+        int acc = 0, kstar = nk - 1, q = 0;
+        for (int k = 0; k < nk; k++) {
+            if (acc >= T) {
+                kstar = k - 1;
+                q = 0;
+                break;
+            }
+            const int b = ranges[k].bits, qd = (T - acc + 7) / 8;
+            if (8 * qd >= b) {
+                acc += b;
+                continue;
+            }
+            kstar = k;
+            q = qd;
+            break;
+        }
+        std::vector<Pass> tmp;
+        int shift = 0;
+        const int np = build_passes(keys, ranges, kstar, q, tmp, &shift);
+        if (np >= full_passes) return HARK_OK;
+        int64_t ties = 0;
+        for (const auto &d : diff)
+            if (d.first > kstar || (d.first == kstar && d.second <= shift)) ties++;
+        if (ties <= thr) {
+            out->on = true;
+            out->kstar = kstar;
+            out->q = q;
+            out->shift = shift;
+            return HARK_OK;
+        }
+    }
+    return HARK_OK;
+}
+
+// Runs the two repair kernels over the sorted buffers (buffer index fb).  *redo: a run too long to repair in place
+// (or a full work list) — the caller must sort again with every pass.
+int fix_truncated(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec> &keys, std::vector<hk_sort_array> &arrays,
+                  const std::vector<KeyRange> &ranges, const TruncPlan &tp, int fb, bool *redo, int64_t *runs) {
+    const int nk = (int)keys.size(), na = (int)arrays.size();
+    FixParams P;
+    memset(&P, 0, sizeof P);
+    P.nk = nk;
+    P.kstar = tp.kstar;
+    P.shift = tp.shift;
+    for (int k = 0; k < nk; k++) P.key[k] = make_fix_key(keys[k], ranges[k], arrays[keys[k].array].buf[fb], arrays[keys[k].array].width);
+    P.na = na;
+    for (int a = 0; a < na; a++) {
+        P.arr[a] = arrays[a].buf[fb];
+        P.width[a] = arrays[a].width;
+        P.moves[a] = 1;
+    }
+    for (int k = 0; k < tp.kstar; k++) P.moves[keys[k].array] = 0; // equal inside a run
+    P.n = n;
+    P.cap = (unsigned long long)std::max<int64_t>(1024, n / 16);
+    void *work = nullptr, *count = nullptr;
+    HK_TRY(ctx->dalloc(&work, sizeof(unsigned long long) * P.cap));
+    int rc = ctx->dalloc(&count, 2 * sizeof(unsigned long long));
+    if (rc != HARK_OK) {
+        ctx->dfree(work);
+        return rc;
+    }
+    P.work = (unsigned long long *)work;
+    P.count = (unsigned long long *)count;
+    cudaError_t e = cudaMemsetAsync(count, 0, 2 * sizeof(unsigned long long), ctx->stream);
+    if (e == cudaSuccess) {
+        const int64_t iters = (n + FIX_T * FIX_I - 1) / (FIX_T * FIX_I);
+        const unsigned g = (unsigned)std::max<int64_t>(1, std::min<int64_t>(iters, (int64_t)ctx->num_sms * 8));
+        hk_sort_fix_find_kernel<<<g, FIX_T, 0, ctx->stream>>>(P);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) {
+        hk_sort_fix_apply_kernel<<<(unsigned)ctx->num_sms * 16, 128, 0, ctx->stream>>>(P);
+        e = cudaGetLastError();
+    }
+    ctx->count_launch(2);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_scalars, count, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    ctx->dfree(work);
+    ctx->dfree(count);
+    if (e != cudaSuccess) return ctx->fail(HARK_ERR_CUDA, std::string("sort(repair): ") + cudaGetErrorString(e));
+    *runs = (int64_t)ctx->h_scalars[0];
+    *redo = ctx->h_scalars[1] != 0;
+    return HARK_OK;
 }
 
 } // namespace
@@ -770,11 +1156,6 @@ int hk_radix_sort(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec> &
     if (info) *info = hk_sort_info{};
     for (auto &a : arrays) a.result = nullptr;
 
-    struct Pass {
-        int key;      // index into keys
-        DigitFn f;
-        int hist_slot;
-    };
     std::vector<Pass> passes;
     unsigned long long *d_hist = nullptr; // [total passes][256]
     uint64_t *d_scratch = nullptr;        // minmax pairs
@@ -796,6 +1177,10 @@ int hk_radix_sort(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec> &
     };
     for (auto &a : arrays) a.buf[0] = a.buf[1] = nullptr;
 
+    const bool chunked = ctx->opt("sort.impl", 0) != 1;
+    std::vector<KeyRange> ranges;
+    TruncPlan trunc;
+    int full_passes = 0;
     if (n > 0 && hash_nparts == 0 && !keys.empty()) {
         // ---- 1. range of every key column -> number of significant digits ----
         const int nk = (int)keys.size();
@@ -818,24 +1203,18 @@ int hk_radix_sort(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec> &
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) return cleanup_fail(HARK_ERR_CUDA, std::string("sort(minmax): ") + cudaGetErrorString(e));
         // ---- 2. pass list: least significant key first, least significant digit first ----
-        for (int k = nk - 1; k >= 0; k--) {
-            const uint64_t lo = ctx->h_scalars[2 * k], hi = ctx->h_scalars[2 * k + 1];
-            const int bits = bit_width_u64(hi - lo);
-            for (int sh = 0; sh < bits; sh += 8) {
-                Pass p;
-                p.key = k;
-                p.f.dtype = keys[k].dtype;
-                p.f.desc = keys[k].desc;
-                p.f.mode = 0;
-                p.f.shift = sh;
-                p.f.mask = (bits - sh >= 8) ? 0xffu : ((1u << (bits - sh)) - 1u);
-                p.f.nparts = 0;
-                p.f.base = keys[k].desc ? hi : lo;
-                p.f.fast = hk_dtype_int(keys[k].dtype) ? (keys[k].desc ? 2 : 1) : 0;
-                p.f.xmask = keys[k].dtype == HARK_I32 ? 0x80000000ull : keys[k].dtype == HARK_I64 ? 0x8000000000000000ull : 0ull;
-                p.hist_slot = (int)passes.size();
-                passes.push_back(p);
-            }
+        ranges.resize(nk);
+        for (int k = 0; k < nk; k++) {
+            ranges[k].lo = ctx->h_scalars[2 * k];
+            ranges[k].hi = ctx->h_scalars[2 * k + 1];
+            ranges[k].bits = bit_width_u64(ranges[k].hi - ranges[k].lo);
+        }
+        full_passes = build_passes(keys, ranges, nk - 1, 0, passes);
+        // ---- 2b. K3t: sort only the top T bits when a key sample says the rest is (almost) never needed ----
+        if (chunked && ctx->opt("sort.trunc", 1) != 0 && nk <= FIX_MAXK && n >= 2) {
+            rc = plan_truncation(ctx, n, keys, arrays, ranges, full_passes, &trunc);
+            if (rc != HARK_OK) return cleanup_fail(rc, "");
+            if (trunc.on) build_passes(keys, ranges, trunc.kstar, trunc.q, passes);
         }
     } else if (n > 0 && hash_nparts > 0) {
         Pass p;
@@ -844,8 +1223,12 @@ int hk_radix_sort(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec> &
         p.hist_slot = 0;
         passes.push_back(p);
     }
-    const int npass = (int)passes.size();
+    int npass = (int)passes.size();
     if (info) info->passes = npass;
+    ctx->opts["sort.last_fallback"] = 0;
+    ctx->opts["sort.last_fix_runs"] = 0;
+    ctx->opts["sort.last_passes"] = npass;
+    ctx->opts["sort.last_truncated"] = 0;
 
     if (npass == 0) { // nothing to move: the result is a copy of the input
         for (auto &a : arrays) {
@@ -864,42 +1247,57 @@ int hk_radix_sort(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec> &
         return HARK_OK;
     }
 
-    const bool chunked = ctx->opt("sort.impl", 0) != 1;
     if (chunked) {
         // ---- K3 v2: every pass = chunk histogram + scan + stable scatter (see hk_lsd_scatter_kernel) ----
-        std::vector<const void *> cur(na);
-        for (int a = 0; a < na; a++) cur[a] = arrays[a].in;
-        for (int p = 0; p < npass; p++) {
-            const int ob = p & 1;
-            for (int a = 0; a < na && rc == HARK_OK; a++)
-                if (!arrays[a].buf[ob]) rc = ctx->dalloc(&arrays[a].buf[ob], (size_t)n * arrays[a].width);
-            if (rc != HARK_OK) return cleanup_fail(rc, "");
-            LsdParams P;
-            memset(&P, 0, sizeof P);
-            P.f = passes[p].f;
-            P.na = na;
-            P.ka = keys[passes[p].key].array;
-            for (int a = 0; a < na; a++) {
-                P.in[a] = cur[a];
-                P.out[a] = arrays[a].buf[ob];
-                P.width[a] = arrays[a].width;
+        for (int attempt = 0;; attempt++) {
+            std::vector<const void *> cur(na);
+            for (int a = 0; a < na; a++) cur[a] = arrays[a].in;
+            for (int p = 0; p < npass; p++) {
+                const int ob = p & 1;
+                for (int a = 0; a < na && rc == HARK_OK; a++)
+                    if (!arrays[a].buf[ob]) rc = ctx->dalloc(&arrays[a].buf[ob], (size_t)n * arrays[a].width);
+                if (rc != HARK_OK) return cleanup_fail(rc, "");
+                LsdParams P;
+                memset(&P, 0, sizeof P);
+                P.f = passes[p].f;
+                P.na = na;
+                P.ka = keys[passes[p].key].array;
+                for (int a = 0; a < na; a++) {
+                    P.in[a] = cur[a];
+                    P.out[a] = arrays[a].buf[ob];
+                    P.width[a] = arrays[a].width;
+                }
+                P.n = n;
+                unsigned long long *d_off = nullptr;
+                if (p == 0 && attempt == 0) ctx->kernel_begin();
+                rc = lsd_pass(ctx, P, arrays[P.ka].width, hash_counts ? &d_off : nullptr);
+                if (rc != HARK_OK) return cleanup_fail(rc, "");
+                if (hash_counts) { // bucket sizes for the caller
+                    e = cudaMemcpyAsync(ctx->h_scalars, d_off, sizeof(uint64_t) * 256, cudaMemcpyDeviceToHost, ctx->stream);
+                    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+                    ctx->dfree(d_off);
+                    if (e != cudaSuccess) return cleanup_fail(HARK_ERR_CUDA, std::string("sort(counts): ") + cudaGetErrorString(e));
+                    for (int i = 0; i < hash_nparts; i++)
+                        hash_counts[i] = (int64_t)((i + 1 < 256 ? ctx->h_scalars[i + 1] : (uint64_t)n) - ctx->h_scalars[i]);
+                }
+                for (int a = 0; a < na; a++) cur[a] = arrays[a].buf[ob];
             }
-            P.n = n;
-            unsigned long long *d_off = nullptr;
-            if (p == 0) ctx->kernel_begin();
-            rc = lsd_pass(ctx, P, arrays[P.ka].width, hash_counts ? &d_off : nullptr);
-            if (p == npass - 1) ctx->kernel_end();
+            if (!trunc.on) break;
+            // ---- K3t: repair the runs the dropped low digits would have ordered ----
+            bool redo = false;
+            int64_t runs = 0;
+            rc = fix_truncated(ctx, n, keys, arrays, ranges, trunc, (npass - 1) & 1, &redo, &runs);
             if (rc != HARK_OK) return cleanup_fail(rc, "");
-            if (hash_counts) { // bucket sizes for the caller
-                e = cudaMemcpyAsync(ctx->h_scalars, d_off, sizeof(uint64_t) * 256, cudaMemcpyDeviceToHost, ctx->stream);
-                if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-                ctx->dfree(d_off);
-                if (e != cudaSuccess) return cleanup_fail(HARK_ERR_CUDA, std::string("sort(counts): ") + cudaGetErrorString(e));
-                for (int i = 0; i < hash_nparts; i++)
-                    hash_counts[i] = (int64_t)((i + 1 < 256 ? ctx->h_scalars[i + 1] : (uint64_t)n) - ctx->h_scalars[i]);
-            }
-            for (int a = 0; a < na; a++) cur[a] = arrays[a].buf[ob];
+            ctx->opts["sort.last_fix_runs"] = runs;
+            if (!redo) break;
+            trunc.on = false; // a long run needed the low digits after all: all passes, from the input
+            ctx->opts["sort.last_fallback"] = 1;
+            npass = build_passes(keys, ranges, (int)keys.size() - 1, 0, passes);
         }
+        ctx->kernel_end();
+        if (info) info->passes = npass;
+        ctx->opts["sort.last_passes"] = npass;
+        ctx->opts["sort.last_truncated"] = trunc.on ? 1 : 0;
     } else {
     // ---- 3. all digit histograms up front (one read per key column), then their exclusive scans ----
         rc = ctx->dalloc((void **)&d_hist, sizeof(unsigned long long) * 256 * npass);

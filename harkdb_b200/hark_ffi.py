@@ -108,6 +108,7 @@ SIGNATURES = {
     "hark_stats_last": (C.c_int, [_P, C.POINTER(HarkStats)]),
     "hark_stats_total_launches": (C.c_int64, [_P]),
     "hark_context_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
+    "hark_context_get_option": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int64)]),
     "hark_host_alloc": (_P, [C.c_int64]),
     "hark_host_free": (None, [_P]),
 }
@@ -284,6 +285,11 @@ class Futhark:
 
     def set_option(self, key: str, value: int):
         self._check(self.lib.hark_context_set_option(self.ctx, key.encode(), int(value)))
+
+    def get_option(self, key: str) -> int:
+        v = C.c_int64(0)
+        self._check(self.lib.hark_context_get_option(self.ctx, key.encode(), C.byref(v)))
+        return v.value
 
     def stats(self) -> dict:
         s = HarkStats()

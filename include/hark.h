@@ -224,6 +224,11 @@ int64_t hark_stats_total_launches(hark_ctx *ctx);
 /* Tuning knobs for experiments ("filter.impl", "filter.ctas_per_sm", ...); returns HARK_ERR_ARG
  * for an unknown key.                                                                          */
 int hark_context_set_option(hark_ctx *ctx, const char *key, int64_t value);
+/* Reads back an option, or one of the read-only counters the last sort left behind: "sort.last_passes",
+ * "sort.last_truncated" (1: only the top digits were sorted and ties repaired), "sort.last_fix_runs",
+ * "sort.last_fallback" (1: the repair met a long run and the sort was redone with every pass).
+ * HARK_ERR_ARG if the key was never set.                                                        */
+int hark_context_get_option(hark_ctx *ctx, const char *key, int64_t *value);
 
 /* ---- pinned host memory for callers that want DMA-speed uploads ---- */
 void *hark_host_alloc(int64_t bytes);

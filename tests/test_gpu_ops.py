@@ -223,6 +223,105 @@ def test_orderby_mixed_types_payload_and_repeats():
     r.free(); t.free()
 
 
+# ---------------------------------------------------------------- K3t: truncated LSD passes + tie repair
+def _sort_info(env):
+    return {k: env.get_option("sort.last_" + k) for k in ("passes", "truncated", "fix_runs", "fallback")}
+
+
+def _check_orderby(env, cols, sel, keys, desc):
+    t = env.from_columns(cols)
+    r = env.query_orderby(t, sel, keys, desc)
+    info = _sort_info(env)
+    exp = NO.query_orderby(cols, sel, keys, desc)
+    for j in range(len(sel)):
+        assert np.array_equal(r.column(j), exp[j], equal_nan=True), f"column {j} differs ({info})"
+    r.free(); t.free()
+    return info
+
+
+def test_orderby_truncated_passes_repair_short_runs():
+    """Wide random keys: only the top digits are sorted, the (many, short) prefix ties are repaired in place."""
+    env = get_env()
+    rng = np.random.default_rng(11)
+    n = 300001
+    k1 = rng.integers(-2 ** 63, 2 ** 63 - 1, n, dtype=np.int64)
+    k2 = rng.integers(-2 ** 63, 2 ** 63 - 1, n, dtype=np.int64)
+    k1[rng.integers(0, n, 2000)] = k1[rng.integers(0, n, 2000)]          # full duplicates of the first key
+    payload = np.arange(n, dtype=np.int32)
+    env.set_option("sort.trunc_slack", 0)                                 # ~2 % of the rows tie on the prefix
+    try:
+        info = _check_orderby(env, [k1, k2, payload], [2, 0, 1], [0, 1], [0, 1])
+        assert info["truncated"] == 1 and info["fallback"] == 0 and info["fix_runs"] > 100 and info["passes"] <= 4, info
+        info = _check_orderby(env, [k1, k2, payload], [2], [0], [1])
+        assert info["truncated"] == 1 and info["fallback"] == 0, info
+    finally:
+        env.set_option("sort.trunc_slack", 4)
+    env.set_option("sort.trunc", 0)
+    try:
+        info = _check_orderby(env, [k1, k2, payload], [2, 0, 1], [0, 1], [0, 1])
+        assert info["truncated"] == 0 and info["passes"] == 16, info
+    finally:
+        env.set_option("sort.trunc", 1)
+
+
+def test_orderby_truncation_at_a_key_boundary_and_floats():
+    env = get_env()
+    rng = np.random.default_rng(12)
+    n = 200003
+    # 24 significant bits in key 0 cover log2(n) + slack: key 1 (f64, with NaNs / infinities / signed zeros) is
+    # never touched by a pass and only decides inside the repaired runs
+    k0 = rng.integers(0, 1 << 24, n).astype(np.uint32)
+    k1 = rng.standard_normal(n)
+    k1[rng.integers(0, n, 50)] = np.nan
+    k1[rng.integers(0, n, 50)] = -0.0
+    k1[rng.integers(0, n, 50)] = 0.0
+    k1[rng.integers(0, n, 20)] = np.inf
+    payload = np.arange(n, dtype=np.int64)
+    info = _check_orderby(env, [k0, k1, payload], [2, 1], [0, 1], [0, 1])
+    assert info["truncated"] == 1 and info["passes"] == 3 and info["fix_runs"] > 0 and info["fallback"] == 0, info
+    # f32 keys: clustered around a few exponents — whatever the planner decides, the order must be exact
+    f = (rng.standard_normal(n) * 1e3).astype(np.float32)
+    f[rng.integers(0, n, 30)] = np.nan
+    info = _check_orderby(env, [f, payload], [1, 0], [0], [0])
+    assert info["fallback"] == 0, info
+    info = _check_orderby(env, [f, k0, payload], [2], [0, 1], [1, 1])
+    assert info["fallback"] == 0, info
+
+
+def test_orderby_truncation_duplicates_cost_nothing_and_clusters_keep_their_passes():
+    env = get_env()
+    rng = np.random.default_rng(13)
+    n = 250000
+    payload = np.arange(n, dtype=np.int32)
+    # 1000 distinct 64-bit values: every prefix tie is a full duplicate — truncated, nothing to repair, stable
+    vals = rng.integers(-2 ** 63, 2 ** 63 - 1, 1000, dtype=np.int64)
+    k = vals[rng.integers(0, 1000, n)]
+    info = _check_orderby(env, [k, payload], [1, 0], [0], [0])
+    assert info["truncated"] == 1 and info["fix_runs"] == 0 and info["fallback"] == 0, info
+    # two far-apart clusters: the top digits say nothing, the sample must veto the truncation
+    c = rng.integers(0, 1 << 20, n).astype(np.int64)
+    c[::2] += 1 << 60
+    info = _check_orderby(env, [c, payload], [1, 0], [0], [0])
+    assert info["fallback"] == 0 and info["truncated"] == 0, info
+
+
+def test_orderby_truncation_falls_back_on_a_long_run():
+    """40 rows share their top 40 bits among a million random keys: the sample cannot see them, the repair meets a
+    run longer than it handles in place, and the sort is redone with every pass — same exact result."""
+    env = get_env()
+    rng = np.random.default_rng(14)
+    n = 1 << 20
+    k = rng.integers(-2 ** 63, 2 ** 63 - 1, n, dtype=np.int64)
+    pos = rng.choice(n, 40, replace=False)
+    k[pos] = (np.int64(0x1234567890) << 24) | rng.integers(0, 1 << 24, 40).astype(np.int64)
+    payload = np.arange(n, dtype=np.int32)
+    info = _check_orderby(env, [k, payload], [1, 0], [0], [0])
+    assert info["fallback"] == 1 and info["truncated"] == 0 and info["passes"] == 8, info
+    k[pos[:20]] = rng.integers(-2 ** 63, 2 ** 63 - 1, 20, dtype=np.int64)   # 20 rows left: repaired in place
+    info = _check_orderby(env, [k, payload], [1, 0], [0], [0])
+    assert info["fallback"] == 0 and info["truncated"] == 1 and info["fix_runs"] >= 1, info
+
+
 def test_sort_by_and_partition_by_hash():
     env = get_env()
     rng = np.random.default_rng(6)

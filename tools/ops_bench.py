@@ -196,8 +196,9 @@ def run_orderby(env, scale, reps):
         okv = (a[lo:hi] < a[lo + 1:hi + 1]) | ((a[lo:hi] == a[lo + 1:hi + 1]) & (b[lo:hi] <= b[lo + 1:hi + 1]))
         sorted_ok = sorted_ok and bool(okv.all().item())
         del okv
+    sort_info = {k: env.get_option("sort.last_" + k) for k in ("passes", "truncated", "fix_runs", "fallback")}
     d = line("orderby_cfg4", n, st, {"check_ok": bool(sums_ok and pair_ok and sorted_ok), "sums_ok": sums_ok,
-                                     "pair_ok": pair_ok, "sorted_ok": sorted_ok})
+                                     "pair_ok": pair_ok, "sorted_ok": sorted_ok, "sort": sort_info})
     del a, b, a0, b0
     r.free(); t.free()
     return d
