@@ -30,7 +30,7 @@ constexpr int FG = 4;              // 4-row groups per thread
 constexpr int FROWS = FG * 4;      // rows per thread
 constexpr int FTILE = FT * FROWS;  // rows per tile (4096)
 constexpr int FWROWS = 32 * FROWS; // rows per warp (512)
-constexpr int MAXP = 8;
+constexpr int MAXP = 16;
 constexpr int MAXS = 16;
 
 struct FilterParams {
@@ -354,6 +354,7 @@ struct CanonPred {
     int en; // bit0 gt, bit1 eq, bit2 lt
     int inv;
     int width;
+    int clause_end; // 1: last predicate of its OR-clause (a plain conjunct is a clause of one)
 };
 
 struct Filter2Params {
@@ -533,6 +534,9 @@ __global__ void __launch_bounds__(FT, F2_MINBLOCKS) hk_filter2_kernel(const __gr
                         }
                     }
                 } else {
+                    // WHERE in conjunctive normal form: the batch mask is the AND over clauses of the OR over each
+                    // clause's predicates (hark.h HARK_PRED_OR); `cl` collects the clause being evaluated
+                    uint32_t cl = 0;
 #pragma unroll 1
                     for (int p = 0; p < np; p++) {
                         const bool w4 = (W_T == 4) || (W_T == 0 && P.pred[p].width == 4);
@@ -541,12 +545,16 @@ __global__ void __launch_bounds__(FT, F2_MINBLOCKS) hk_filter2_kernel(const __gr
                             if (w4) {
                                 uint32_t x[UL * 4];
                                 f2_load_wave<4, UL>(P.pcol[p], lrow, u0, P.n, 0xffffffffu, x);
-                                mask = f2_merge<UL>(mask, f2_eval<4, UL * 4>(x, P.pred[p]), u0);
+                                cl |= f2_eval<4, UL * 4>(x, P.pred[p]) << (u0 * 4);
                             } else {
                                 uint64_t x[UL * 4];
                                 f2_load_wave<8, UL>(P.pcol[p], lrow, u0, P.n, 0xffffffffu, x);
-                                mask = f2_merge<UL>(mask, f2_eval<8, UL * 4>(x, P.pred[p]), u0);
+                                cl |= f2_eval<8, UL * 4>(x, P.pred[p]) << (u0 * 4);
                             }
+                        }
+                        if (P.pred[p].clause_end) {
+                            mask &= cl;
+                            cl = 0;
                         }
                     }
                 }
@@ -685,8 +693,11 @@ CanonPred canonicalise(const hark_pred &pr, int dtype) {
     memset(&q, 0, sizeof q);
     q.width = hk_dtype_size(dtype);
     static const int en_of[6] = {1, 3, 4, 6, 2, 2}; // GT GE LT LE EQ NE(=EQ ^ inv)
-    q.en = en_of[pr.op];
-    q.inv = pr.op == HARK_NE;
+    const int op = pr.op & HARK_PRED_OP_MASK;
+    const int neg = (pr.op & HARK_PRED_NOT) ? 1 : 0;
+    q.clause_end = (pr.op & HARK_PRED_OR) ? 0 : 1;
+    q.en = en_of[op];
+    q.inv = (op == HARK_NE) ^ neg;
     if (dtype == HARK_F32) {
         const float f = (float)pr.fval;
         uint32_t bits;
@@ -709,13 +720,13 @@ CanonPred canonicalise(const hark_pred &pr, int dtype) {
     if (c < lo || c > hi) { // constant outside the column's range: the comparison is a constant
         const bool below = c < lo; // every x is > c
         bool always;
-        switch (pr.op) {
+        switch (op) {
         case HARK_GT: case HARK_GE: always = below; break;
         case HARK_LT: case HARK_LE: always = !below; break;
         case HARK_EQ: always = false; break;
         default: always = true; break;
         }
-        q.en = always ? 7 : 0;
+        q.en = (always ^ (neg != 0)) ? 7 : 0;
         q.inv = 0;
         q.c = 0;
         return q;
@@ -809,9 +820,13 @@ int hk_filter(hark_ctx *ctx, hark_table **out, const hark_table *db, const int32
         HK_ARG(ctx, cols[j] >= 0 && cols[j] < m, "query: selected column index out of bounds");
     for (int64_t p = 0; p < np; p++) {
         HK_ARG(ctx, preds[p].col >= 0 && preds[p].col < m, "query: predicate column index out of bounds");
-        HK_ARG(ctx, preds[p].op >= HARK_GT && preds[p].op <= HARK_NE, "query: bad comparison operator");
+        HK_ARG(ctx, (preds[p].op & ~(HARK_PRED_OP_MASK | HARK_PRED_OR | HARK_PRED_NOT)) == 0 &&
+                        (preds[p].op & HARK_PRED_OP_MASK) <= HARK_NE, "query: bad comparison operator");
     }
-    HK_ARG(ctx, np <= MAXP, "query: at most 8 conjuncts are supported");
+    HK_ARG(ctx, np <= MAXP, "query: at most 16 predicates are supported");
+    HK_ARG(ctx, np == 0 || !(preds[np - 1].op & HARK_PRED_OR), "query: the last predicate cannot be OR-ed with a next one");
+    bool cnf = false; // any OR / NOT: the runtime-count v2 kernel evaluates clauses; v1 and the static kernels are AND-only
+    for (int64_t p = 0; p < np; p++) cnf = cnf || (preds[p].op & (HARK_PRED_OR | HARK_PRED_NOT));
     std::vector<int32_t> dts;
     for (int64_t j = 0; j < k; j++) dts.push_back(db->cols[cols[j]].dtype);
 
@@ -860,7 +875,7 @@ int hk_filter(hark_ctx *ctx, hark_table **out, const hark_table *db, const int32
     for (int64_t j = 0; j < k; j++) see(dts[j]);
 
     cudaError_t e = cudaSuccess;
-    const int64_t impl = ctx->opt("filter.impl", 0);
+    const int64_t impl = cnf ? 3 : ctx->opt("filter.impl", 0);
     uint64_t n_out = 0;
     // more than MAXS selected columns: several launches over column groups (predicates re-evaluated)
     for (int64_t j0 = 0; j0 < std::max<int64_t>(k, 1) && e == cudaSuccess; j0 += MAXS) {

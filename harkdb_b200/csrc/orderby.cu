@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "hark_internal.cuh"
+#include "dense_agg.cuh"
 #include "sort.cuh"
 
 namespace {
@@ -61,7 +62,15 @@ int hk_orderby(hark_ctx *ctx, hark_table **out, const hark_table *db, const int3
         a.width = hk_dtype_size(db->cols[c].dtype);
         key_array_of_col[c] = (int)arrays.size();
         arrays.push_back(a);
-        keys.push_back(hk_sort_keyspec{key_array_of_col[c], db->cols[c].dtype, desc ? (desc[j] != 0) : 0});
+        hk_sort_keyspec ks;
+        ks.array = key_array_of_col[c];
+        ks.dtype = db->cols[c].dtype;
+        ks.desc = desc ? (desc[j] != 0) : 0;
+        if (n > 0) { // the column's cached min / max order key saves the sort a pass over the column
+            HK_TRY(hk_column_minmax(ctx, db->cols[c], n, ks.dtype, &ks.lo, &ks.hi));
+            ks.have_range = true;
+        }
+        keys.push_back(ks);
     }
     bool need_rowid = false;
     for (int64_t j = 0; j < k; j++)

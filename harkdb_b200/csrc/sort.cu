@@ -965,7 +965,7 @@ int plan_truncation(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec>
     out->on = false;
     int total_bits = 0;
     for (int k = 0; k < nk; k++) total_bits += ranges[k].bits;
-    const int slack = (int)std::max<int64_t>(0, ctx->opt("sort.trunc_slack", 4));
+    const int slack = (int)std::max<int64_t>(0, ctx->opt("sort.trunc_slack", 5));
     int T = bit_width_u64((uint64_t)(n - 1)) + slack;
     if (T + 8 > total_bits) return HARK_OK; // nothing to save
     // ---- sample, sorted by the full tuple; per adjacent pair: first differing key and its highest differing bit ----
@@ -1007,8 +1007,11 @@ int plan_truncation(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec>
                 break;
             }
     }
-    const double expect = 2.0 * (double)S * (double)S / (double)n; // ties a sample of harmless short runs would show
-    const int64_t thr = (int64_t)std::min<double>(std::max(4.0, expect), S / 8.0);
+    // A sample of S rows sees a prefix tie of the data only if it holds both rows: ties_sample ~ ties_data * (S/n)^2.
+    // The repair stays cheaper than the passes it replaces while ties_data < n/8 (which is also the work list's size),
+    // and a uniform key at the default slack shows 1/8 of that.
+    const double expect = (double)S * (double)S / (8.0 * (double)n);
+    const int64_t thr = (int64_t)std::max(4.0, expect);
     // ---- smallest digit-aligned prefix whose sample ties stay under the threshold ----
     for (;; T += 8) {
         int acc = 0, kstar = nk - 1, q = 0;
@@ -1064,7 +1067,7 @@ int fix_truncated(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec> &
     }
     for (int k = 0; k < tp.kstar; k++) P.moves[keys[k].array] = 0; // equal inside a run
     P.n = n;
-    P.cap = (unsigned long long)std::max<int64_t>(1024, n / 16);
+    P.cap = (unsigned long long)std::max<int64_t>(1024, n / 8);
     void *work = nullptr, *count = nullptr;
     HK_TRY(ctx->dalloc(&work, sizeof(unsigned long long) * P.cap));
     int rc = ctx->dalloc(&count, 2 * sizeof(unsigned long long));
@@ -1189,6 +1192,7 @@ int hk_radix_sort(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec> &
         for (int k = 0; k < nk; k++) ctx->h_scalars[2 * k] = ~0ull, ctx->h_scalars[2 * k + 1] = 0;
         e = cudaMemcpyAsync(d_scratch, ctx->h_scalars, sizeof(uint64_t) * 2 * nk, cudaMemcpyHostToDevice, ctx->stream);
         for (int k = 0; k < nk && e == cudaSuccess; k++) {
+            if (keys[k].have_range) continue;
             const hk_sort_array &ka = arrays[keys[k].array];
             const unsigned g = grid_for(ctx, n, 8);
             if (ka.width == 4)
@@ -1205,8 +1209,8 @@ int hk_radix_sort(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec> &
         // ---- 2. pass list: least significant key first, least significant digit first ----
         ranges.resize(nk);
         for (int k = 0; k < nk; k++) {
-            ranges[k].lo = ctx->h_scalars[2 * k];
-            ranges[k].hi = ctx->h_scalars[2 * k + 1];
+            ranges[k].lo = keys[k].have_range ? keys[k].lo : ctx->h_scalars[2 * k];
+            ranges[k].hi = keys[k].have_range ? keys[k].hi : ctx->h_scalars[2 * k + 1];
             ranges[k].bits = bit_width_u64(ranges[k].hi - ranges[k].lo);
         }
         full_passes = build_passes(keys, ranges, nk - 1, 0, passes);

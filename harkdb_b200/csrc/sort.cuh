@@ -11,6 +11,9 @@ struct hk_sort_keyspec {
     int array;     // index into the carried arrays
     int32_t dtype; // hark_dtype that defines the order (U32 for the reference-pinned paths)
     int32_t desc;
+    // optional: min / max order key of the column when the caller already knows them (column statistics)
+    bool have_range = false;
+    uint64_t lo = 0, hi = 0;
 };
 
 struct hk_sort_array {

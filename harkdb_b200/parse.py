@@ -7,7 +7,8 @@ same column-index lists and aggregate codes (``prod 1, sum 2, max 3, min 4``, :8
 itself contributes ``(g_col, 0)``, :73-75), and the same exception messages (:33,54,69,78,87).
 
 Extensions (clauses the reference's README lists but parse.py ignores): ``where``
-(conjunction of column-vs-constant comparisons), ``count``/``avg`` (codes 5, 6), ``having``,
+(AND / OR / NOT over column-vs-constant comparisons, BETWEEN, IN — handed to libhark in conjunctive
+normal form), ``count``/``avg`` (codes 5, 6), ``having``,
 ``orderby``, ``join``, ``limit``, ``select *`` and the single-column select that crashes the
 reference (:48-51 iterates a dict).  They appear as extra plan keys; a plan without them is
 byte-for-byte what the reference would build.
@@ -42,22 +43,16 @@ def _strip_qualifier(name, aliases):
     return None, name
 
 
-def _conjuncts(expr):
-    if isinstance(expr, dict) and "and" in expr:
-        out = []
-        for e in expr["and"]:
-            out.extend(_conjuncts(e))
-        return out
-    return [expr]
+PRED_OP_MASK, PRED_OR, PRED_NOT = 0xFF, 0x100, 0x200       # include/hark.h HARK_PRED_*
+MAX_PREDS = 16                                             # libhark's limit on one predicate list
 
 
-def _pred(expr, resolve):
+def _leaf(expr, resolve):
     """{"gt": ["a", 4]} -> (col_index, op_code, ival, fval).  `resolve(operand) -> column index`."""
-    if not isinstance(expr, dict) or len(expr) != 1:
-        raise Exception(f"unsupported predicate {expr}")
     (op, args), = expr.items()
     if op not in CMP_TO_CODE or not isinstance(args, list) or len(args) != 2:
-        raise Exception(f"unsupported predicate operator {op} (only AND of column-vs-constant comparisons)")
+        raise Exception(f"unsupported predicate operator {op} (column-vs-constant comparisons, AND / OR / NOT, "
+                        f"BETWEEN and IN are supported)")
     lhs, rhs = args
     if isinstance(lhs, (int, float)) and not isinstance(rhs, (int, float)):
         lhs, rhs, op = rhs, lhs, _FLIP[op]
@@ -68,23 +63,69 @@ def _pred(expr, resolve):
     return (idx, CMP_TO_CODE[op], ival, float(rhs))
 
 
+def _cnf(expr, resolve, neg=False):
+    """Boolean expression -> conjunctive normal form: a list of clauses, each a list of leaf predicates
+    (col, op | PRED_NOT?, ival, fval).  NOT is pushed down to the leaves (De Morgan) and stays a flag on the
+    comparison, so NOT (x > c) keeps rows where x is NaN; OR over ANDs is distributed."""
+    if not isinstance(expr, dict) or len(expr) != 1:
+        raise Exception(f"unsupported predicate {expr}")
+    (op, args), = expr.items()
+    if op == "not":
+        return _cnf(args, resolve, not neg)
+    if op in ("and", "or"):
+        parts = [_cnf(e, resolve, neg) for e in args]
+        if (op == "and") != neg:                      # conjunction: concatenate the clause lists
+            return [cl for p in parts for cl in p]
+        out = [[]]                                    # disjunction: one clause per choice of a clause from each part
+        for p in parts:
+            out = [a + b for a in out for b in p]
+            if sum(len(cl) for cl in out) > 4 * MAX_PREDS:
+                raise Exception("WHERE / HAVING expression is too large once in conjunctive normal form")
+        return out
+    if op in ("between", "not_between"):
+        x, lo, hi = args
+        e = {"and": [{"gte": [x, lo]}, {"lte": [x, hi]}]}
+        return _cnf(e, resolve, neg != (op == "not_between"))
+    if op in ("in", "nin"):
+        x, vals = args
+        e = {"or": [{"eq": [x, v]} for v in _as_list(vals)]}
+        return _cnf(e, resolve, neg != (op == "nin"))
+    c, code, ival, fval = _leaf(expr, resolve)
+    return [[(c, code | (PRED_NOT if neg else 0), ival, fval)]]
+
+
+def _preds(expr, resolve):
+    """WHERE / HAVING expression -> libhark predicate list (conjunctive normal form, hark.h hark_pred): clauses are
+    AND-ed, a predicate carrying PRED_OR is OR-ed with the next one.  A plain conjunction comes out exactly as the
+    flag-free list of its comparisons."""
+    out = []
+    for clause in _cnf(expr, resolve):
+        uniq = list(dict.fromkeys(clause))
+        for j, (c, code, ival, fval) in enumerate(uniq):
+            out.append((c, code | (PRED_OR if j + 1 < len(uniq) else 0), ival, fval))
+    if len(out) > MAX_PREDS:
+        raise Exception(f"WHERE / HAVING needs {len(out)} comparisons in conjunctive normal form; at most {MAX_PREDS}")
+    return out
+
+
 def finalize_pred(pred, is_int_column):
     """Integer columns compare in int64: fold a fractional constant into an equivalent integer one."""
     import math
-    col, op, ival, fval = pred
+    col, code, ival, fval = pred
+    op, flags = code & PRED_OP_MASK, code & ~PRED_OP_MASK
     if not is_int_column:
-        return (col, op, 0 if ival is None else ival, fval)
+        return (col, code, 0 if ival is None else ival, fval)
     if ival is not None:
-        return (col, op, ival, fval)
+        return (col, code, ival, fval)
     # x > 2.5 <=> x > 2 ; x >= 2.5 <=> x > 2 ; x < 2.5 <=> x < 3 ; x <= 2.5 <=> x < 3 ; = never ; != always
     fl = math.floor(fval)
     if op in (0, 1):
-        return (col, 0, fl, fval)
+        return (col, 0 | flags, fl, fval)
     if op in (2, 3):
-        return (col, 2, fl + 1, fval)
+        return (col, 2 | flags, fl + 1, fval)
     if op == 4:
-        return (col, 2, -(2 ** 63), fval)      # x < INT64_MIN: never true
-    return (col, 1, -(2 ** 63), fval)          # x >= INT64_MIN: always true
+        return (col, 2 | flags, -(2 ** 63), fval)      # x < INT64_MIN: never true
+    return (col, 1 | flags, -(2 ** 63), fval)          # x >= INT64_MIN: always true
 
 
 def sql_parse(tables, sql_statement):
@@ -132,7 +173,7 @@ def sql_parse(tables, sql_statement):
             raise Exception(f"unsupported predicate operand {operand}")
         return col_index(c)
 
-    where = [_pred(e, resolve_plain) for e in _conjuncts(js_obj["where"])] if "where" in js_obj else []
+    where = _preds(js_obj["where"], resolve_plain) if "where" in js_obj else []
     orderby = _as_list(js_obj["orderby"]) if "orderby" in js_obj else []
     extras = {}
     if where:
@@ -212,7 +253,7 @@ def sql_parse(tables, sql_statement):
         raise Exception(f"{c} is not an output column of the GROUP BY")
 
     if "having" in js_obj:
-        extras["having"] = [_pred(e, resolve_output) for e in _conjuncts(js_obj["having"])]
+        extras["having"] = _preds(js_obj["having"], resolve_output)
     if orderby:
         extras["orderby"] = [(resolve_output(k["value"]), 1 if k.get("sort") == "desc" else 0) for k in orderby]
     extras.pop("aliases", None)

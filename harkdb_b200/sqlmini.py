@@ -13,6 +13,9 @@ on are catalogued in SURVEY.md App. C:
     ... group by a                     "groupby": {"value": "a"}
     ... having count(c) > 3            "having": {"gt": [{"count": "c"}, 3]}
     ... order by a, b desc             "orderby": [{"value": "a"}, {"value": "b", "sort": "desc"}]
+    ... where a > 4 or not (b = 2)     "where": {"or": [{"gt": ["a", 4]}, {"not": {"eq": ["b", 2]}}]}
+    ... where a between 1 and 5        "where": {"between": ["a", 1, 5]}          (not between: "not_between")
+    ... where a in (1, 2, 3)           "where": {"in": ["a", [1, 2, 3]]}          (not in: "nin")
     from f join d on f.fk = d.pk       "from": ["f", {"join": "d", "on": {"eq": ["f.fk", "d.pk"]}}]
     ... limit 10                       "limit": 10
 """
@@ -23,7 +26,7 @@ import re
 from typing import Any, List
 
 KEYWORDS = {"select", "from", "where", "group", "by", "having", "order", "limit", "and", "or", "not", "as",
-            "join", "inner", "on", "asc", "desc"}
+            "join", "inner", "on", "asc", "desc", "between", "in"}
 CMP = {"=": "eq", "==": "eq", "!=": "neq", "<>": "neq", ">": "gt", ">=": "gte", "<": "lt", "<=": "lte"}
 
 _TOKEN = re.compile(r"""
@@ -109,6 +112,25 @@ class _Parser:
             self.eat("punct", ")")
             return e
         lhs = self.operand()
+        negated = False
+        if self.at_kw("not") and self.peek(1)[0] == "kw" and self.peek(1)[1] in ("between", "in"):
+            self.eat()
+            negated = True
+        if self.at_kw("between"):
+            self.eat()
+            lo = self.operand()
+            self.eat("kw", "and")
+            hi = self.operand()
+            return {"not_between" if negated else "between": [lhs, lo, hi]}
+        if self.at_kw("in"):
+            self.eat()
+            self.eat("punct", "(")
+            vals = [self.operand()]
+            while self.peek() == ("punct", ","):
+                self.eat()
+                vals.append(self.operand())
+            self.eat("punct", ")")
+            return {"nin" if negated else "in": [lhs, vals[0] if len(vals) == 1 else vals]}
         op = self.eat("op")[1]
         rhs = self.operand()
         return {CMP[op]: [lhs, rhs]}

@@ -50,6 +50,14 @@ typedef enum {
 /* Comparison operators of a WHERE / HAVING conjunct. */
 typedef enum { HARK_GT = 0, HARK_GE = 1, HARK_LT = 2, HARK_LE = 3, HARK_EQ = 4, HARK_NE = 5 } hark_cmp;
 
+/* Flags OR-ed into hark_pred.op.  A predicate list is in conjunctive normal form: HARK_PRED_OR chains a predicate
+ * with the NEXT one into an OR-clause (a maximal chain; the last predicate of the list must not carry it), the
+ * result is the AND of the clauses; HARK_PRED_NOT negates the comparison's boolean result (so NOT (x > c) is true
+ * for a NaN x, unlike x <= c).  A list without flags is the plain conjunction.                                    */
+#define HARK_PRED_OP_MASK 0xff
+#define HARK_PRED_OR 0x100
+#define HARK_PRED_NOT 0x200
+
 /* One conjunct `column <op> constant`.  Integer columns (i32/u32/i64) are widened to int64
  * and compared with `ival`; f32 columns compare in f32 against (float)fval, f64 columns in
  * f64 against fval; NaN compares false except under HARK_NE (IEEE).                        */

@@ -255,12 +255,29 @@ def _cmp(a: np.ndarray, op: int, ival: int, fval: float) -> np.ndarray:
 
 
 def query_filter(columns: Sequence[np.ndarray], cols: Sequence[int], preds: Sequence[Pred]) -> List[np.ndarray]:
-    """SELECT cols WHERE p1 AND p2 ...; input row order kept."""
+    """SELECT cols WHERE <preds in conjunctive normal form>; input row order kept.  A predicate whose op carries
+    PRED_OR is OR-ed with the next one; the row passes when every such clause holds; PRED_NOT negates the comparison
+    (include/hark.h).  Without flags this is p1 AND p2 AND ..."""
+    return [np.ascontiguousarray(columns[c][pred_mask(columns, preds)]) for c in cols]
+
+
+PRED_OP_MASK, PRED_OR, PRED_NOT = 0xFF, 0x100, 0x200
+
+
+def pred_mask(columns: Sequence[np.ndarray], preds: Sequence[Pred]) -> np.ndarray:
     n = len(columns[0]) if columns else 0
     mask = np.ones(n, dtype=bool)
+    clause = np.zeros(n, dtype=bool)
     for (c, op, ival, fval) in preds:
-        mask &= _cmp(columns[c], op, ival, fval)
-    return [np.ascontiguousarray(columns[c][mask]) for c in cols]
+        m = _cmp(columns[c], op & PRED_OP_MASK, ival, fval)
+        if op & PRED_NOT:
+            m = ~m
+        clause |= m
+        if op & PRED_OR:
+            continue
+        mask &= clause
+        clause = np.zeros(n, dtype=bool)
+    return mask
 
 
 def _agg_typed(op: int, v: np.ndarray, starts: np.ndarray, counts: np.ndarray) -> np.ndarray:

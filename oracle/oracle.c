@@ -346,17 +346,25 @@ static inline int cmp_f64(int op, double x, double c) {
     }
 }
 
+/* hark.h HARK_PRED_OR / HARK_PRED_NOT: the list is in conjunctive normal form — a predicate carrying HARK_PRED_OR
+ * is OR-ed with the next one, the row passes when every such clause holds; HARK_PRED_NOT negates the comparison. */
 static inline int row_passes(const char *row, int dt, const hark_pred *preds, int64_t np) {
+    int clause = 0;
     for (int64_t p = 0; p < np; p++) {
         int ok;
+        const int op = preds[p].op & HARK_PRED_OP_MASK;
         switch (dt) {
-        case HARK_I32: ok = cmp_i64(preds[p].op, ((const int32_t *)row)[preds[p].col], preds[p].ival); break;
-        case HARK_U32: ok = cmp_i64(preds[p].op, ((const uint32_t *)row)[preds[p].col], preds[p].ival); break;
-        case HARK_I64: ok = cmp_i64(preds[p].op, ((const int64_t *)row)[preds[p].col], preds[p].ival); break;
-        case HARK_F32: ok = cmp_f32(preds[p].op, ((const float *)row)[preds[p].col], (float)preds[p].fval); break;
-        default: ok = cmp_f64(preds[p].op, ((const double *)row)[preds[p].col], preds[p].fval); break;
+        case HARK_I32: ok = cmp_i64(op, ((const int32_t *)row)[preds[p].col], preds[p].ival); break;
+        case HARK_U32: ok = cmp_i64(op, ((const uint32_t *)row)[preds[p].col], preds[p].ival); break;
+        case HARK_I64: ok = cmp_i64(op, ((const int64_t *)row)[preds[p].col], preds[p].ival); break;
+        case HARK_F32: ok = cmp_f32(op, ((const float *)row)[preds[p].col], (float)preds[p].fval); break;
+        default: ok = cmp_f64(op, ((const double *)row)[preds[p].col], preds[p].fval); break;
         }
-        if (!ok) return 0;
+        if (preds[p].op & HARK_PRED_NOT) ok = !ok;
+        clause |= ok;
+        if (preds[p].op & HARK_PRED_OR) continue;
+        if (!clause) return 0;
+        clause = 0;
     }
     return 1;
 }
@@ -384,7 +392,7 @@ int oracle_query_filter(const void *db, int64_t n, int64_t m, int32_t dtype, con
     if (dtype < HARK_I32 || dtype > HARK_F64) return 1;
     for (int64_t j = 0; j < k; j++) if (cols[j] < 0 || cols[j] >= m) return 1;
     for (int64_t p = 0; p < np; p++)
-        if (preds[p].col < 0 || preds[p].col >= m || preds[p].op < HARK_GT || preds[p].op > HARK_NE) return 1;
+        if (preds[p].col < 0 || preds[p].col >= m || (preds[p].op & HARK_PRED_OP_MASK) > HARK_NE || (preds[p].op & ~0x3ff)) return 1;
     size_t w = dtype_size(dtype);
 #ifdef _OPENMP
     if (threads > 1) {

@@ -261,3 +261,64 @@ def test_filter_full_size_properties():
     assert cnt + a.shape[0] == b.shape[0]
     for x in (a, b, r, t):
         x.free()
+
+
+# ---- WHERE in conjunctive normal form: OR-clauses and NOT (hark.h HARK_PRED_OR / HARK_PRED_NOT) ----
+@pytest.mark.parametrize("dtype", ALL_DT)
+@pytest.mark.parametrize("n", [0, 1, 1023, 4097, 32769, 250007])
+def test_filter_cnf_clauses(dtype, n):
+    env = get_env()
+    OR, NOT = NO.PRED_OR, NO.PRED_NOT
+    rng = np.random.default_rng(7 * n + dtype)
+    a = rand_table(rng, n, 5, dtype, lo=-8 if dtype != NO.U32 else 0, hi=9, nan_frac=0.02)
+    if dtype in (NO.F32, NO.F64):
+        a = np.round(a * 16) / 16
+    c = 0.5 if dtype in (NO.F32, NO.F64) else 3
+    iv, fv = (0, c) if dtype in (NO.F32, NO.F64) else (c, float(c))
+    pred_lists = [
+        [(0, NO.GT | OR, iv, fv), (1, NO.LT, iv, fv)],                                              # a OR b
+        [(0, NO.GT | NOT, iv, fv)],                                                                 # NOT a (NaN rows pass)
+        [(0, NO.GT | OR, iv, fv), (1, NO.LE | NOT | OR, iv, fv), (2, NO.EQ, iv, fv), (3, NO.NE | NOT, iv, fv)],
+        [(4, NO.GE, iv, fv), (0, NO.EQ | OR, iv, fv), (0, NO.EQ | OR, iv + 1, fv + 0.25), (0, NO.EQ, iv - 2, fv - 0.25),
+         (2, NO.LT | NOT | OR, iv, fv), (3, NO.GT | NOT, iv, fv)],                                  # c AND a IN (..) AND (..)
+        [(p % 5, [NO.GT, NO.LT, NO.NE, NO.GE][p % 4] | (OR if p % 3 != 2 else 0) | (NOT if p % 5 == 1 else 0),
+          iv + p % 3 - 1, fv + 0.125 * (p % 3 - 1)) for p in range(15)] + [(1, NO.NE, iv, fv)],     # 16 predicates
+    ]
+    t = env.to_device(a)
+    for preds in pred_lists:
+        r = env.query_filter(t, [0, 4, 2], preds)
+        exp = NO.query_filter(cols_of(a), [0, 4, 2], preds)
+        assert r.shape[0] == len(exp[0]), (dtype, n, preds)
+        for j in range(3):
+            assert np.array_equal(r.column(j), exp[j], equal_nan=True), (dtype, n, preds, j)
+        r.free()
+    t.free()
+
+
+def test_filter_cnf_mixed_widths_and_bad_lists():
+    env = get_env()
+    OR, NOT = NO.PRED_OR, NO.PRED_NOT
+    rng = np.random.default_rng(99)
+    n = 70001
+    cols = [rng.integers(-5, 6, n).astype(np.int32), rng.integers(-5, 6, n).astype(np.int64),
+            rng.random(n).astype(np.float32), rng.random(n)]
+    cols[3][rng.integers(0, n, 500)] = np.nan
+    t = env.from_columns(cols)
+    preds = [(0, NO.GT | OR, 2, 2.0), (3, NO.LT | NOT, 0, 0.5), (1, NO.EQ | OR, -1, -1.0), (2, NO.GE, 0, 0.75)]
+    r = env.query_filter(t, [3, 1, 0], preds)
+    exp = NO.query_filter(cols, [3, 1, 0], preds)
+    for j in range(3):
+        assert np.array_equal(r.column(j), exp[j], equal_nan=True)
+    r.free()
+    # constants outside an i32 column's range fold to always / never, also under NOT
+    preds = [(0, NO.LT | NOT | OR, 1 << 40, 0.0), (1, NO.GT, 3, 3.0)]
+    r = env.query_filter(t, [1], preds)
+    assert np.array_equal(r.column(0), NO.query_filter(cols, [1], preds)[0])
+    r.free()
+    with pytest.raises(Exception, match="last predicate"):
+        env.query_filter(t, [0], [(0, NO.GT | OR, 0, 0.0)])
+    with pytest.raises(Exception, match="bad comparison"):
+        env.query_filter(t, [0], [(0, NO.GT | 0x400, 0, 0.0)])
+    with pytest.raises(Exception, match="at most 16"):
+        env.query_filter(t, [0], [(0, NO.GT, 0, 0.0)] * 17)
+    t.free()

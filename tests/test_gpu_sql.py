@@ -57,6 +57,45 @@ def test_where(fc):
     assert fc.sql("select col1 from game_1 where col1 > 100").shape == (0, 1)
 
 
+def test_where_or_not_between_in(fc):
+    d = json.load(open(os.path.join(GOLDEN, "data_csv.json")))
+    a = np.asarray(d["rows"])
+    c = {f"col{i + 1}": a[:, i] for i in range(a.shape[1])}
+    cases = [
+        ("col1 > 5 or col3 = 3", (c["col1"] > 5) | (c["col3"] == 3)),
+        ("not (col1 > 5 or col3 = 3)", ~((c["col1"] > 5) | (c["col3"] == 3))),
+        ("col1 between 1 and 6 and col2 not in (0, 6)", (c["col1"] >= 1) & (c["col1"] <= 6) & ~np.isin(c["col2"], [0, 6])),
+        ("col1 in (0, 1) or (col2 >= 1 and not col5 < 6)", np.isin(c["col1"], [0, 1]) | ((c["col2"] >= 1) & ~(c["col5"] < 6))),
+        ("col1 > 0.5 or col2 < -0.5", (c["col1"] > 0.5) | (c["col2"] < -0.5)),
+    ]
+    for w, m in cases:
+        out = fc.sql(f"select col1, col3 from game_1 where {w}")
+        assert out.tolist() == a[m][:, [0, 2]].tolist(), w
+    out = fc.sql("select col1, sum(col2), count(col2) from game_1 where col2 > 0 or col1 = 0 group by col1 "
+                 "having count(col2) > 1 or sum(col2) >= 2 order by col1 desc")
+    m = (c["col2"] > 0) | (c["col1"] == 0)
+    exp = []
+    for k in sorted(set(a[m][:, 0].tolist()), reverse=True):
+        v = a[m][a[m][:, 0] == k][:, 1]
+        if len(v) > 1 or v.sum() >= 2:
+            exp.append([k, int(v.sum()), len(v)])
+    assert out.tolist() == exp
+
+
+def test_where_or_float_table_nan():
+    need_gpu()
+    from harkdb_b200 import FutharkContext
+    rng = np.random.default_rng(8)
+    a = rng.random((200001, 4)).astype(np.float32)
+    a[rng.integers(0, len(a), 1000), 1] = np.nan
+    ctx = FutharkContext()
+    ctx.create_table("t", pd.DataFrame(a, columns=["a", "b", "c", "d"]))
+    out = ctx.sql("select a, d from t where (a < 0.25 or not b > 0.5) and c between 0.1 and 0.9")
+    with np.errstate(invalid="ignore"):
+        m = ((a[:, 0] < np.float32(0.25)) | ~(a[:, 1] > np.float32(0.5))) & (a[:, 2] >= np.float32(0.1)) & (a[:, 2] <= np.float32(0.9))
+    assert np.array_equal(out, a[m][:, [0, 3]])
+
+
 def test_where_float_table():
     need_gpu()
     from harkdb_b200 import FutharkContext

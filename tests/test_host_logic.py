@@ -95,8 +95,10 @@ def test_plan_extensions():
     assert plan["groupbys"] == [0, 2, 5, 6] and plan["select"] == [0, 1, 1, 1]
     assert plan["having"] == [(3, 0, 1, 1.0)]          # output column 3 = count (0 is the key)
     assert plan["orderby"] == [(0, 1)]
-    with pytest.raises(Exception, match="only AND"):
-        sql_parse({"game_1": t}, "select col1 from game_1 where col1 > 1 or col2 < 3")
+    plan = sql_parse({"game_1": t}, "select col1 from game_1 where col1 > 1 or col2 < 3")
+    assert plan["where"] == [(0, 0 | 0x100, 1, 1.0), (1, 2, 3, 3.0)]     # one OR-clause (HARK_PRED_OR on the first)
+    with pytest.raises(Exception, match="right-hand side must be a numeric constant"):
+        sql_parse({"game_1": t}, "select col1 from game_1 where col1 > col2")
 
 
 def test_plan_join():
@@ -116,6 +118,97 @@ def test_finalize_pred_integer_columns():
     assert finalize_pred((0, 3, None, -2.5), True) == (0, 2, -2, -2.5)  # x <= -2.5 <=> x < -2
     assert finalize_pred((0, 0, 7, 7.0), True) == (0, 0, 7, 7.0)
     assert finalize_pred((0, 0, None, 0.5), False) == (0, 0, 0, 0.5)
+
+
+# ---- WHERE / HAVING boolean expressions -> conjunctive normal form (hark.h HARK_PRED_OR / HARK_PRED_NOT) ----
+def test_sql_shapes_between_in():
+    p = sqlmini.parse
+    assert p("select a from t where a between 1 and 5 and b > 2")["where"] == \
+        {"and": [{"between": ["a", 1, 5]}, {"gt": ["b", 2]}]}
+    assert p("select a from t where a not between -1 and 5")["where"] == {"not_between": ["a", -1, 5]}
+    assert p("select a from t where a in (1, 2, 3)")["where"] == {"in": ["a", [1, 2, 3]]}
+    assert p("select a from t where a not in (7)")["where"] == {"nin": ["a", 7]}
+    assert p("select a from t where (a > 1 or b < 2) and not (c = 3 or a = 4)")["where"] == \
+        {"and": [{"or": [{"gt": ["a", 1]}, {"lt": ["b", 2]}]}, {"not": {"or": [{"eq": ["c", 3]}, {"eq": ["a", 4]}]}}]}
+
+
+def _eval_tree(expr, cols, names):
+    """Direct evaluation of a moz_sql_parser-shaped boolean expression with numpy (IEEE comparisons)."""
+    (op, args), = expr.items()
+    if op == "and":
+        return np.logical_and.reduce([_eval_tree(e, cols, names) for e in args])
+    if op == "or":
+        return np.logical_or.reduce([_eval_tree(e, cols, names) for e in args])
+    if op == "not":
+        return ~_eval_tree(args, cols, names)
+    if op in ("between", "not_between"):
+        x = cols[names.index(args[0])]
+        m = (x >= args[1]) & (x <= args[2])
+        return ~m if op == "not_between" else m
+    if op in ("in", "nin"):
+        x = cols[names.index(args[0])]
+        vals = args[1] if isinstance(args[1], list) else [args[1]]
+        m = np.logical_or.reduce([x == v for v in vals])
+        return ~m if op == "nin" else m
+    x = cols[names.index(args[0])]
+    with np.errstate(invalid="ignore"):
+        return {"gt": x > args[1], "gte": x >= args[1], "lt": x < args[1], "lte": x <= args[1], "eq": x == args[1],
+                "neq": x != args[1]}[op]
+
+
+def test_where_boolean_expressions_become_cnf_with_the_same_truth_table():
+    from harkdb_b200.parse import PRED_NOT, PRED_OR, _preds
+    from oracle import np_oracle as NO
+    rng = np.random.default_rng(5)
+    n = 4000
+    names = ["a", "b", "c", "d"]
+    cols = [rng.integers(-5, 6, n).astype(np.int32), rng.integers(0, 10, n).astype(np.int64),
+            rng.integers(-5, 6, n).astype(np.float32), rng.random(n)]
+    cols[2][rng.integers(0, n, 200)] = np.nan
+    cols[3][rng.integers(0, n, 200)] = np.nan
+    is_int = [True, True, False, False]
+    resolve = names.index
+    stmts = [
+        "a > 1 or b < 3",
+        "not (a > 1 or b < 3)",
+        "not c > 0",                                      # true for NaN rows, unlike c <= 0
+        "(a > 1 and b < 3) or (c >= 0 and d < 0.5)",
+        "a between -2 and 2 and not d between 0.25 and 0.75",
+        "a in (1, 3, 5) or c not in (0, 2)",
+        "not (a = 1 and (b <> 2 or not (c < 1.5))) and d >= 0.1",
+        "a > 2.5 or not b <= 3.5 or a = 1.5 or not a <> 0.5",
+        "(a > 0 or b > 5 or c > 1) and (a < 3 or d < 0.9) and b <> 4",
+    ]
+    for w in stmts:
+        tree = sqlmini.parse("select a from t where " + w)["where"]
+        preds = [finalize_pred(p, is_int[p[0]]) for p in _preds(tree, resolve)]
+        assert not (preds[-1][1] & PRED_OR) and len(preds) <= 16
+        got = NO.pred_mask(cols, preds)
+        exp = _eval_tree(tree, cols, names)
+        assert np.array_equal(got, exp), w
+    # a plain conjunction is exactly the flag-free list the reference-shaped plan always had
+    tree = sqlmini.parse("select a from t where a > 1 and b <= 2 and c <> 0.5")["where"]
+    assert _preds(tree, resolve) == [(0, 0, 1, 1.0), (1, 3, 2, 2.0), (2, 5, None, 0.5)]
+    assert _preds(sqlmini.parse("select a from t where not a > 1")["where"], resolve) == [(0, 0 | PRED_NOT, 1, 1.0)]
+    with pytest.raises(Exception, match="conjunctive normal form"):
+        big = " or ".join(f"(a > {i} and b < {i} and c > {i})" for i in range(4))
+        _preds(sqlmini.parse("select a from t where " + big)["where"], resolve)
+
+
+def test_c_oracle_filter_cnf_matches_numpy_oracle():
+    from harkdb_b200.parse import PRED_NOT, PRED_OR
+    from oracle import c_oracle as CO
+    from oracle import np_oracle as NO
+    rng = np.random.default_rng(6)
+    for dtype in (NO.I32, NO.F32, NO.F64, NO.I64):
+        a = rng.integers(-4, 5, (3000, 3)).astype(NO.NP_DTYPES[dtype])
+        if dtype in (NO.F32, NO.F64):
+            a[rng.integers(0, 3000, 100), rng.integers(0, 3, 100)] = np.nan
+        preds = [(0, NO.GT | PRED_OR, 1, 1.0), (1, NO.LT | PRED_NOT | PRED_OR, 0, 0.0), (2, NO.EQ, 2, 2.0),
+                 (1, NO.NE | PRED_NOT, -1, -1.0)]
+        got = CO.query_filter(a, [2, 0], preds)
+        exp = NO.query_filter([np.ascontiguousarray(a[:, c]) for c in range(3)], [2, 0], preds)
+        assert np.array_equal(got[:, 0], exp[0], equal_nan=True) and np.array_equal(got[:, 1], exp[1], equal_nan=True)
 
 
 # ---- table.py ----
