@@ -78,6 +78,8 @@ class FutharkContext:
         if "join" in val_dic:
             return self._sql_join(val_dic)
 
+        if "g_cols" in val_dic:
+            return self._sql_groupby_ext(val_dic)
         if "groupbys" not in val_dic:
             if plain:
                 res = self.FutEnv.query_sel(t1, np.array(sel_cols))
@@ -122,16 +124,21 @@ class FutharkContext:
         env = self.FutEnv
         t, tmp = self._as_device(plan["table"])
         try:
-            g_col, s_cols, ops = plan["g_col"], list(plan["select"]), list(plan["groupbys"])
+            multi = "g_cols" in plan                      # GROUP BY a, b, ... (parse.py:64's TODO)
+            g_cols = list(plan["g_cols"]) if multi else [plan["g_col"]]
+            s_cols, ops = list(plan["select"]), list(plan["groupbys"])
             cur, cur_tmp = t, False
             if "where" in plan:
                 preds = [finalize_pred(p, self._is_int_col(t, p[0])) for p in plan["where"]]
-                need = [g_col] + [c for c in dict.fromkeys(s_cols) if c != g_col]
+                need = g_cols + [c for c in dict.fromkeys(s_cols) if c not in g_cols]
                 cur = env.query_filter(t, need, preds)
                 cur_tmp = True
                 s_cols = [need.index(c) for c in s_cols]
-                g_col = 0
-            res = env.query_groupby_ex(cur, g_col, s_cols, ops)
+                g_cols = list(range(len(g_cols)))
+            if multi:
+                res = env.query_groupby_multi(cur, g_cols, s_cols, ops)
+            else:
+                res = env.query_groupby_ex(cur, g_cols[0], s_cols, ops)
             if cur_tmp:
                 cur.free()
             if "having" in plan:

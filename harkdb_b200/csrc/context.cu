@@ -43,7 +43,9 @@ void hark_ctx::dfree(void *p) {
 }
 
 void hark_ctx::entry_begin() {
+    if (entry_depth++ > 0) return; // nested operator: the outer entry's clock keeps running
     entry_launches = 0;
+    kernel_marked = false;
     last = hark_stats{};
     cudaEventRecord(ev_t0, stream);
     cudaEventRecord(ev_k0, stream); // entries without a marked kernel report kernel_ms ~ 0
@@ -51,6 +53,7 @@ void hark_ctx::entry_begin() {
 }
 
 void hark_ctx::entry_end(int64_t alg_bytes, int64_t rows_in, int64_t rows_out) {
+    if (entry_depth > 0 && --entry_depth > 0) return;
     cudaEventRecord(ev_t1, stream);
     last.alg_bytes = alg_bytes;
     last.rows_in = rows_in;
@@ -159,6 +162,7 @@ extern "C" void hark_context_free(hark_ctx *ctx) {
 
 #define HK_ENTER(ctx)                                       \
     if (!(ctx)) return HARK_ERR_ARG;                        \
+    (ctx)->entry_depth = 0;          \
     HK_CUDA(ctx, cudaSetDevice((ctx)->device))
 
 extern "C" int hark_context_sync(hark_ctx *ctx) {

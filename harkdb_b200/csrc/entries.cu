@@ -13,6 +13,7 @@
 
 #define HK_ENTER(ctx)                \
     if (!(ctx)) return HARK_ERR_ARG; \
+    (ctx)->entry_depth = 0;          \
     HK_CUDA(ctx, cudaSetDevice((ctx)->device))
 
 extern "C" int hark_entry_query_sel(hark_ctx *ctx, hark_table **out, const hark_table *db, const int32_t *cols,
@@ -50,6 +51,20 @@ extern "C" int hark_entry_query_groupby_ex(hark_ctx *ctx, hark_table **out, cons
     HK_ARG(ctx, out && db && c >= 0 && (c == 0 || (s_cols && ops)) && nh >= 0 && (nh == 0 || having),
            "query_groupby_ex: bad argument");
     return hk_groupby(ctx, out, db, g_col, s_cols, ops, c, having, nh, /*pinned_u32=*/false);
+    HK_ABI_END(ctx)
+}
+
+extern "C" int hark_entry_query_groupby_multi(hark_ctx *ctx, hark_table **out, const hark_table *db, const int32_t *g_cols,
+                                              int64_t ng, const int32_t *s_cols, const int32_t *ops, int64_t c,
+                                              const hark_pred *having, int64_t nh) {
+    HK_ENTER(ctx);
+    HK_ABI_BEGIN
+    HK_ARG(ctx, out && db && g_cols && ng >= 1 && c >= 0 && (c == 0 || (s_cols && ops)) && nh >= 0 && (nh == 0 || having),
+           "query_groupby_multi: bad argument");
+    if (ng == 1) { // one key: the single-key operator, with the key column first as everywhere else
+        return hk_groupby(ctx, out, db, g_cols[0], s_cols, ops, c, having, nh, /*pinned_u32=*/false);
+    }
+    return hk_groupby_multi(ctx, out, db, g_cols, ng, s_cols, ops, c, having, nh);
     HK_ABI_END(ctx)
 }
 

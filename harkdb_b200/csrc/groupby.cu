@@ -640,15 +640,11 @@ int hk_groupby(hark_ctx *ctx, hark_table **out, const hark_table *db, int32_t g_
                 if (nh > 0) { // HAVING: K1 over the (small) group table; output column indices
                     std::vector<int32_t> all;
                     for (int64_t j = 0; j < 1 + c; j++) all.push_back((int32_t)j);
-                    hark_stats keep = ctx->last;
-                    const int64_t keep_launches = ctx->entry_launches;
                     hark_table *f = nullptr;
                     int rc = hk_filter(ctx, &f, t, all.data(), 1 + c, having, nh);
                     hark_table_free(ctx, t);
                     if (rc != HARK_OK) return rc;
                     t = f;
-                    ctx->last = keep;
-                    ctx->entry_launches += keep_launches;
                 }
                 int64_t alg = n * hk_dtype_size(key_dtype);
                 for (int v = 0; v < rq.nvals; v++) alg += n * 4;
@@ -713,15 +709,11 @@ int hk_groupby(hark_ctx *ctx, hark_table **out, const hark_table *db, int32_t g_
     if (nh > 0) { // HAVING: K1 over the (small) group table; output column indices
         std::vector<int32_t> all;
         for (int64_t j = 0; j < 1 + c; j++) all.push_back((int32_t)j);
-        hark_stats keep = ctx->last;
-        const int64_t keep_launches = ctx->entry_launches;
         hark_table *f = nullptr;
         rc = hk_filter(ctx, &f, t, all.data(), 1 + c, having, nh);
         hark_table_free(ctx, t);
         if (rc != HARK_OK) return rc;
         t = f;
-        ctx->last = keep;
-        ctx->entry_launches += keep_launches;
     }
     int64_t alg = 0;
     for (auto &a : arrays) alg += n * a.width;

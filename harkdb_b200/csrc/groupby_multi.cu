@@ -1,0 +1,266 @@
+// groupby_multi.cu — GROUP BY over several integer key columns.
+//
+// The reference groups on ONE column and says so with regret (parse.py:64 "TODO: allow to be several columns";
+// groupby.fut:51-58 takes a single g_col).  This extension keeps every fast path of the single-key operator by
+// turning the key tuple into one dense integer first:
+//   1. every key column's min / max order key comes from the column statistics (one read each, cached);
+//   2. hk_pack_keys_kernel streams the key columns once and writes the composite
+//          comp = sum_k (ordkey_k(x_k) - min_k) << shift_k          (most significant key in the top bits),
+//      an i32 column when the keys' combined ranges need <= 31 bits, else i64 (<= 63 bits) — composite order is
+//      the lexicographic order of the tuple, each key in its own dtype's signed/unsigned order;
+//   3. the single-key GROUP BY (K2 dense / partitioned shared-memory aggregation when the composite range allows,
+//      K3 + K4 otherwise) runs on the composite;
+//   4. hk_unpack_keys_kernel turns the G group composites back into typed key columns.
+// HBM traffic added to the single-key operator: n * (sum of key widths) read + n * 4|8 written by the pack pass.
+// Semantics (restated by the test oracle): output = [key_1..key_ng, agg_1..agg_c], rows ascending
+// lexicographically; aggregates as hark_entry_query_groupby_ex.
+#include <algorithm>
+#include <new>
+#include <stdexcept>
+#include <vector>
+
+#include "dense_agg.cuh"
+#include "hark_internal.cuh"
+
+namespace {
+
+constexpr int GM_MAXK = 8;
+
+struct PackParams {
+    int nk;
+    const void *col[GM_MAXK];
+    int width[GM_MAXK];
+    int dtype[GM_MAXK];
+    uint64_t lo[GM_MAXK];
+    int shift[GM_MAXK];
+    int64_t n;
+    void *out;
+};
+
+__device__ __forceinline__ uint64_t gm_ordkey(const void *col, int width, int dtype, int64_t r) {
+    if (width == 4) return (uint64_t)hk_ordkey32(reinterpret_cast<const uint32_t *>(col)[r], dtype);
+    return hk_ordkey64(reinterpret_cast<const uint64_t *>(col)[r], dtype);
+}
+
+// OW = width of the composite (4 or 8).  Four consecutive rows per thread so that a warp reads 512 / 1024
+// contiguous bytes of every key column and writes one 16 / 32-byte piece per thread.
+template <int OW>
+__global__ void __launch_bounds__(256) hk_pack_keys_kernel(const __grid_constant__ PackParams P) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+    for (int64_t r0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; r0 < P.n; r0 += stride) {
+        uint64_t comp[4] = {0, 0, 0, 0};
+        const bool full = r0 + 4 <= P.n;
+#pragma unroll 1
+        for (int k = 0; k < P.nk; k++) {
+            if (full) {
+                if (P.width[k] == 4) {
+                    const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(P.col[k]) + r0));
+                    comp[0] |= ((uint64_t)hk_ordkey32(v.x, P.dtype[k]) - P.lo[k]) << P.shift[k];
+                    comp[1] |= ((uint64_t)hk_ordkey32(v.y, P.dtype[k]) - P.lo[k]) << P.shift[k];
+                    comp[2] |= ((uint64_t)hk_ordkey32(v.z, P.dtype[k]) - P.lo[k]) << P.shift[k];
+                    comp[3] |= ((uint64_t)hk_ordkey32(v.w, P.dtype[k]) - P.lo[k]) << P.shift[k];
+                } else {
+                    const uint64_t *p = reinterpret_cast<const uint64_t *>(P.col[k]) + r0;
+                    const ulonglong2 a = __ldcs(reinterpret_cast<const ulonglong2 *>(p));
+                    const ulonglong2 b = __ldcs(reinterpret_cast<const ulonglong2 *>(p + 2));
+                    comp[0] |= (hk_ordkey64(a.x, P.dtype[k]) - P.lo[k]) << P.shift[k];
+                    comp[1] |= (hk_ordkey64(a.y, P.dtype[k]) - P.lo[k]) << P.shift[k];
+                    comp[2] |= (hk_ordkey64(b.x, P.dtype[k]) - P.lo[k]) << P.shift[k];
+                    comp[3] |= (hk_ordkey64(b.y, P.dtype[k]) - P.lo[k]) << P.shift[k];
+                }
+            } else {
+                for (int e = 0; e < 4; e++)
+                    if (r0 + e < P.n) comp[e] |= (gm_ordkey(P.col[k], P.width[k], P.dtype[k], r0 + e) - P.lo[k]) << P.shift[k];
+            }
+        }
+        if constexpr (OW == 4) {
+            uint32_t *o = reinterpret_cast<uint32_t *>(P.out) + r0;
+            if (full) {
+                __stcs(reinterpret_cast<uint4 *>(o), make_uint4((uint32_t)comp[0], (uint32_t)comp[1], (uint32_t)comp[2], (uint32_t)comp[3]));
+            } else {
+                for (int e = 0; e < 4; e++)
+                    if (r0 + e < P.n) o[e] = (uint32_t)comp[e];
+            }
+        } else {
+            uint64_t *o = reinterpret_cast<uint64_t *>(P.out) + r0;
+            if (full) {
+                __stcs(reinterpret_cast<ulonglong2 *>(o), make_ulonglong2(comp[0], comp[1]));
+                __stcs(reinterpret_cast<ulonglong2 *>(o + 2), make_ulonglong2(comp[2], comp[3]));
+            } else {
+                for (int e = 0; e < 4; e++)
+                    if (r0 + e < P.n) o[e] = comp[e];
+            }
+        }
+    }
+}
+
+struct UnpackParams {
+    int nk;
+    const void *comp;
+    int comp_w;
+    void *out[GM_MAXK];
+    int width[GM_MAXK];
+    int dtype[GM_MAXK];
+    uint64_t lo[GM_MAXK];
+    uint64_t mask[GM_MAXK];
+    int shift[GM_MAXK];
+    int64_t n;
+};
+
+__global__ void __launch_bounds__(256) hk_unpack_keys_kernel(const __grid_constant__ UnpackParams P) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < P.n; r += stride) {
+        const uint64_t c = P.comp_w == 4 ? (uint64_t)reinterpret_cast<const uint32_t *>(P.comp)[r]
+                                         : reinterpret_cast<const uint64_t *>(P.comp)[r];
+        for (int k = 0; k < P.nk; k++) {
+            const uint64_t u = ((c >> P.shift[k]) & P.mask[k]) + P.lo[k]; // the order key; undo the sign-bit flip
+            if (P.width[k] == 4) reinterpret_cast<uint32_t *>(P.out[k])[r] = (uint32_t)u ^ (P.dtype[k] == HARK_I32 ? 0x80000000u : 0u);
+            else reinterpret_cast<uint64_t *>(P.out[k])[r] = u ^ 0x8000000000000000ull; // 8-byte integer keys are i64
+        }
+    }
+}
+
+int bits_of(uint64_t v) {
+    int b = 0;
+    while (v) {
+        b++;
+        v >>= 1;
+    }
+    return b;
+}
+
+} // namespace
+
+int hk_groupby_multi(hark_ctx *ctx, hark_table **out, const hark_table *db, const int32_t *g_cols, int64_t ng,
+                     const int32_t *s_cols, const int32_t *ops, int64_t c, const hark_pred *having, int64_t nh) {
+    const int64_t n = db->n, m = (int64_t)db->cols.size();
+    HK_ARG(ctx, ng >= 1 && ng <= GM_MAXK, "query_groupby_multi: between 1 and 8 group columns");
+    for (int64_t k = 0; k < ng; k++) {
+        HK_ARG(ctx, g_cols[k] >= 0 && g_cols[k] < m, "query_groupby_multi: group column index out of bounds");
+        HK_ARG(ctx, hk_dtype_int(db->cols[g_cols[k]].dtype), "query_groupby_multi: the group keys must be integer columns");
+    }
+    for (int64_t j = 0; j < c; j++)
+        HK_ARG(ctx, s_cols[j] >= 0 && s_cols[j] < m, "query_groupby_multi: aggregated column index out of bounds");
+
+    ctx->entry_begin();
+    // ---- 1. key ranges -> bit layout of the composite ----
+    PackParams PP;
+    memset(&PP, 0, sizeof PP);
+    UnpackParams UP;
+    memset(&UP, 0, sizeof UP);
+    int bits[GM_MAXK], total_bits = 0;
+    for (int64_t k = 0; k < ng; k++) {
+        const hark_col &col = db->cols[g_cols[k]];
+        uint64_t lo = 0, hi = 0;
+        if (n > 0) HK_TRY(hk_column_minmax(ctx, col, n, col.dtype, &lo, &hi));
+        bits[k] = n > 0 ? bits_of(hi - lo) : 0;
+        total_bits += bits[k];
+        PP.col[k] = col.ptr;
+        PP.width[k] = UP.width[k] = hk_dtype_size(col.dtype);
+        PP.dtype[k] = UP.dtype[k] = col.dtype;
+        PP.lo[k] = UP.lo[k] = lo;
+        UP.mask[k] = bits[k] >= 64 ? ~0ull : ((1ull << bits[k]) - 1ull);
+    }
+    if (total_bits > 63)
+        return ctx->fail(HARK_ERR_UNSUPPORTED, "query_groupby_multi: the group keys' combined value ranges need more than 63 bits");
+    for (int sh = 0, k = (int)ng - 1; k >= 0; k--) {
+        PP.shift[k] = UP.shift[k] = sh;
+        sh += bits[k];
+    }
+    const int cw = total_bits <= 31 ? 4 : 8;
+    const int32_t cdt = cw == 4 ? HARK_I32 : HARK_I64;
+
+    // ---- 2. composite key column ----
+    void *comp = nullptr;
+    HK_TRY(ctx->dalloc(&comp, (size_t)std::max<int64_t>(n, 1) * cw + 256));
+    if (n > 0) {
+        PP.nk = (int)ng;
+        PP.n = n;
+        PP.out = comp;
+        const unsigned g = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n / 4 + 255) / 256, (int64_t)ctx->num_sms * 8));
+        if (cw == 4) hk_pack_keys_kernel<4><<<g, 256, 0, ctx->stream>>>(PP);
+        else hk_pack_keys_kernel<8><<<g, 256, 0, ctx->stream>>>(PP);
+        cudaError_t e = cudaGetLastError();
+        ctx->count_launch();
+        if (e != cudaSuccess) {
+            ctx->dfree(comp);
+            return ctx->fail(HARK_ERR_CUDA, std::string("query_groupby_multi(pack): ") + cudaGetErrorString(e));
+        }
+    }
+
+    // ---- 3. single-key GROUP BY over [composite] ++ the table's columns (borrowed) ----
+    hark_table tmp;
+    tmp.n = n;
+    tmp.cap = n;
+    hark_col cc;
+    cc.ptr = comp;
+    cc.dtype = cdt;
+    cc.owned = false;
+    tmp.cols.push_back(cc);
+    for (const auto &col : db->cols) {
+        hark_col b = col;
+        b.owned = false;
+        tmp.cols.push_back(b);
+    }
+    std::vector<int32_t> sc((size_t)c);
+    for (int64_t j = 0; j < c; j++) sc[j] = s_cols[j] + 1;
+    hark_table *g = nullptr;
+    int rc = hk_groupby(ctx, &g, &tmp, 0, sc.data(), ops, c, nullptr, 0, /*pinned_u32=*/false);
+    ctx->dfree(comp);
+    if (rc != HARK_OK) return rc;
+
+    // ---- 4. typed key columns back out of the group composites; the aggregates move over ----
+    const int64_t G = g->n;
+    std::vector<int32_t> odt;
+    for (int64_t k = 0; k < ng; k++) odt.push_back(db->cols[g_cols[k]].dtype);
+    hark_table *keys = nullptr;
+    rc = hk_table_alloc(ctx, &keys, G, G, odt.data(), ng);
+    if (rc != HARK_OK) {
+        hark_table_free(ctx, g);
+        return rc;
+    }
+    if (G > 0) {
+        UP.nk = (int)ng;
+        UP.comp = g->cols[0].ptr;
+        UP.comp_w = cw;
+        for (int64_t k = 0; k < ng; k++) UP.out[k] = keys->cols[k].ptr;
+        UP.n = G;
+        const unsigned gr = (unsigned)std::max<int64_t>(1, std::min<int64_t>((G + 255) / 256, (int64_t)ctx->num_sms * 8));
+        hk_unpack_keys_kernel<<<gr, 256, 0, ctx->stream>>>(UP);
+        cudaError_t e = cudaGetLastError();
+        ctx->count_launch();
+        if (e != cudaSuccess) {
+            hark_table_free(ctx, g);
+            hark_table_free(ctx, keys);
+            return ctx->fail(HARK_ERR_CUDA, std::string("query_groupby_multi(unpack): ") + cudaGetErrorString(e));
+        }
+    }
+    hark_table *t = keys; // [key_1..key_ng] ++ [agg_1..agg_c]: the aggregate columns change owner, the composite is dropped
+    for (int64_t j = 1; j < (int64_t)g->cols.size(); j++) {
+        t->cols.push_back(g->cols[j]);
+        g->cols[j].owned = false;
+    }
+    t->cap = std::min(t->cap, g->cap);
+    hark_table_free(ctx, g);
+
+    if (nh > 0) { // HAVING over the output columns (K1 on the small group table)
+        std::vector<int32_t> all;
+        for (int64_t j = 0; j < ng + c; j++) all.push_back((int32_t)j);
+        hark_table *f = nullptr;
+        rc = hk_filter(ctx, &f, t, all.data(), ng + c, having, nh);
+        hark_table_free(ctx, t);
+        if (rc != HARK_OK) return rc;
+        t = f;
+    }
+    int64_t alg = 0;
+    std::vector<int> seen((size_t)m, 0);
+    for (int64_t k = 0; k < ng; k++) seen[g_cols[k]] = 1;
+    for (int64_t j = 0; j < c; j++)
+        if (ops[j] != HARK_AGG_COUNT) seen[s_cols[j]] = 1;
+    for (int64_t col = 0; col < m; col++)
+        if (seen[col]) alg += n * hk_dtype_size(db->cols[col].dtype);
+    for (auto &col : t->cols) alg += t->n * hk_dtype_size(col.dtype);
+    ctx->entry_end(alg, n, t->n);
+    *out = t;
+    return HARK_OK;
+}

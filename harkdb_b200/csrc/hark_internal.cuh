@@ -52,6 +52,7 @@ struct hark_ctx {
     bool stats_pending = false; // events recorded, elapsed not yet read
     int64_t total_launches = 0;
     int64_t entry_launches = 0;
+    int entry_depth = 0; // operators call each other (HAVING -> K1, multi-key GROUP BY -> GROUP BY): only the outermost begin/end count
     std::map<std::string, int64_t> opts;
     struct hk_peer_state *peer = nullptr; // K8c: receive arena + the other ranks' arenas (repartition.cu)
 
@@ -74,7 +75,12 @@ struct hark_ctx {
     }
     void entry_begin();                    // reset per-entry stats, record ev_t0
     void entry_end(int64_t alg_bytes, int64_t rows_in, int64_t rows_out);
-    void kernel_begin() { cudaEventRecord(ev_k0, stream); }
+    // kernel_ms spans the entry's first marked kernel to its last (nested operators extend the span, never restart it)
+    bool kernel_marked = false;
+    void kernel_begin() {
+        if (!kernel_marked) cudaEventRecord(ev_k0, stream);
+        kernel_marked = true;
+    }
     void kernel_end() { cudaEventRecord(ev_k1, stream); }
 };
 
@@ -130,6 +136,8 @@ int hk_copy_columns(hark_ctx *ctx, hark_table *dst, const hark_table *src, const
 
 int hk_groupby(hark_ctx *ctx, hark_table **out, const hark_table *db, int32_t g_col, const int32_t *s_cols,
                const int32_t *ops, int64_t c, const hark_pred *having, int64_t nh, bool pinned_u32);
+int hk_groupby_multi(hark_ctx *ctx, hark_table **out, const hark_table *db, const int32_t *g_cols, int64_t ng,
+                     const int32_t *s_cols, const int32_t *ops, int64_t c, const hark_pred *having, int64_t nh);
 int hk_orderby(hark_ctx *ctx, hark_table **out, const hark_table *db, const int32_t *cols, int64_t k,
                const int32_t *key_cols, const int32_t *desc, int64_t nk);
 int hk_join(hark_ctx *ctx, hark_table **out, const hark_table *db1, const hark_table *db2, int32_t col1, int32_t col2,

@@ -104,6 +104,7 @@ int fill_keycols(hark_ctx *ctx, KeyCols &K, const hark_table *db, const int32_t 
 
 #define HK_ENTER(ctx)                \
     if (!(ctx)) return HARK_ERR_ARG; \
+    (ctx)->entry_depth = 0;          \
     HK_CUDA(ctx, cudaSetDevice((ctx)->device))
 
 extern "C" int hark_table_partition_by_splitters(hark_ctx *ctx, hark_table **out, const hark_table *db,

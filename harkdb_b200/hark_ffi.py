@@ -86,6 +86,8 @@ SIGNATURES = {
     "hark_entry_query_filter": (C.c_int, [_P, C.POINTER(_P), _P, _I32P, C.c_int64, C.POINTER(HarkPred), C.c_int64]),
     "hark_entry_query_groupby_ex": (C.c_int, [_P, C.POINTER(_P), _P, C.c_int32, _I32P, _I32P, C.c_int64,
                                               C.POINTER(HarkPred), C.c_int64]),
+    "hark_entry_query_groupby_multi": (C.c_int, [_P, C.POINTER(_P), _P, _I32P, C.c_int64, _I32P, _I32P, C.c_int64,
+                                                 C.POINTER(HarkPred), C.c_int64]),
     "hark_entry_query_orderby": (C.c_int, [_P, C.POINTER(_P), _P, _I32P, C.c_int64, _I32P, _I32P, C.c_int64]),
     "hark_entry_join_groupby": (C.c_int, [_P, C.POINTER(_P), _P, _P, C.c_int32, C.c_int32, C.c_int32, _I32P, _I32P,
                                           C.c_int64]),
@@ -426,6 +428,19 @@ class Futhark:
             h = C.c_void_p()
             self._check(self.lib.hark_entry_query_groupby_ex(self.ctx, C.byref(h), t.handle, int(g_col), _i32p(s),
                                                              _i32p(o), len(s), make_preds(having), len(having)))
+            return DeviceTable(self, h.value)
+        finally:
+            if tmp:
+                t.free()
+
+    def query_groupby_multi(self, db: TableLike, g_cols, s_cols, ops, having=()) -> DeviceTable:
+        """GROUP BY several integer columns: output = the key columns, then one column per aggregate."""
+        t, tmp = self._as_table(db)
+        try:
+            g, s, o = _i32arr(g_cols), _i32arr(s_cols), _i32arr(ops)
+            h = C.c_void_p()
+            self._check(self.lib.hark_entry_query_groupby_multi(self.ctx, C.byref(h), t.handle, _i32p(g), len(g), _i32p(s),
+                                                                _i32p(o), len(s), make_preds(having), len(having)))
             return DeviceTable(self, h.value)
         finally:
             if tmp:

@@ -9,7 +9,7 @@ itself contributes ``(g_col, 0)``, :73-75), and the same exception messages (:33
 Extensions (clauses the reference's README lists but parse.py ignores): ``where``
 (AND / OR / NOT over column-vs-constant comparisons, BETWEEN, IN — handed to libhark in conjunctive
 normal form), ``count``/``avg`` (codes 5, 6), ``having``,
-``orderby``, ``join``, ``limit``, ``select *`` and the single-column select that crashes the
+``orderby``, ``join``, ``limit``, GROUP BY over several columns (``g_cols``), ``select *`` and the single-column select that crashes the
 reference (:48-51 iterates a dict).  They appear as extra plan keys; a plan without them is
 byte-for-byte what the reference would build.
 
@@ -203,7 +203,7 @@ def sql_parse(tables, sql_statement):
     typ_cols_selects = []
     gb = js_obj["groupby"]
     if isinstance(gb, list):
-        raise Exception("GROUP BY over several columns is not supported")
+        return _plan_groupby_multi(js_obj, gb, table_name, table, columns, aliases, extras, orderby)
     g_col_name = _strip_qualifier(gb["value"], aliases)[1]
     g_col = getIndex(columns, g_col_name)
     if g_col < 0:
@@ -259,6 +259,67 @@ def sql_parse(tables, sql_statement):
     extras.pop("aliases", None)
     return {"select": fut_cols_selects, "groupbys": typ_cols_selects, "table": table.get_handle(), "g_col": g_col,
             **extras}
+
+
+def _plan_groupby_multi(js_obj, gb, table_name, table, columns, aliases, extras, orderby):
+    """GROUP BY a, b, ... — the several-columns case the reference leaves as a TODO (parse.py:64).  Plan keys:
+    ``g_cols`` (instead of ``g_col``), ``select`` / ``groupbys`` as in the single-key plan (a selected group column
+    carries code 0).  Output columns of the operator: the group columns, then one column per select item — the
+    single-key layout (key, then the select items) with more keys."""
+    def col_index(name):
+        c = _strip_qualifier(name, aliases)[1]
+        idx = getIndex(columns, c)
+        if idx < 0:
+            raise Exception(f"{c} is not in the schema of table {table_name}")
+        return idx
+
+    g_cols = [col_index(g["value"]) for g in gb]
+    if len(set(g_cols)) != len(g_cols):
+        raise Exception("GROUP BY lists a column twice")
+    ng = len(g_cols)
+    sel, codes, out_names = [], [], []
+    aliases_out = {}
+    select_pairs = _as_list(js_obj["select"]) if js_obj["select"] != "*" else [{"value": columns[g]} for g in g_cols]
+    for dic in select_pairs:
+        val = dic["value"]
+        if isinstance(val, str):
+            idx = col_index(val)
+            if idx not in g_cols:
+                raise Exception(f"{val} is not an aggregation function or the columns thats grouped on")
+            sel.append(idx)
+            codes.append(0)
+            out_names.append(("key", idx))
+        else:
+            for agg_func, agg_val in FUNC_TO_FUT_EXT.items():
+                if agg_func in val:
+                    agg_col = g_cols[0] if val[agg_func] == "*" else col_index(val[agg_func])
+                    sel.append(agg_col)
+                    codes.append(agg_val)
+                    out_names.append((agg_func, agg_col))
+        if "name" in dic and out_names:
+            aliases_out[dic["name"]] = ng + len(out_names) - 1
+
+    def resolve_output(operand):
+        if isinstance(operand, dict):
+            (f, c), = operand.items()
+            c_idx = g_cols[0] if c == "*" else col_index(c)
+            for i, nm in enumerate(out_names):
+                if nm == (f, c_idx):
+                    return ng + i
+            raise Exception(f"{f}({c}) must appear in the select list to be used in HAVING / ORDER BY")
+        c = _strip_qualifier(operand, aliases)[1]
+        if c in aliases_out:
+            return aliases_out[c]
+        idx = getIndex(columns, c)
+        if idx in g_cols:
+            return g_cols.index(idx)
+        raise Exception(f"{c} is not an output column of the GROUP BY")
+
+    if "having" in js_obj:
+        extras["having"] = _preds(js_obj["having"], resolve_output)
+    if orderby:
+        extras["orderby"] = [(resolve_output(k["value"]), 1 if k.get("sort") == "desc" else 0) for k in orderby]
+    return {"select": sel, "groupbys": codes, "table": table.get_handle(), "g_cols": g_cols, **extras}
 
 
 def _plan_join(js_obj, name1, table1, pj, aliases):

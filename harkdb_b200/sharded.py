@@ -534,6 +534,10 @@ class ShardedEnv:
             if tmp:
                 t.free()
 
+    def query_groupby_multi(self, db, g_cols, s_cols, ops, having=()) -> ShardTable:
+        raise NotImplementedError("GROUP BY over several columns is single-GPU for now (DESIGN.md §9): the partial-"
+                                  "aggregate merge repartitions by one key column")
+
     # ---- ORDER BY ----
     def query_orderby(self, db, cols, key_cols, desc=None) -> ShardTable:
         t, tmp = self._as_shard(db)

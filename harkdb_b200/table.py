@@ -11,6 +11,11 @@ error messages are the reference's.  Differences, all invisible in query results
 * integer data is narrowed to the dtype the reference's entries take (i32, else u32, else i64) with a
   range check, because pandas hands the reference int64 (table.py:28) while main.fut's entries are
   i32/u32 (SURVEY.md §8b "dtype hazard").
+* a DataFrame / csv / Arrow table whose columns differ in dtype keeps ONE DTYPE PER COLUMN on the device
+  (``hark_table_from_columns``): integer keys stay integers next to float measures, which the reference's
+  single homogeneous array cannot hold (README.md:8 blames the Futhark compiler).  ``get_data()`` is still the
+  homogeneous 2-D array the reference would have built (``df.to_numpy()``, table.py:9).
+* ``pyarrow.Table`` objects and ``.parquet`` files load column by column.
 """
 
 import numpy as np
@@ -41,7 +46,46 @@ def load_file(file_name, col_names=None):
         else:
             headers = col_names
         return (table, headers)
+    if file_name.endswith(".parquet"):
+        import pyarrow.parquet as pq
+        return load_arrow(pq.read_table(file_name))
     raise Exception("We do not support loading this file type")
+
+
+def load_arrow(tbl):
+    """pyarrow.Table -> (homogeneous values, headers), like load_df on the equivalent DataFrame."""
+    cols = arrow_columns(tbl)
+    values = np.column_stack(cols) if cols else np.zeros((tbl.num_rows, 0))
+    return values, [str(nm).strip() for nm in tbl.column_names]
+
+
+def arrow_columns(tbl):
+    cols = []
+    for i in range(tbl.num_columns):
+        c = tbl.column(i)
+        if c.null_count:
+            raise Exception(f"column {tbl.column_names[i]} holds nulls; tables are dense numeric arrays")
+        cols.append(np.ascontiguousarray(c.to_numpy()))
+    return cols
+
+
+def _is_arrow(obj):
+    return type(obj).__module__.startswith("pyarrow") and hasattr(obj, "column_names") and hasattr(obj, "num_rows")
+
+
+def source_columns(table):
+    """Per-column host arrays of a source that has them (DataFrame, csv, Arrow, parquet), else None."""
+    if isinstance(table, pd.DataFrame):
+        return [np.ascontiguousarray(table[c].to_numpy()) for c in table.columns]
+    if _is_arrow(table):
+        return arrow_columns(table)
+    if isinstance(table, str) and table[-3:] == "csv":
+        df = pd.read_csv(table)
+        return [np.ascontiguousarray(df[c].to_numpy()) for c in df.columns]
+    if isinstance(table, str) and table.endswith(".parquet"):
+        import pyarrow.parquet as pq
+        return arrow_columns(pq.read_table(table))
+    return None
 
 
 def load_table(table_name, table):
@@ -51,6 +95,8 @@ def load_table(table_name, table):
         return load_np(table)
     elif isinstance(table, str):
         return load_file(table)
+    elif _is_arrow(table):
+        return load_arrow(table)
     else:
         raise Exception("Table is not in a file, numpy array or dataframe")
 
@@ -83,6 +129,14 @@ class Table:
         self._schema = list(headers)
         self._data = table
         self._device = None
+        # one dtype per column when the source has them and they differ (else the homogeneous array is the table)
+        self._columns = None
+        cols = source_columns(file_name)
+        if cols is not None and len(cols) == table.shape[1] and len({c.dtype for c in cols}) > 1:
+            for c, h in zip(cols, self._schema):
+                if c.dtype.kind not in "iubf":
+                    raise Exception(f"column {h} has dtype {c.dtype}; tables are numeric")
+            self._columns = cols
 
     def get_schema(self):
         return self._schema
@@ -97,8 +151,17 @@ class Table:
     def upload(self, env):
         """Transpose to device SoA once; later queries use the resident handle."""
         if self._device is None:
-            self._device = env.to_device(self._data, entry_dtype(self._data))
+            if self._columns is not None:
+                self._device = env.from_columns([c.astype(entry_dtype(c), copy=False) for c in self._columns])
+            else:
+                self._device = env.to_device(self._data, entry_dtype(self._data))
         return self._device
+
+    def get_column_dtypes(self):
+        """Device dtype of every column (what ``upload`` stores)."""
+        if self._columns is not None:
+            return [entry_dtype(c) for c in self._columns]
+        return [entry_dtype(self._data)] * self._data.shape[1]
 
     def get_handle(self):
         """Resident device table if uploaded, else the host array (uploaded per query like the reference)."""

@@ -170,6 +170,13 @@ int hark_entry_query_filter(hark_ctx *ctx, hark_table **out, const hark_table *d
 int hark_entry_query_groupby_ex(hark_ctx *ctx, hark_table **out, const hark_table *db, int32_t g_col,
                                 const int32_t *s_cols, const int32_t *ops, int64_t c, const hark_pred *having,
                                 int64_t nh);
+/* GROUP BY several integer key columns — what parse.py:64 ("TODO: allow to be several columns") asks for.  Output
+ * columns: the ng keys in g_cols order, then the c aggregates (codes and types as hark_entry_query_groupby_ex);
+ * rows ascending lexicographically by the keys, each in its own signedness.  HAVING indexes the output columns.
+ * The keys' combined value ranges (max - min per key) must fit 63 bits, else HARK_ERR_UNSUPPORTED.              */
+int hark_entry_query_groupby_multi(hark_ctx *ctx, hark_table **out, const hark_table *db, const int32_t *g_cols,
+                                   int64_t ng, const int32_t *s_cols, const int32_t *ops, int64_t c,
+                                   const hark_pred *having, int64_t nh);
 /* SELECT cols ORDER BY key_cols[0] [DESC], key_cols[1] ... ; stable w.r.t. input row order;
  * signed order for i32/i64, IEEE total order with NaN last for f32/f64.                       */
 int hark_entry_query_orderby(hark_ctx *ctx, hark_table **out, const hark_table *db, const int32_t *cols, int64_t k,

@@ -227,7 +227,7 @@ def test_filter_errors():
     with pytest.raises(HarkError):
         env.query_filter(t, [0], [(0, 9, 0, 0.0)])
     with pytest.raises(HarkError):
-        env.query_filter(t, [0], [(0, NO.GT, 0, 0.0)] * 9)
+        env.query_filter(t, [0], [(0, NO.GT, 0, 0.0)] * 17)
     t.free()
 
 

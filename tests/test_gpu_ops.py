@@ -158,6 +158,58 @@ def test_groupby_ex_sizes_and_single_group(gb_impl, n):
     r.free(); t.free()
 
 
+# ---------------------------------------------------------------- GROUP BY over several key columns
+@pytest.mark.parametrize("n", [0, 1, 5, 4097, 200003])
+def test_groupby_multi_vs_oracle(gb_impl, n):
+    env = get_env()
+    rng = np.random.default_rng(31 + n)
+    cols = [rng.integers(-3, 4, n).astype(np.int32), rng.integers(10 ** 12, 10 ** 12 + 40, n).astype(np.int64),
+            rng.integers(0, 3, n).astype(np.uint32), rng.integers(-1000, 1000, n).astype(np.int32),
+            rng.random(n).astype(np.float32), rng.random(n)]
+    t = env.from_columns(cols)
+    ops = [NO.AGG_SUM, NO.AGG_COUNT, NO.AGG_AVG, NO.AGG_MIN, NO.AGG_MAX, NO.AGG_SUM, NO.AGG_KEY]
+    s_cols = [3, 3, 4, 3, 5, 4, 0]
+    for g_cols in ([0, 1, 2], [2, 0], [1, 0]):
+        r = env.query_groupby_multi(t, g_cols, s_cols, ops)
+        _check_cols(r.columns(), NO.query_groupby_multi(cols, g_cols, s_cols, ops))
+        assert r.dtypes[:len(g_cols)] == [t.dtypes[g] for g in g_cols]
+        r.free()
+    having = [(2, NO.GT | NO.PRED_OR, 0, 0.0), (3, NO.GE, 3, 3.0)]          # SUM > 0 OR COUNT >= 3 (output columns)
+    r = env.query_groupby_multi(t, [0, 2], [3, 3], [NO.AGG_SUM, NO.AGG_COUNT], having)
+    _check_cols(r.columns(), NO.query_groupby_multi(cols, [0, 2], [3, 3], [NO.AGG_SUM, NO.AGG_COUNT], having))
+    r.free()
+    r = env.query_groupby_multi(t, [1], [3], [NO.AGG_MAX])                   # one key: the single-key operator
+    _check_cols(r.columns(), NO.query_groupby_ex(cols, 1, [3], [NO.AGG_MAX]))
+    r.free(); t.free()
+
+
+def test_groupby_multi_wide_composite_and_errors(gb_impl):
+    env = get_env()
+    from harkdb_b200.hark_ffi import HarkError
+    rng = np.random.default_rng(77)
+    n = 150001
+    # 20 + 30 + 12 = 62 bits of combined range: an i64 composite, sorted (too wide for the dense tables)
+    cols = [rng.integers(0, 1 << 20, n).astype(np.uint32), rng.integers(-(1 << 29), 1 << 29, n).astype(np.int64) // 977 * 977,
+            rng.integers(-2048, 2048, n).astype(np.int32), rng.integers(0, 10, n).astype(np.int32)]
+    cols[0][: n // 2] = cols[0][n // 2: 2 * (n // 2)]        # make groups of more than one row
+    cols[1][: n // 2] = cols[1][n // 2: 2 * (n // 2)]
+    cols[2][: n // 2] = cols[2][n // 2: 2 * (n // 2)]
+    t = env.from_columns(cols)
+    r = env.query_groupby_multi(t, [0, 1, 2], [3, 3], [NO.AGG_SUM, NO.AGG_COUNT])
+    _check_cols(r.columns(), NO.query_groupby_multi(cols, [0, 1, 2], [3, 3], [NO.AGG_SUM, NO.AGG_COUNT]))
+    r.free(); t.free()
+    wide = [rng.integers(-2 ** 62, 2 ** 62, 1000, dtype=np.int64), rng.integers(0, 4, 1000).astype(np.int32),
+            rng.random(1000)]
+    t = env.from_columns(wide)
+    with pytest.raises(HarkError, match="more than 63 bits"):
+        env.query_groupby_multi(t, [0, 1], [1], [NO.AGG_COUNT])
+    with pytest.raises(HarkError, match="integer columns"):
+        env.query_groupby_multi(t, [1, 2], [1], [NO.AGG_COUNT])
+    with pytest.raises(HarkError, match="out of bounds"):
+        env.query_groupby_multi(t, [1, 3], [1], [NO.AGG_COUNT])
+    t.free()
+
+
 # ---------------------------------------------------------------- ORDER BY
 @pytest.mark.parametrize("dtype", [NO.I32, NO.U32, NO.I64, NO.F32, NO.F64])
 @pytest.mark.parametrize("n", [0] + SIZES)

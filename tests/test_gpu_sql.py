@@ -78,7 +78,7 @@ def test_where_or_not_between_in(fc):
     for k in sorted(set(a[m][:, 0].tolist()), reverse=True):
         v = a[m][a[m][:, 0] == k][:, 1]
         if len(v) > 1 or v.sum() >= 2:
-            exp.append([k, int(v.sum()), len(v)])
+            exp.append([k, k, int(v.sum()), len(v)])      # reference shape: key column, then one column per select item
     assert out.tolist() == exp
 
 
@@ -94,6 +94,33 @@ def test_where_or_float_table_nan():
     with np.errstate(invalid="ignore"):
         m = ((a[:, 0] < np.float32(0.25)) | ~(a[:, 1] > np.float32(0.5))) & (a[:, 2] >= np.float32(0.1)) & (a[:, 2] <= np.float32(0.9))
     assert np.array_equal(out, a[m][:, [0, 3]])
+
+
+def test_tpch_q1_shape_mixed_dtypes_group_by_two_columns():
+    """TPC-H Q1's shape on a frame with integer keys next to float measures: per-column dtypes at create_table,
+    WHERE, GROUP BY two columns, SUM / AVG / COUNT, HAVING, ORDER BY."""
+    need_gpu()
+    from harkdb_b200 import FutharkContext
+    rng = np.random.default_rng(19)
+    n = 300007
+    df = pd.DataFrame({"flag": rng.integers(0, 3, n), "status": rng.integers(0, 2, n), "qty": rng.integers(1, 51, n),
+                       "price": rng.random(n) * 1000, "shipdate": rng.integers(8000, 10600, n)})
+    ctx = FutharkContext()
+    ctx.create_table("lineitem", df)
+    assert ctx.tables["lineitem"].get_handle().dtypes == [NO.I32, NO.I32, NO.I32, NO.F64, NO.I32]
+    out = ctx.sql("select flag, status, sum(qty), avg(price), count(*) from lineitem where shipdate <= 10471 "
+                  "group by flag, status having count(*) > 10 order by flag desc, status")
+    g = df[df.shipdate <= 10471].groupby(["flag", "status"], sort=True).agg(q=("qty", "sum"), p=("price", "mean"),
+                                                                            c=("qty", "size")).reset_index()
+    g = g[g.c > 10].sort_values(["flag", "status"], ascending=[False, True], kind="stable")
+    assert out.shape == (len(g), 7)                       # 2 key columns + the 5 select items
+    assert np.array_equal(out[:, 0], g.flag) and np.array_equal(out[:, 1], g.status)
+    assert np.array_equal(out[:, 2], g.flag) and np.array_equal(out[:, 3], g.status)
+    assert np.array_equal(out[:, 4], g.q) and np.allclose(out[:, 5], g.p, rtol=1e-12) and np.array_equal(out[:, 6], g.c)
+    # single key on the same frame: integer key, float measure
+    out = ctx.sql("select flag, max(price) from lineitem group by flag")
+    gm = df.groupby("flag", sort=True).price.max()
+    assert np.array_equal(out[:, 0], gm.index) and np.array_equal(out[:, 2], gm.to_numpy())
 
 
 def test_where_float_table():
