@@ -270,16 +270,31 @@ def run_gpu_arm(args):
             head.to_numpy(out=host_in)               # fill the pinned host table from the device generator
             head.free()
 
+            phases = []
+
             def e2e_step():
+                ta = time.perf_counter()
                 r = env.query_filter(host_in, SEL_COLS, PREDS)    # H2D + transpose + filter
                 k = r.shape[0]
+                tb = time.perf_counter()
                 r.to_numpy(out=host_out[:k])                      # D2H of the result
                 r.free()
+                phases.append((round((tb - ta) * 1e3, 1), round((time.perf_counter() - tb) * 1e3, 1)))
                 return k
 
             for _ in range(args.e2e_warmup):
                 k = e2e_step()
+            # a fresh box keeps paging its image in for a while and the first uploads see 2-4x the steady step time:
+            # keep warming (bounded) until two consecutive steps are within 10 % of the best one seen
+            extra = 0
+            while extra < 12:
+                best = min(a + b for a, b in phases)
+                if len(phases) >= 2 and all(a + b <= 1.1 * best for a, b in phases[-2:]):
+                    break
+                k = e2e_step()
+                extra += 1
             barrier()
+            del phases[:]
             t0 = time.perf_counter()
             for _ in range(args.e2e_steps):
                 k = e2e_step()
@@ -291,7 +306,8 @@ def run_gpu_arm(args):
                 dt = float(tm.item())
             e2e = {"value": world * e2e_rows * args.e2e_steps / dt, "unit": "rows/s",
                    "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": int(k) * 8, "rows_per_step": e2e_rows,
-                   "steps": args.e2e_steps, "warmup": args.e2e_warmup, "ms_per_step": 1e3 * dt / args.e2e_steps,
+                   "steps": args.e2e_steps, "warmup": args.e2e_warmup + extra, "ms_per_step": 1e3 * dt / args.e2e_steps,
+                   "step_phases_ms[upload+filter, download]": list(phases),
                    "path": "pinned host row-major table -> hark_table_from_host (H2D + transpose) -> "
                            "hark_entry_query_filter -> hark_table_to_host (D2H), all inside the timed step"}
             # and the product's default (resident table, only the result crosses PCIe)
@@ -367,7 +383,7 @@ def main():
     ap.add_argument("--rows", type=int, default=10 ** 9, help="rows per GPU")
     ap.add_argument("--cpu-rows", type=int, default=1 << 26, help="rows of the bounded CPU sample")
     ap.add_argument("--e2e-rows", type=int, default=1 << 28)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-warmup", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
