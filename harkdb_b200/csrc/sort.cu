@@ -494,7 +494,26 @@ __device__ __forceinline__ void lsd_write_out_peer(const unsigned long long *s_p
     }
 }
 
-// RANK: 0 = match.any, 1 = eight ballots (register-only multisplit).  PEER: outputs go to per-digit base addresses
+// One step of the ballot multisplit: peers &= lanes whose digit agrees with mine in the bit `bitmask`.
+// peers & ~(ballot ^ m), m = all-ones when my bit is set: one LOP3 (LUT 0x90) after the vote.
+__device__ __forceinline__ uint32_t hk_ballot_step(uint32_t peers, uint32_t d, uint32_t bitmask) {
+    uint32_t out;
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        " .reg .b32 b, m, t;\n"
+        " and.b32 t, %2, %3;\n"
+        " setp.ne.u32 p, t, 0;\n"
+        " vote.sync.ballot.b32 b, p, 0xffffffff;\n"
+        " selp.b32 m, 0xffffffff, 0, p;\n"
+        " lop3.b32 %0, %1, b, m, 0x90;\n"
+        "}\n"
+        : "=r"(out)
+        : "r"(peers), "r"(d), "r"(bitmask));
+    return out;
+}
+
+// RANK: 0 = match.any, 1 = eight ballots (register-only multisplit), 2 = lean ballots (default).  PEER: outputs go to per-digit base addresses
 // (other GPUs' arenas) and the key array itself (the destination digit) is not written anywhere.
 template <int KW, int RANK, bool PEER = false>
 __global__ void __launch_bounds__(LT, 2) hk_lsd_scatter_kernel(const __grid_constant__ LsdParams P) {
@@ -536,6 +555,55 @@ __global__ void __launch_bounds__(LT, 2) hk_lsd_scatter_kernel(const __grid_cons
         // (issuing the 8 counter updates as back-to-back atomics and reading the results after the loop was tried:
         //  the extra live registers spill under the 64-register cap and the pass got 7 % slower)
         uint32_t rank[LI];
+        if constexpr (RANK == 2) {
+            // lean variant of the ballot ranking (ncu: the ranking loop was 55 % of the kernel's instructions): digits
+            // are extracted once with the pass constants in registers, a ballot step is 4 SASS instructions (bit test,
+            // vote, select, one LOP3), the highest peer lane leads (FLO, no BREV), full tiles skip the validity votes
+            uint32_t dpk[LI / 4];
+            if (P.f.fast == 1) {
+                const KT xm = (KT)P.f.xmask, base = (KT)P.f.base;
+                const int sh = P.f.shift;
+                const uint32_t mk = P.f.mask;
+#pragma unroll
+                for (int i = 0; i < LI; i++) {
+                    const uint32_t d = (uint32_t)(((key[i] ^ xm) - base) >> sh) & mk;
+                    if ((i & 3) == 0) dpk[i >> 2] = d;
+                    else dpk[i >> 2] |= d << ((i & 3) * 8);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < LI; i++) {
+                    const uint32_t d = digit_of<KW>(key[i], P.f) & 0xffu;
+                    if ((i & 3) == 0) dpk[i >> 2] = d;
+                    else dpk[i >> 2] |= d << ((i & 3) * 8);
+                }
+            }
+            const bool full = cur_count == LTILE;
+            uint32_t *whw = &wh[warp][0];
+#pragma unroll
+            for (int i = 0; i < LI; i++) {
+                const int idx = warp * (LI * 32) + i * 32 + lane;
+                const uint32_t d = (dpk[i >> 2] >> ((i & 3) * 8)) & 0xffu;
+                bool valid = true;
+                uint32_t peers = 0xffffffffu;
+                if (!full) {
+                    valid = idx < cur_count;
+                    peers = __ballot_sync(HK_FULL_MASK, valid);
+                    if (!valid) peers = ~peers;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) peers = hk_ballot_step(peers, d, 1u << k);
+                const int leader = 31 - __clz((int)peers);
+                uint32_t old = 0;
+                if (valid && lane == leader) {
+                    old = whw[d];
+                    whw[d] = old + __popc(peers);
+                }
+                old = __shfl_sync(HK_FULL_MASK, old, leader);
+                rank[i] = (valid ? (d << 16) : 0xffff0000u) | (old + __popc(peers & lt_mask));
+                __syncwarp();
+            }
+        } else {
 #pragma unroll
         for (int i = 0; i < LI; i++) {
             const int idx = warp * (LI * 32) + i * 32 + lane;
@@ -562,6 +630,7 @@ __global__ void __launch_bounds__(LT, 2) hk_lsd_scatter_kernel(const __grid_cons
             old = __shfl_sync(HK_FULL_MASK, old, leader);
             rank[i] = (valid ? (d << 16) : 0xffff0000u) | (old + __popc(peers & lt_mask));
             __syncwarp();
+        }
         }
         __syncthreads();
         // ---- thread b owns bin b: offsets of the warps inside the bin, bin start inside the tile, global base ----
@@ -639,10 +708,11 @@ int lsd_pass(hark_ctx *ctx, LsdParams &P, int kw, unsigned long long **d_offsets
     P.num_tiles = (P.n + LTILE - 1) / LTILE;
     const size_t smem = (size_t)LTILE * 8;
     int occ = 1;
-    const bool ballots = ctx->opt("sort.rank", 1) == 1;
-    void (*scatter)(const LsdParams) = kw == 4 ? (ballots ? hk_lsd_scatter_kernel<4, 1> : hk_lsd_scatter_kernel<4, 0>)
-                                               : (ballots ? hk_lsd_scatter_kernel<8, 1> : hk_lsd_scatter_kernel<8, 0>);
-    if (P.peer_out) scatter = hk_lsd_scatter_kernel<4, 1, true>; // the key is the 4-byte destination digit
+    const int64_t rk = ctx->opt("sort.rank", 2);
+    void (*scatter)(const LsdParams) =
+        kw == 4 ? (rk == 2 ? hk_lsd_scatter_kernel<4, 2> : rk == 1 ? hk_lsd_scatter_kernel<4, 1> : hk_lsd_scatter_kernel<4, 0>)
+                : (rk == 2 ? hk_lsd_scatter_kernel<8, 2> : rk == 1 ? hk_lsd_scatter_kernel<8, 1> : hk_lsd_scatter_kernel<8, 0>);
+    if (P.peer_out) scatter = rk == 2 ? hk_lsd_scatter_kernel<4, 2, true> : hk_lsd_scatter_kernel<4, 1, true>; // the key is the 4-byte destination digit
     cudaError_t e = cudaFuncSetAttribute(scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scatter, LT, smem);
     if (e != cudaSuccess) return ctx->fail(HARK_ERR_CUDA, std::string("sort(pass setup): ") + cudaGetErrorString(e));
