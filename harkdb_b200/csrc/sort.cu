@@ -1035,7 +1035,7 @@ int plan_truncation(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec>
     out->on = false;
     int total_bits = 0;
     for (int k = 0; k < nk; k++) total_bits += ranges[k].bits;
-    const int slack = (int)std::max<int64_t>(0, ctx->opt("sort.trunc_slack", 5));
+    const int slack = (int)std::max<int64_t>(0, ctx->opt("sort.trunc_slack", 4));
     int T = bit_width_u64((uint64_t)(n - 1)) + slack;
     if (T + 8 > total_bits) return HARK_OK; // nothing to save
     // ---- sample, sorted by the full tuple; per adjacent pair: first differing key and its highest differing bit ----

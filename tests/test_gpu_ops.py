@@ -307,7 +307,7 @@ def test_orderby_truncated_passes_repair_short_runs():
         info = _check_orderby(env, [k1, k2, payload], [2], [0], [1])
         assert info["truncated"] == 1 and info["fallback"] == 0, info
     finally:
-        env.set_option("sort.trunc_slack", 5)
+        env.set_option("sort.trunc_slack", 4)
     env.set_option("sort.trunc", 0)
     try:
         info = _check_orderby(env, [k1, k2, payload], [2, 0, 1], [0, 1], [0, 1])

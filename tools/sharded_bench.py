@@ -52,9 +52,19 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    all_ms = []
+
     def timed(fn):
-        best, keep = None, None
+        """Two untimed warm-ups (kernel loading, memory-pool growth, IPC arena set-up), then `reps` timed runs.  Every
+        result but the last is freed before the next run: a kept result makes the pool grow again inside the timed
+        run (the first cut of this tool kept the best one and reported 2x the steady-state time at 8 GPUs)."""
+        del all_ms[:]
+        for _ in range(2):
+            fn().free()
+        best, r = None, None
         for _ in range(args.reps):
+            if r is not None:
+                r.free()
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -66,13 +76,9 @@ def main():
                 t = torch.tensor([ms], device="cuda", dtype=torch.float64)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 ms = float(t.item())
-            if best is None or ms < best:
-                if keep is not None:
-                    keep.free()
-                best, keep = ms, r
-            else:
-                r.free()
-        return best, keep
+            all_ms.append(round(ms, 2))
+            best = ms if best is None else min(best, ms)
+        return best, r
 
     def allsum(x):
         t = torch.tensor([int(x)], device="cuda", dtype=torch.int64)
@@ -94,7 +100,7 @@ def main():
     results = []
 
     def emit(d):
-        d.update(n_gpus=world, scaling="strong" if args.strong else "weak")
+        d.update(n_gpus=world, scaling="strong" if args.strong else "weak", ms_all_reps=list(all_ms))
         if senv.trace_on:      # HARK_SHARD_TRACE=1: phase times include a device sync each, so they sum to more than `ms`
             d["trace_ms_rank0"] = {k: round(v / (args.reps + 0), 3) for k, v in senv.pop_trace().items()}
         results.append(d)
@@ -143,7 +149,8 @@ def main():
             imb = a.shape[0] / max(per, 1)
             emit({"op": "orderby_cfg4", "rows_total": total, "rows_per_gpu": per, "ms": ms, "rows_per_s": total / (ms * 1e-3),
                   "check_ok": bool(n_out == total and s_in == s_out and allsum(int(srt)) == world),
-                  "rank0_load_vs_even": imb, "nvlink_bytes_per_gpu": int(per * 16 * (world - 1) / world)})
+                  "rank0_load_vs_even": imb, "nvlink_bytes_per_gpu": int(per * 16 * (world - 1) / world),
+                  "sort_rank0": {k: env.get_option("sort.last_" + k) for k in ("passes", "truncated", "fix_runs", "fallback")}})
             del a, b
             r.free(); t.free()
         elif op == "join":
