@@ -338,6 +338,13 @@ class ShardedEnv:
             arr = convert_for_entry(arr, dtype, "table")     # range check on the whole table, like one GPU
         return self._wrap(self.engine.to_device(np.ascontiguousarray(arr[lo:hi]), None))
 
+    def from_columns(self, cols) -> ShardTable:
+        """Every rank passes the SAME host columns (one dtype each); rank r keeps rows [r*n/W, (r+1)*n/W)."""
+        cols = [np.asarray(c) for c in cols]
+        n = len(cols[0]) if cols else 0
+        lo, hi = self.rank * n // self.world, (self.rank + 1) * n // self.world
+        return self._wrap(self.engine.from_columns([np.ascontiguousarray(c[lo:hi]) for c in cols]))
+
     def all_counts(self, n_local: int) -> List[int]:
         if self.world == 1:
             return [n_local]
@@ -535,8 +542,42 @@ class ShardedEnv:
                 t.free()
 
     def query_groupby_multi(self, db, g_cols, s_cols, ops, having=()) -> ShardTable:
-        raise NotImplementedError("GROUP BY over several columns is single-GPU for now (DESIGN.md §9): the partial-"
-                                  "aggregate merge repartitions by one key column")
+        """GROUP BY over several key columns.  Shard-local partial aggregation by the key tuple, range repartition of
+        the partial groups by sampled TUPLE splitters (the ORDER BY exchange: equal tuples land on one rank), merge
+        with the same multi-key operator, finalize.  Rank order = lexicographic key order."""
+        g_cols = [int(g) for g in g_cols]
+        if len(g_cols) == 1:
+            return self.query_groupby_ex(db, g_cols[0], s_cols, ops, having)
+        if len(g_cols) > 4 and self.world > 1:
+            raise NotImplementedError("the splitter exchange compares tuples of at most 4 key columns")
+        t, tmp = self._as_shard(db)
+        try:
+            eng, ng = self.engine, len(g_cols)
+            ops = [int(x) for x in ops]
+            p_s, p_ops = expand_partial_ops([int(x) for x in s_cols], ops)
+            with self.phase("local"):
+                part = eng.query_groupby_multi(t.local, g_cols, p_s, p_ops)        # [key_1..key_ng, partials...]
+            if self.world > 1:
+                recv = self.repartition(part, list(range(ng)), [0] * ng)
+                part.free()
+                m = recv.shape[1]
+                with self.phase("merge"):
+                    merged = eng.query_groupby_multi(recv, list(range(ng)), list(range(ng, m)), merge_ops_for(p_ops))
+                recv.free()
+            else:
+                merged = part
+            with self.phase("finalize"):
+                # groupby_finalize passes non-AVG columns through: the keys after the first ride along as such
+                final = eng.groupby_finalize(merged, [AGG_MIN] * (ng - 1) + final_ops_for(ops))
+                merged.free()
+                if having:
+                    f2 = eng.query_filter(final, list(range(final.shape[1])), list(having))
+                    final.free()
+                    final = f2
+            return self._wrap(final)
+        finally:
+            if tmp:
+                t.free()
 
     # ---- ORDER BY ----
     def query_orderby(self, db, cols, key_cols, desc=None) -> ShardTable:

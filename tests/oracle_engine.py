@@ -84,6 +84,10 @@ class OracleEngine:
     def query_groupby_ex(self, t, g_col, s_cols, ops, having=()):
         return OTable(NO.query_groupby_ex(t.cols, int(g_col), [int(x) for x in s_cols], [int(x) for x in ops], list(having)))
 
+    def query_groupby_multi(self, t, g_cols, s_cols, ops, having=()):
+        return OTable(NO.query_groupby_multi(t.cols, [int(g) for g in g_cols], [int(x) for x in s_cols],
+                                             [int(x) for x in ops], list(having)))
+
     def groupby_finalize(self, t, ops):
         out, col = [t.cols[0]], 1
         for op in ops:

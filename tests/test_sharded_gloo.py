@@ -114,6 +114,33 @@ def _scn_groupby(senv):
         _check(senv.gather_columns(r), NO.query_groupby_ex(cols, 0, s_cols, ops, having=hv), "groupby having")
 
 
+def _scn_groupby_multi(senv):
+    rng = np.random.default_rng(8)
+    n = 15013
+    cols = [rng.integers(-3, 4, n).astype(np.int32), rng.integers(10 ** 12, 10 ** 12 + 9, n).astype(np.int64),
+            rng.integers(0, 3, n).astype(np.uint32), rng.integers(-100, 100, n).astype(np.int32), rng.random(n)]
+    t = _shard(senv, cols)
+    ops = [NO.AGG_SUM, NO.AGG_AVG, NO.AGG_COUNT, NO.AGG_MIN, NO.AGG_MAX, NO.AGG_KEY]
+    s_cols = [3, 4, 3, 3, 4, 0]
+    for g_cols in ([0, 1, 2], [2, 0], [1]):
+        r = senv.query_groupby_multi(t, g_cols, s_cols, ops)
+        exp = NO.query_groupby_multi(cols, g_cols, s_cols, ops) if len(g_cols) > 1 else NO.query_groupby_ex(cols, g_cols[0], s_cols, ops)
+        _check(senv.gather_columns(r), exp, f"groupby_multi {g_cols}")
+    hv = [(3, NO.GT | NO.PRED_OR, 40, 40.0), (5, NO.GE, 120, 120.0)]           # SUM > 40 OR COUNT >= 120
+    r = senv.query_groupby_multi(t, [0, 2], s_cols, ops, having=hv)
+    _check(senv.gather_columns(r), NO.query_groupby_multi(cols, [0, 2], s_cols, ops, having=hv), "groupby_multi having")
+    import pandas as pd
+    from harkdb_b200.sharded import ShardedFutharkContext
+    fc = ShardedFutharkContext(engine=senv.engine)
+    df = pd.DataFrame({"a": cols[0], "c": cols[2].astype(np.int64), "v": cols[3], "f": cols[4]})
+    fc.create_table("t", df)
+    out = fc.sql("select a, c, sum(v), avg(f) from t where v > -50 group by a, c order by a desc, c")
+    g = df[df.v > -50].groupby(["a", "c"], sort=True).agg(s=("v", "sum"), m=("f", "mean")).reset_index()
+    g = g.sort_values(["a", "c"], ascending=[False, True], kind="stable")
+    assert np.array_equal(out[:, 0], g.a) and np.array_equal(out[:, 1], g.c) and np.array_equal(out[:, 4], g.s)
+    assert np.allclose(out[:, 5], g.m, rtol=1e-12)
+
+
 def _scn_groupby_pinned(senv):
     rng = np.random.default_rng(3)
     db = rng.integers(0, 2 ** 32, (6007, 4), dtype=np.uint64).astype(np.uint32)
@@ -170,13 +197,14 @@ def _scn_sql(senv):
 
 
 # ------------------------------------------------------------------ tests
-@pytest.mark.parametrize("scenario", ["filter", "groupby", "groupby_pinned", "orderby", "join", "sql"])
+@pytest.mark.parametrize("scenario", ["filter", "groupby", "groupby_multi", "groupby_pinned", "orderby", "join", "sql"])
 def test_sharded_world2(scenario):
     _run(scenario, 2)
 
 
 def test_sharded_world3_uneven_shards():
     _run("groupby", 3)
+    _run("groupby_multi", 3)
     _run("orderby", 3)
 
 
