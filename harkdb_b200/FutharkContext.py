@@ -141,29 +141,63 @@ class FutharkContext:
                 res = env.query_groupby_ex(cur, g_cols[0], s_cols, ops)
             if cur_tmp:
                 cur.free()
-            if "having" in plan:
-                dts = res.dtypes
-                hv = [finalize_pred(p, dts[p[0]] in (I32, U32, I64)) for p in plan["having"]]
-                nxt = env.query_filter(res, list(range(len(dts))), hv)
-                res.free()
-                res = nxt
-            if "orderby" in plan:
-                m = res.shape[1]
-                nxt = env.query_orderby(res, list(range(m)), [k for k, _ in plan["orderby"]],
-                                        [d for _, d in plan["orderby"]])
-                res.free()
-                res = nxt
-            return self._finish(res, plan.get("limit"))
+            return self._post(res, plan)
         finally:
             if tmp:
                 t.free()
 
+    def _post(self, res, plan):
+        """HAVING, ORDER BY and LIMIT over an operator's result table (consumed)."""
+        env = self.FutEnv
+        if "having" in plan:
+            dts = res.dtypes
+            hv = [finalize_pred(p, dts[p[0]] in (I32, U32, I64)) for p in plan["having"]]
+            nxt = env.query_filter(res, list(range(len(dts))), hv)
+            res.free()
+            res = nxt
+        if "orderby" in plan:
+            m = res.shape[1]
+            nxt = env.query_orderby(res, list(range(m)), [k for k, _ in plan["orderby"]], [d for _, d in plan["orderby"]])
+            res.free()
+            res = nxt
+        return self._finish(res, plan.get("limit"))
+
+    def _pushed_down(self, t, preds, used):
+        """WHERE clauses of one joined table, applied before the join.  Returns (table, temporary?, column map):
+        only the columns the join still needs survive the filter, `column map` translates the plan's indices."""
+        if not preds:
+            return t, False, {c: c for c in used}
+        need = list(dict.fromkeys(used))
+        fp = [finalize_pred(p, self._is_int_col(t, p[0])) for p in preds]
+        return self.FutEnv.query_filter(t, need, fp), True, {c: i for i, c in enumerate(need)}
+
     def _sql_join(self, plan):
         env = self.FutEnv
         col1, col2 = plan["join"]
-        if "groupbys" in plan:
-            res = env.join_groupby(plan["table"], plan["table2"], col1, col2, plan["g_col"], plan["select"],
-                                   plan["groupbys"])
-        else:
-            res = env.join(plan["table"], plan["table2"], col1, col2, plan["select"], plan["select2"])
-        return self._finish(res, plan.get("limit"))
+        t1, tmp1 = self._as_device(plan["table"])
+        t2, tmp2 = self._as_device(plan["table2"])
+        f1 = f2 = None
+        try:
+            grouped = "groupbys" in plan
+            used1 = [col1] + list(plan["select"])
+            used2 = [col2] + ([plan["g_col"]] if grouped else list(plan["select2"]))
+            f1, ftmp1, m1 = self._pushed_down(t1, plan.get("where"), used1)
+            f2, ftmp2, m2 = self._pushed_down(t2, plan.get("where2"), used2)
+            try:
+                if grouped:
+                    res = env.join_groupby(f1, f2, m1[col1], m2[col2], m2[plan["g_col"]], [m1[c] for c in plan["select"]],
+                                           plan["groupbys"])
+                else:
+                    res = env.join(f1, f2, m1[col1], m2[col2], [m1[c] for c in plan["select"]],
+                                   [m2[c] for c in plan["select2"]])
+            finally:
+                if ftmp1:
+                    f1.free()
+                if ftmp2:
+                    f2.free()
+            return self._post(res, plan)
+        finally:
+            if tmp1:
+                t1.free()
+            if tmp2:
+                t2.free()

@@ -350,19 +350,47 @@ def _plan_join(js_obj, name1, table1, pj, aliases):
     if not (ta == name1 and tb == name2):
         raise Exception("JOIN condition must compare one column of each table")
     plan = {"table": table1.get_handle(), "table2": table2.get_handle(), "join": (ca, cb)}
-    for key in ("where", "having", "orderby"):
-        if key in js_obj:
-            raise Exception(f"{key.upper()} together with JOIN is not supported")
+    if "limit" in js_obj:
+        plan["limit"] = int(js_obj["limit"])
+    orderby = _as_list(js_obj["orderby"]) if "orderby" in js_obj else []
+    if "where" in js_obj:
+        # predicate push-down: every clause of the conjunctive normal form goes to the table its columns belong to
+        # and is applied BEFORE the join ("where" -> first table, "where2" -> joined table)
+        off = 1 << 20
+
+        def resolve_where(operand):
+            q, c = locate(operand)
+            return c + (off if q == name2 and name1 != name2 else 0)
+
+        w1, w2, clause = [], [], []
+        for pr in _preds(js_obj["where"], resolve_where):
+            clause.append(pr)
+            if pr[1] & PRED_OR:
+                continue
+            sides = {x[0] >= off for x in clause}
+            if len(sides) > 1:
+                raise Exception("a WHERE clause that ORs columns of both joined tables is not supported")
+            if sides.pop():
+                w2 += [(x[0] - off, x[1], x[2], x[3]) for x in clause]
+            else:
+                w1 += clause
+            clause = []
+        if w1:
+            plan["where"] = w1
+        if w2:
+            plan["where2"] = w2
     if "groupby" in js_obj:
         gq, gc = locate(js_obj["groupby"]["value"])
         if gq != name2:
             raise Exception("JOIN ... GROUP BY must group on a column of the joined (second) table")
-        s_cols, ops = [], []
+        s_cols, ops, out_names, out_alias = [], [], [], {}
         for dic in _as_list(js_obj["select"]):
             val = dic["value"]
             if isinstance(val, str):
                 if locate(val) != (gq, gc):
                     raise Exception(f"{val} is not an aggregation function or the columns thats grouped on")
+                if "name" in dic:
+                    out_alias[dic["name"]] = 0
                 continue            # the key is output column 0 anyway
             for agg_func, agg_val in FUNC_TO_FUT_EXT.items():
                 if agg_func in val:
@@ -374,8 +402,33 @@ def _plan_join(js_obj, name1, table1, pj, aliases):
                             raise Exception("aggregates after a JOIN must be over columns of the first table")
                         s_cols.append(c)
                     ops.append(agg_val)
+                    out_names.append((agg_func, s_cols[-1]))
+                    if "name" in dic:
+                        out_alias[dic["name"]] = len(out_names)
+
+        def resolve_output(operand):
+            """HAVING / ORDER BY operand -> output column (0 = the group key, i = i-th aggregate)."""
+            if isinstance(operand, dict):
+                (f, c), = operand.items()
+                c_idx = ca if c == "*" else locate(c)[1]
+                for i, nm in enumerate(out_names):
+                    if nm == (f, c_idx):
+                        return i + 1
+                raise Exception(f"{f}({c}) must appear in the select list to be used in HAVING / ORDER BY")
+            if operand in out_alias:
+                return out_alias[operand]
+            if locate(operand) == (gq, gc):
+                return 0
+            raise Exception(f"{operand} is not an output column of the GROUP BY")
+
+        if "having" in js_obj:
+            plan["having"] = _preds(js_obj["having"], resolve_output)
+        if orderby:
+            plan["orderby"] = [(resolve_output(k["value"]), 1 if k.get("sort") == "desc" else 0) for k in orderby]
         plan.update({"g_col": gc, "select": s_cols, "groupbys": ops})
         return plan
+    if "having" in js_obj:
+        raise Exception("HAVING needs a GROUP BY clause")
     cols1, cols2 = [], []
     sel = js_obj["select"]
     if sel == "*":
@@ -391,5 +444,14 @@ def _plan_join(js_obj, name1, table1, pj, aliases):
                 cols2.append(c)
             else:
                 raise Exception("select list after a JOIN must list first-table columns before second-table columns")
+    if orderby:        # ORDER BY over the join's output columns (first-table columns, then second-table columns)
+        out_cols = [(name1, c) for c in cols1] + [(name2, c) for c in cols2]
+        keys = []
+        for k in orderby:
+            loc = locate(k["value"])
+            if loc not in out_cols:
+                raise Exception(f"{k['value']} must appear in the select list to be used in ORDER BY")
+            keys.append((out_cols.index(loc), 1 if k.get("sort") == "desc" else 0))
+        plan["orderby"] = keys
     plan.update({"select": cols1, "select2": cols2})
     return plan

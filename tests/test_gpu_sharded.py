@@ -102,5 +102,5 @@ def test_sharded_env_end_to_end_on_the_available_ranks():
     """world 1 under plain pytest; all GPUs under `torchrun -m pytest tests/test_gpu_sharded.py -m gpu`."""
     from tests import test_sharded_gloo as G
     senv = _sharded_env()
-    for name in ("filter", "groupby", "groupby_multi", "groupby_pinned", "orderby", "join", "sql"):
+    for name in ("filter", "groupby", "groupby_multi", "groupby_pinned", "orderby", "join", "sql", "sql_join"):
         getattr(G, "_scn_" + name)(senv)

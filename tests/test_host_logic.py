@@ -111,6 +111,25 @@ def test_plan_join():
     assert plan["join"] == (0, 0) and plan["g_col"] == 1 and plan["select"] == [1, 0] and plan["groupbys"] == [2, 5]
 
 
+def test_plan_join_where_pushdown_having_orderby():
+    f = Table("fact", pd.DataFrame({"fk": [1, 2], "val": [5, 6], "qty": [1, 2]}))
+    d = Table("dim", pd.DataFrame({"pk": [1, 2], "attr": [7, 8]}))
+    tabs = {"fact": f, "dim": d}
+    plan = sql_parse(tabs, "select d.attr, sum(f.val) as s, count(*) from fact f join dim d on f.fk = d.pk "
+                           "where f.qty > 1 and (d.attr = 7 or d.attr = 8) and not f.val < 0 "
+                           "group by d.attr having s > 3 order by count(*) desc, d.attr limit 3")
+    assert plan["where"] == [(2, 0, 1, 1.0), (1, 2 | 0x200, 0, 0.0)]                 # fact-side clauses, fact indices
+    assert plan["where2"] == [(1, 4 | 0x100, 7, 7.0), (1, 4, 8, 8.0)]               # one OR-clause on the dim side
+    assert plan["having"] == [(1, 0, 3, 3.0)] and plan["orderby"] == [(2, 1), (0, 0)] and plan["limit"] == 3
+    assert plan["select"] == [1, 0] and plan["groupbys"] == [2, 5] and plan["g_col"] == 1
+    plan = sql_parse(tabs, "select f.val, d.attr from fact f join dim d on f.fk = d.pk order by d.attr desc, f.val")
+    assert plan["orderby"] == [(1, 1), (0, 0)] and "where" not in plan
+    with pytest.raises(Exception, match="both joined tables"):
+        sql_parse(tabs, "select f.val, d.attr from fact f join dim d on f.fk = d.pk where f.qty = 1 or d.attr = 7")
+    with pytest.raises(Exception, match="HAVING needs a GROUP BY"):
+        sql_parse(tabs, "select f.val, d.attr from fact f join dim d on f.fk = d.pk having f.val > 1")
+
+
 def test_finalize_pred_integer_columns():
     assert finalize_pred((0, 0, None, 2.5), True) == (0, 0, 2, 2.5)     # x > 2.5  <=> x > 2
     assert finalize_pred((0, 1, None, 2.5), True) == (0, 0, 2, 2.5)     # x >= 2.5 <=> x > 2

@@ -196,10 +196,45 @@ def _scn_sql(senv):
     assert fc.sql("select col1, col3 from game_1 where col1 > 0 order by col3 desc, col1").tolist() == [[6, 6], [6, 6], [1, 3]]
 
 
+def _scn_sql_join(senv):
+    """JOIN with WHERE pushed down to both sides, GROUP BY, HAVING, ORDER BY, LIMIT — against pandas."""
+    import pandas as pd
+    from harkdb_b200.sharded import ShardedFutharkContext
+    rng = np.random.default_rng(11)
+    nd, nf = 503, 20011
+    dim = pd.DataFrame({"pk": rng.permutation(nd).astype(np.int64), "attr": rng.integers(0, 9, nd), "region": rng.integers(0, 4, nd)})
+    fact = pd.DataFrame({"fk": rng.integers(0, nd + 40, nf), "val": rng.integers(-50, 50, nf), "qty": rng.integers(1, 20, nf)})
+    fc = ShardedFutharkContext(engine=senv.engine)
+    fc.create_table("fact", fact)
+    fc.create_table("dim", dim)
+    out = fc.sql("select d.attr, sum(f.val), count(*) as n from fact f join dim d on f.fk = d.pk "
+                 "where f.qty > 5 and (d.region = 1 or d.region = 3) and not f.val between -10 and 10 "
+                 "group by d.attr having n > 50 order by sum(f.val) desc, d.attr limit 5")
+    j = fact[(fact.qty > 5) & ~fact.val.between(-10, 10)].merge(dim[dim.region.isin([1, 3])], left_on="fk", right_on="pk")
+    g = j.groupby("attr", sort=True).agg(s=("val", "sum"), n=("val", "size")).reset_index()
+    g = g[g.n > 50].sort_values(["s", "attr"], ascending=[False, True], kind="stable").head(5)
+    assert out.tolist() == g[["attr", "s", "n"]].to_numpy().tolist(), (out.tolist(), g.to_numpy().tolist())
+    if senv.world > 1:        # the sharded reference join wants u32 key columns (unsigned splitter order); tables here are i32
+        return
+    # plain join, reference row order (key, left row, right row), then ORDER BY over its output columns
+    out = fc.sql("select f.fk, f.val, d.attr from fact f join dim d on f.fk = d.pk where f.qty = 19 and d.attr < 2 "
+                 "order by d.attr desc, f.fk")          # (non-negative sort keys: the reference join's output is u32)
+    j = fact[fact.qty == 19].reset_index().merge(dim[dim.attr < 2].reset_index(), left_on="fk", right_on="pk")
+    j = j.sort_values(["fk", "index_x", "index_y"], kind="stable")              # join.fut:55-75 order
+    j = j.sort_values(["attr", "fk"], ascending=[False, True], kind="stable")
+    assert out.astype(np.int32).tolist() == j[["fk", "val", "attr"]].to_numpy().tolist()
+    with pytest.raises(Exception, match="both joined tables"):
+        fc.sql("select f.val, d.attr from fact f join dim d on f.fk = d.pk where f.qty = 19 or d.attr < 2")
+
+
 # ------------------------------------------------------------------ tests
-@pytest.mark.parametrize("scenario", ["filter", "groupby", "groupby_multi", "groupby_pinned", "orderby", "join", "sql"])
+@pytest.mark.parametrize("scenario", ["filter", "groupby", "groupby_multi", "groupby_pinned", "orderby", "join", "sql", "sql_join"])
 def test_sharded_world2(scenario):
     _run(scenario, 2)
+
+
+def test_sharded_world1_sql_join():
+    _run("sql_join", 1)
 
 
 def test_sharded_world3_uneven_shards():
