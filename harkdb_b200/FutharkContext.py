@@ -78,6 +78,8 @@ class FutharkContext:
         if "join" in val_dic:
             return self._sql_join(val_dic)
 
+        if val_dic.get("global"):
+            return self._sql_global_agg(val_dic)
         if "g_cols" in val_dic:
             return self._sql_groupby_ext(val_dic)
         if "groupbys" not in val_dic:
@@ -143,6 +145,34 @@ class FutharkContext:
                 cur.free()
             return self._post(res, plan)
         finally:
+            if tmp:
+                t.free()
+
+    def _sql_global_agg(self, plan):
+        """SELECT agg(..), .. FROM t [WHERE ..] without GROUP BY (TPC-H Q6's shape): a GROUP BY over a constant key
+        column put in front of the (filtered) table; the key is dropped from the one-row result."""
+        env = self.FutEnv
+        t, tmp = self._as_device(plan["table"])
+        cur, cur_tmp = t, False
+        try:
+            s_cols, ops = list(plan["select"]), list(plan["groupbys"])
+            if "where" in plan:
+                preds = [finalize_pred(p, self._is_int_col(t, p[0])) for p in plan["where"]]
+                need = list(dict.fromkeys(s_cols))
+                cur = env.query_filter(t, need, preds)
+                cur_tmp = True
+                s_cols = [need.index(c) for c in s_cols]
+            keyed = env.with_constant_key(cur)
+            try:
+                grouped = env.query_groupby_ex(keyed, 0, [c + 1 for c in s_cols], ops)
+            finally:
+                keyed.free()
+            res = env.query_filter(grouped, list(range(1, 1 + len(ops))), [])
+            grouped.free()
+            return self._finish(res, plan.get("limit"))
+        finally:
+            if cur_tmp:
+                cur.free()
             if tmp:
                 t.free()
 

@@ -341,6 +341,18 @@ class Futhark:
         self._check(self.lib.hark_table_from_device(self.ctx, C.byref(h), pa, dts, n, m))
         return DeviceTable(self, h.value)
 
+    def with_constant_key(self, t: DeviceTable) -> DeviceTable:
+        """[constant i32 column 0] ++ the columns of `t` (borrowed, no copy): the table a GROUP BY-less aggregate groups."""
+        n, m = t.shape
+        key = self.synth(n, [I32], [dict(kind=2, lo=0)])                     # HARK_GEN_CONST
+        if n == 0:
+            view = self.from_columns([np.zeros(0, np.int32)] + [np.zeros(0, NP_DTYPES[d]) for d in t.dtypes])
+            key.free()
+            return view
+        view = self.from_device_pointers([key.column_ptr(0)] + [t.column_ptr(c) for c in range(m)], [I32] + list(t.dtypes), n)
+        view._keepalive = (key, t)
+        return view
+
     def synth(self, n: int, dtypes: Sequence[int], specs: Sequence[dict], seed: int = 42, row0: int = 0) -> DeviceTable:
         m = len(dtypes)
         dts = (C.c_int32 * max(m, 1))(*dtypes)

@@ -9,7 +9,7 @@ itself contributes ``(g_col, 0)``, :73-75), and the same exception messages (:33
 Extensions (clauses the reference's README lists but parse.py ignores): ``where``
 (AND / OR / NOT over column-vs-constant comparisons, BETWEEN, IN — handed to libhark in conjunctive
 normal form), ``count``/``avg`` (codes 5, 6), ``having``,
-``orderby``, ``join``, ``limit``, GROUP BY over several columns (``g_cols``), ``select *`` and the single-column select that crashes the
+``orderby``, ``join``, ``limit``, GROUP BY over several columns (``g_cols``), aggregates without GROUP BY (``global``), ``select *`` and the single-column select that crashes the
 reference (:48-51 iterates a dict).  They appear as extra plan keys; a plan without them is
 byte-for-byte what the reference would build.
 
@@ -183,6 +183,21 @@ def sql_parse(tables, sql_statement):
 
     # ---- plain SELECT (parse.py:42-58) ----
     if "groupby" not in js_obj.keys():
+        pairs = _as_list(js_obj["select"]) if js_obj["select"] != "*" else []
+        if pairs and all(isinstance(p.get("value"), dict) for p in pairs):
+            # SELECT sum(a), count(*) ... with no GROUP BY: one group holding every (filtered) row
+            sel, codes = [], []
+            for p in pairs:
+                for agg_func, agg_val in FUNC_TO_FUT_EXT.items():
+                    if agg_func in p["value"]:
+                        arg = p["value"][agg_func]
+                        sel.append(0 if arg == "*" else col_index(_strip_qualifier(arg, aliases)[1]))
+                        codes.append(agg_val)
+            if len(sel) != len(pairs):
+                raise Exception(f"unsupported aggregate in {js_obj['select']}")
+            if "having" in js_obj or orderby:
+                raise Exception("HAVING / ORDER BY need a GROUP BY clause")
+            return {"table": table.get_handle(), "select": sel, "groupbys": codes, "global": True, **extras}
         fut_cols_selects = []
         if js_obj["select"] == "*":
             fut_cols_selects = list(range(len(columns)))

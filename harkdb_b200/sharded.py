@@ -345,6 +345,9 @@ class ShardedEnv:
         lo, hi = self.rank * n // self.world, (self.rank + 1) * n // self.world
         return self._wrap(self.engine.from_columns([np.ascontiguousarray(c[lo:hi]) for c in cols]))
 
+    def with_constant_key(self, t: ShardTable) -> ShardTable:
+        return self._wrap(self.engine.with_constant_key(t.local))
+
     def all_counts(self, n_local: int) -> List[int]:
         if self.world == 1:
             return [n_local]

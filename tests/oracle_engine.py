@@ -84,6 +84,10 @@ class OracleEngine:
     def query_groupby_ex(self, t, g_col, s_cols, ops, having=()):
         return OTable(NO.query_groupby_ex(t.cols, int(g_col), [int(x) for x in s_cols], [int(x) for x in ops], list(having)))
 
+    def with_constant_key(self, t):
+        n = len(t.cols[0]) if t.cols else 0
+        return OTable([np.zeros(n, dtype=np.int32)] + list(t.cols))
+
     def query_groupby_multi(self, t, g_cols, s_cols, ops, having=()):
         return OTable(NO.query_groupby_multi(t.cols, [int(g) for g in g_cols], [int(x) for x in s_cols],
                                              [int(x) for x in ops], list(having)))

@@ -117,6 +117,14 @@ def test_tpch_q1_shape_mixed_dtypes_group_by_two_columns():
     assert np.array_equal(out[:, 0], g.flag) and np.array_equal(out[:, 1], g.status)
     assert np.array_equal(out[:, 2], g.flag) and np.array_equal(out[:, 3], g.status)
     assert np.array_equal(out[:, 4], g.q) and np.allclose(out[:, 5], g.p, rtol=1e-12) and np.array_equal(out[:, 6], g.c)
+    # TPC-H Q6's shape: filter + aggregates without GROUP BY
+    out = ctx.sql("select sum(price), count(*), avg(qty), min(shipdate) from lineitem "
+                  "where shipdate between 9000 and 9364 and qty < 24 and not flag = 1")
+    m = df.shipdate.between(9000, 9364) & (df.qty < 24) & (df.flag != 1)
+    assert out.shape == (1, 4)
+    assert np.isclose(out[0, 0], df.price[m].sum(), rtol=1e-12) and out[0, 1] == m.sum()
+    assert np.isclose(out[0, 2], df.qty[m].mean(), rtol=1e-12) and out[0, 3] == df.shipdate[m].min()
+    assert ctx.sql("select count(*) from lineitem where qty > 1000").shape == (0, 1)
     # single key on the same frame: integer key, float measure
     out = ctx.sql("select flag, max(price) from lineitem group by flag")
     gm = df.groupby("flag", sort=True).price.max()

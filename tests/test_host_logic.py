@@ -111,6 +111,17 @@ def test_plan_join():
     assert plan["join"] == (0, 0) and plan["g_col"] == 1 and plan["select"] == [1, 0] and plan["groupbys"] == [2, 5]
 
 
+def test_plan_global_aggregates():
+    t = _game_table()
+    plan = sql_parse({"game_1": t}, "select sum(col2), count(*), avg(col3) from game_1 where col1 > 0 limit 1")
+    assert plan["global"] is True and plan["select"] == [1, 0, 2] and plan["groupbys"] == [2, 5, 6]
+    assert plan["where"] == [(0, 0, 0, 0.0)] and plan["limit"] == 1 and "g_col" not in plan
+    with pytest.raises(Exception, match="needs a GROUP BY clause"):
+        sql_parse({"game_1": t}, "select col1, sum(col2) from game_1")
+    with pytest.raises(Exception, match="need a GROUP BY"):
+        sql_parse({"game_1": t}, "select sum(col2) from game_1 having sum(col2) > 1")
+
+
 def test_plan_join_where_pushdown_having_orderby():
     f = Table("fact", pd.DataFrame({"fk": [1, 2], "val": [5, 6], "qty": [1, 2]}))
     d = Table("dim", pd.DataFrame({"pk": [1, 2], "attr": [7, 8]}))

@@ -194,6 +194,11 @@ def _scn_sql(senv):
     out = fc.sql("select col1, sum(col2), count(col2), avg(col2) from game_1 group by col1 having count(col2) > 1")
     assert out.tolist() == [[0.0, 0.0, 0.0, 4.0, 0.0], [6.0, 6.0, 12.0, 2.0, 6.0]]
     assert fc.sql("select col1, col3 from game_1 where col1 > 0 order by col3 desc, col1").tolist() == [[6, 6], [6, 6], [1, 3]]
+    # aggregates without GROUP BY (TPC-H Q6's shape): one row, the constant key is dropped
+    out = fc.sql("select sum(col2), count(*), avg(col2), max(col3) from game_1 where col1 > 0")
+    assert out.shape == (1, 4) and out[0].tolist() == [14.0, 3.0, 14.0 / 3.0, 6.0]
+    assert fc.sql("select count(*) from game_1").tolist() == [[7]]
+    assert fc.sql("select min(col1), max(col1) from game_1 where col1 > 100").shape == (0, 2)
 
 
 def _scn_sql_join(senv):
