@@ -63,7 +63,13 @@ class FutharkContext:
         return self.FutEnv.to_device(t, entry_dtype(np.asarray(t))), True
 
     def _finish(self, res, limit=None):
-        out = self.FutEnv.from_futhark(res)
+        """Result table (consumed) -> ndarray.  LIMIT is applied on the device, so only `limit` rows cross PCIe."""
+        env = self.FutEnv
+        if limit is not None and limit > 0 and hasattr(env, "slice") and isinstance(res, DeviceTable) and res.shape[0] > limit:
+            head = env.slice(res, 0, int(limit))
+            res.free()
+            res = head
+        out = env.from_futhark(res)
         res.free()
         return out if limit is None else out[:limit]
 
@@ -143,6 +149,10 @@ class FutharkContext:
                 res = env.query_groupby_ex(cur, g_cols[0], s_cols, ops)
             if cur_tmp:
                 cur.free()
+            if plan.get("distinct"):            # SELECT DISTINCT: the key columns are the result
+                keys = env.query_filter(res, list(range(len(g_cols))), [])
+                res.free()
+                res = keys
             return self._post(res, plan)
         finally:
             if tmp:

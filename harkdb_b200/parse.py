@@ -181,6 +181,28 @@ def sql_parse(tables, sql_statement):
     if "limit" in js_obj:
         extras["limit"] = int(js_obj["limit"])
 
+    # ---- SELECT DISTINCT a, b: GROUP BY a, b whose (COUNT) aggregate is dropped; rows come out in key order ----
+    if "select_distinct" in js_obj:
+        if "groupby" in js_obj or "having" in js_obj:
+            raise Exception("SELECT DISTINCT together with GROUP BY / HAVING is not supported")
+        sd = js_obj["select_distinct"]
+        names = list(columns) if sd == "*" else [p["value"] for p in _as_list(sd)]
+        if not all(isinstance(nm, str) for nm in names):
+            raise Exception("SELECT DISTINCT takes plain columns")
+        g_cols = [col_index(_strip_qualifier(nm, aliases)[1]) for nm in names]
+        if len(set(g_cols)) != len(g_cols):
+            raise Exception("SELECT DISTINCT lists a column twice")
+        if orderby:
+            keys = []
+            for k in orderby:
+                idx = col_index(_strip_qualifier(k["value"], aliases)[1])
+                if idx not in g_cols:
+                    raise Exception(f"{k['value']} must appear in the select list to be used in ORDER BY")
+                keys.append((g_cols.index(idx), 1 if k.get("sort") == "desc" else 0))
+            extras["orderby"] = keys
+        return {"table": table.get_handle(), "select": [g_cols[0]], "groupbys": [FUNC_TO_FUT_EXT["count"]],
+                "g_cols": g_cols, "distinct": True, **extras}
+
     # ---- plain SELECT (parse.py:42-58) ----
     if "groupby" not in js_obj.keys():
         pairs = _as_list(js_obj["select"]) if js_obj["select"] != "*" else []

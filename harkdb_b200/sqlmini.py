@@ -8,6 +8,7 @@ on are catalogued in SURVEY.md App. C:
     select a, b from t                 {"select": [{"value": "a"}, {"value": "b"}], "from": "t"}
     select a from t                    {"select": {"value": "a"}, "from": "t"}            (dict, not list)
     select * from t                    {"select": "*", "from": "t"}
+    select distinct a, b from t        {"select_distinct": [{"value": "a"}, {"value": "b"}], "from": "t"}
     select max(c) from t               {"select": {"value": {"max": "c"}}, ...}
     ... where a > 4 and b <= 2.5       "where": {"and": [{"gt": ["a", 4]}, {"lte": ["b", 2.5]}]}
     ... group by a                     "groupby": {"value": "a"}
@@ -26,7 +27,7 @@ import re
 from typing import Any, List
 
 KEYWORDS = {"select", "from", "where", "group", "by", "having", "order", "limit", "and", "or", "not", "as",
-            "join", "inner", "on", "asc", "desc", "between", "in"}
+            "join", "inner", "on", "asc", "desc", "between", "in", "distinct"}
 CMP = {"=": "eq", "==": "eq", "!=": "neq", "<>": "neq", ">": "gt", ">=": "gte", "<": "lt", "<=": "lte"}
 
 _TOKEN = re.compile(r"""
@@ -176,15 +177,19 @@ class _Parser:
     def query(self) -> dict:
         out: dict = {}
         self.eat("kw", "select")
+        sel_key = "select"
+        if self.at_kw("distinct"):
+            self.eat()
+            sel_key = "select_distinct"
         if self.peek() == ("punct", "*"):
             self.eat()
-            out["select"] = "*"
+            out[sel_key] = "*"
         else:
             items = [self.select_item()]
             while self.peek() == ("punct", ","):
                 self.eat()
                 items.append(self.select_item())
-            out["select"] = items[0] if len(items) == 1 else items
+            out[sel_key] = items[0] if len(items) == 1 else items
         self.eat("kw", "from")
         frm: List[Any] = [self.table_ref()]
         while self.at_kw("join", "inner"):

@@ -111,6 +111,16 @@ def test_plan_join():
     assert plan["join"] == (0, 0) and plan["g_col"] == 1 and plan["select"] == [1, 0] and plan["groupbys"] == [2, 5]
 
 
+def test_plan_select_distinct():
+    assert sqlmini.parse("select distinct a, b from t") == {"select_distinct": [{"value": "a"}, {"value": "b"}], "from": "t"}
+    t = _game_table()
+    plan = sql_parse({"game_1": t}, "select distinct col3, col1 from game_1 where col2 < 6 order by col1 desc limit 2")
+    assert plan["g_cols"] == [2, 0] and plan["distinct"] is True and plan["groupbys"] == [5]
+    assert plan["orderby"] == [(1, 1)] and plan["limit"] == 2 and plan["where"] == [(1, 2, 6, 6.0)]
+    with pytest.raises(Exception, match="must appear in the select list"):
+        sql_parse({"game_1": t}, "select distinct col1 from game_1 order by col2")
+
+
 def test_plan_global_aggregates():
     t = _game_table()
     plan = sql_parse({"game_1": t}, "select sum(col2), count(*), avg(col3) from game_1 where col1 > 0 limit 1")

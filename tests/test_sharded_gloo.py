@@ -198,6 +198,8 @@ def _scn_sql(senv):
     out = fc.sql("select sum(col2), count(*), avg(col2), max(col3) from game_1 where col1 > 0")
     assert out.shape == (1, 4) and out[0].tolist() == [14.0, 3.0, 14.0 / 3.0, 6.0]
     assert fc.sql("select count(*) from game_1").tolist() == [[7]]
+    assert fc.sql("select distinct col1 from game_1").tolist() == [[0], [1], [6]]
+    assert fc.sql("select distinct col3, col1 from game_1 where col2 < 6 order by col1 desc").tolist() == [[3, 1], [0, 0]]
     assert fc.sql("select min(col1), max(col1) from game_1 where col1 > 100").shape == (0, 2)
 
 
