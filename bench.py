@@ -310,6 +310,26 @@ def run_gpu_arm(args):
                    "step_phases_ms[upload+filter, download]": list(phases),
                    "path": "pinned host row-major table -> hark_table_from_host (H2D + transpose) -> "
                            "hark_entry_query_filter -> hark_table_to_host (D2H), all inside the timed step"}
+            # the step is PCIe-bound: report it against the box's pinned host->device copy rate, measured here
+            try:
+                pb = 1 << 30
+                hp = torch.empty(pb, dtype=torch.uint8, pin_memory=True)
+                dp = torch.empty(pb, dtype=torch.uint8, device="cuda")
+                best_copy = None
+                for _ in range(4):
+                    torch.cuda.synchronize()
+                    tc = time.perf_counter()
+                    dp.copy_(hp, non_blocking=True)
+                    torch.cuda.synchronize()
+                    tc = time.perf_counter() - tc
+                    best_copy = tc if best_copy is None else min(best_copy, tc)
+                del hp, dp
+                moved = in_bytes + int(k) * 8
+                e2e["pcie"] = {"achieved_gbs": moved / (dt / args.e2e_steps) / 1e9, "h2d_peak_gbs": pb / best_copy / 1e9,
+                               "frac": (moved / (dt / args.e2e_steps)) / (pb / best_copy),
+                               "note": "bytes crossing PCIe per step / step time, against a pinned 1 GiB torch copy timed in this run"}
+            except Exception as ex:      # never lose the bench line over a diagnostic
+                e2e["pcie"] = {"error": repr(ex)[:200]}
             # and the product's default (resident table, only the result crosses PCIe)
             t0 = time.perf_counter()
             for _ in range(args.e2e_steps):
