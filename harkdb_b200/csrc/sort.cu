@@ -1,6 +1,6 @@
-// sort.cu — K3: CUB-free, stable LSD radix sort over SoA arrays ("onesweep": one read + one write of
-// the carried arrays per 8-bit digit, chained-scan look-back per digit bin), plus hash partitioning
-// (one pass with digit = mix(key) % nparts).
+// sort.cu — K3: CUB-free, stable LSD radix sort over SoA arrays (one read + one write of the carried arrays per
+// 8-bit digit), K3t: passes over the top bits only + in-place tie repair when the composite key is much wider than
+// log2(n), plus hash partitioning (one pass with digit = mix(key) % nparts).
 //
 // Reference: the radix sort inside GROUP BY and JOIN — futhark/groupby.fut:8-22 and join.fut:9-23 —
 // is 32 stable 1-bit passes, each two scans + a full copy + a scatter of WHOLE rows.  Only its result
@@ -8,11 +8,13 @@
 //   * keys are normalised per column to  t = ordkey(x) - min  (or max - ordkey(x) for DESC), where
 //     ordkey flips the sign bit of signed ints / IEEE-flips floats (NaN last); only ceil(bits(max-min)/8)
 //     digits are sorted, so 20-bit keys cost 3 passes, not 32;
-//   * digit histograms of every pass are permutation invariant, so they are all computed up front,
-//     one read of each key column;
+//   * a pass (default, "chunked"): per-chunk digit histogram -> one-CTA scan -> stable scatter with running offsets,
+//     no inter-CTA communication; the first implementation ("onesweep": all histograms up front, chained-scan
+//     look-back per (tile, digit)) is kept behind sort.impl=1 for A/B;
 //   * a pass moves each carried array (key columns and payload / row ids) exactly once, through a
 //     tile-local shared-memory reorder so that the global writes are contiguous runs per digit.
-// HBM-bound: algorithmic bytes per pass = 2 · n · (sum of carried widths).
+// Algorithmic bytes per pass = n · key width (histogram) + 2 · n · (sum of carried widths); the scatter kernel is
+// issue-bound, not HBM-bound.
 #include <algorithm>
 #include <new>
 #include <stdexcept>
