@@ -197,8 +197,11 @@ extern "C" int hark_context_set_option(hark_ctx *ctx, const char *key, int64_t v
 
 extern "C" int hark_context_get_option(hark_ctx *ctx, const char *key, int64_t *value) {
     if (!ctx || !key || !value) return HARK_ERR_ARG;
-    auto it = ctx->opts.find(key);
-    if (it == ctx->opts.end()) return ctx->fail(HARK_ERR_ARG, std::string("option not set: ") + key);
+    auto it = ctx->counters.find(key);
+    if (it == ctx->counters.end()) {
+        it = ctx->opts.find(key);
+        if (it == ctx->opts.end()) return ctx->fail(HARK_ERR_ARG, std::string("option not set: ") + key);
+    }
     *value = it->second;
     return HARK_OK;
 }

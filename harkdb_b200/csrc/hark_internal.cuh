@@ -53,7 +53,8 @@ struct hark_ctx {
     int64_t total_launches = 0;
     int64_t entry_launches = 0;
     int entry_depth = 0; // operators call each other (HAVING -> K1, multi-key GROUP BY -> GROUP BY): only the outermost begin/end count
-    std::map<std::string, int64_t> opts;
+    std::map<std::string, int64_t> opts;     // tuning knobs (hark_context_set_option)
+    std::map<std::string, int64_t> counters; // read-only facts about the last operation ("sort.last_passes", ...)
     struct hk_peer_state *peer = nullptr; // K8c: receive arena + the other ranks' arenas (repartition.cu)
 
     int fail(int code, const std::string &msg) {

@@ -1301,10 +1301,10 @@ int hk_radix_sort(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec> &
     }
     int npass = (int)passes.size();
     if (info) info->passes = npass;
-    ctx->opts["sort.last_fallback"] = 0;
-    ctx->opts["sort.last_fix_runs"] = 0;
-    ctx->opts["sort.last_passes"] = npass;
-    ctx->opts["sort.last_truncated"] = 0;
+    ctx->counters["sort.last_fallback"] = 0;
+    ctx->counters["sort.last_fix_runs"] = 0;
+    ctx->counters["sort.last_passes"] = npass;
+    ctx->counters["sort.last_truncated"] = 0;
 
     if (npass == 0) { // nothing to move: the result is a copy of the input
         for (auto &a : arrays) {
@@ -1364,16 +1364,16 @@ int hk_radix_sort(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec> &
             int64_t runs = 0;
             rc = fix_truncated(ctx, n, keys, arrays, ranges, trunc, (npass - 1) & 1, &redo, &runs);
             if (rc != HARK_OK) return cleanup_fail(rc, "");
-            ctx->opts["sort.last_fix_runs"] = runs;
+            ctx->counters["sort.last_fix_runs"] = runs;
             if (!redo) break;
             trunc.on = false; // a long run needed the low digits after all: all passes, from the input
-            ctx->opts["sort.last_fallback"] = 1;
+            ctx->counters["sort.last_fallback"] = 1;
             npass = build_passes(keys, ranges, (int)keys.size() - 1, 0, passes);
         }
         ctx->kernel_end();
         if (info) info->passes = npass;
-        ctx->opts["sort.last_passes"] = npass;
-        ctx->opts["sort.last_truncated"] = trunc.on ? 1 : 0;
+        ctx->counters["sort.last_passes"] = npass;
+        ctx->counters["sort.last_truncated"] = trunc.on ? 1 : 0;
     } else {
     // ---- 3. all digit histograms up front (one read per key column), then their exclusive scans ----
         rc = ctx->dalloc((void **)&d_hist, sizeof(unsigned long long) * 256 * npass);

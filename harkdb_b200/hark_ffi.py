@@ -344,7 +344,7 @@ class Futhark:
     def with_constant_key(self, t: DeviceTable) -> DeviceTable:
         """[constant i32 column 0] ++ the columns of `t` (borrowed, no copy): the table a GROUP BY-less aggregate groups."""
         n, m = t.shape
-        key = self.synth(n, [I32], [dict(kind=2, lo=0)])                     # HARK_GEN_CONST
+        key = self.synth(n, [I32], [dict(kind=GEN_CONST, lo=0)])
         if n == 0:
             view = self.from_columns([np.zeros(0, np.int32)] + [np.zeros(0, NP_DTYPES[d]) for d in t.dtypes])
             key.free()
