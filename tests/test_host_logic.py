@@ -235,6 +235,46 @@ def test_where_boolean_expressions_become_cnf_with_the_same_truth_table():
         _preds(sqlmini.parse("select a from t where " + big)["where"], resolve)
 
 
+def test_cnf_conversion_property_random_trees():
+    """hypothesis: any AND / OR / NOT / BETWEEN / IN tree over four columns either converts to a CNF predicate list
+    with the tree's truth table (NaN rows included) or is rejected for its size — never silently wrong."""
+    from hypothesis import given, settings, strategies as st
+    from harkdb_b200.parse import _preds
+    from oracle import np_oracle as NO
+    rng = np.random.default_rng(17)
+    n = 600
+    names = ["a", "b", "c", "d"]
+    cols = [rng.integers(-3, 4, n).astype(np.int32), rng.integers(0, 5, n).astype(np.int64),
+            np.round(rng.random(n) * 4).astype(np.float32) / 4, np.round(rng.random(n) * 4) / 4]
+    cols[2][rng.integers(0, n, 60)] = np.nan
+    cols[3][rng.integers(0, n, 60)] = np.nan
+    is_int = [True, True, False, False]
+    consts = {"a": [-2, 0, 1, 2.5], "b": [0, 2, 3, 1.5], "c": [0.25, 0.5, 1], "d": [0, 0.5, 0.75]}
+    leaf = st.one_of(
+        st.builds(lambda nm, op, i: f"{nm} {op} {consts[nm][i % len(consts[nm])]}", st.sampled_from(names),
+                  st.sampled_from(["<", "<=", ">", ">=", "=", "<>"]), st.integers(0, 3)),
+        st.builds(lambda nm, i: f"{nm} between {consts[nm][0]} and {consts[nm][i % len(consts[nm])]}", st.sampled_from(names),
+                  st.integers(0, 3)),
+        st.builds(lambda nm: f"{nm} in ({consts[nm][0]}, {consts[nm][1]})", st.sampled_from(names)),
+        st.builds(lambda nm: f"{nm} not in ({consts[nm][1]}, {consts[nm][2]})", st.sampled_from(names)))
+    tree = st.recursive(leaf, lambda ch: st.one_of(
+        st.builds(lambda x, y: f"({x} and {y})", ch, ch), st.builds(lambda x, y: f"({x} or {y})", ch, ch),
+        st.builds(lambda x: f"not ({x})", ch)), max_leaves=5)
+
+    @settings(max_examples=150, deadline=None)
+    @given(tree)
+    def check(w):
+        t = sqlmini.parse("select a from t where " + w)["where"]
+        try:
+            preds = [finalize_pred(p, is_int[p[0]]) for p in _preds(t, names.index)]
+        except Exception as e:
+            assert "conjunctive normal form" in str(e), (w, e)
+            return
+        assert np.array_equal(NO.pred_mask(cols, preds), _eval_tree(t, cols, names)), w
+
+    check()
+
+
 def test_c_oracle_filter_cnf_matches_numpy_oracle():
     from harkdb_b200.parse import PRED_NOT, PRED_OR
     from oracle import c_oracle as CO
