@@ -150,12 +150,21 @@ def cpu_filter_time(CO, db, out, threads, reps):
     return best, n_out
 
 
+def host_threads():
+    """All the host cores this process may use.  torchrun exports OMP_NUM_THREADS=1, which must not shrink the CPU arm:
+    the thread count is passed to the port explicitly (num_threads clause)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     from oracle import c_oracle as CO
-    threads = CO.max_threads()
+    threads = host_threads()
     rows = args.cpu_rows
     CO, db, out = cpu_filter_setup(rows, threads)
     cpu_filter_time(CO, db, out, threads, max(args.warmup, 1))
@@ -379,8 +388,7 @@ def run_gpu_arm(args):
     if e2e:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu:
-        from oracle import c_oracle as CO
-        threads = CO.max_threads()
+        threads = host_threads()
         COm, db, out = cpu_filter_setup(args.cpu_rows, threads)
         cpu_filter_time(COm, db, out, threads, 1)
         times, _ = cpu_filter_time(COm, db, out, threads, 3)
