@@ -133,6 +133,48 @@ def run_groupby(env, scale, reps):
     return d
 
 
+def run_groupby_f32(env, scale, reps):
+    """Config 3's f32 variant: val f32 uniform [0,1); float SUM accumulates in f64 and rounds once."""
+    import torch
+    n = int(10 ** 9 * scale)
+    specs = [dict(kind=0, lo=0, range=1 << 20), dict(kind=0, flo=0.0, fhi=1.0)]
+    t = env.synth(n, [I32, F32], specs, seed=42)
+    ops = [AGG_SUM, AGG_COUNT, AGG_AVG]
+    st, r = timed(env, lambda: env.query_groupby_ex(t, 0, [1, 1, 1], ops), reps)
+    keys, sums, cnts, avgs = r.columns()
+    total = float(as_torch(t, 1).sum(dtype=torch.float64).item())
+    ok = (np.all(np.diff(keys.astype(np.int64)) > 0) and int(cnts.sum()) == n and sums.dtype == np.float32
+          and abs(float(sums.astype(np.float64).sum()) - total) <= 1e-5 * total
+          and np.allclose(avgs, sums.astype(np.float64) / cnts, rtol=1e-5))
+    d = line("groupby_cfg3_f32", n, st, {"groups": len(keys), "check_ok": bool(ok)})
+    r.free(); t.free()
+    return d
+
+
+def run_join_half(env, scale, reps):
+    """Config 5's 50 %-match run: fk uniform over twice the dimension's key range."""
+    import torch
+    nf, nd = int(4 * 10 ** 9 * scale), int(10 ** 8 * min(1.0, scale * 4))
+    a = 2654435761
+    while np.gcd(a, nd) != 1:
+        a += 2
+    dim = env.synth(nd, [I32, I32], [dict(kind=1, a=a, b=12345, range=nd), dict(kind=0, lo=0, range=1024)], seed=7)
+    fact = env.synth(nf, [I32, I32], [dict(kind=0, lo=0, range=2 * nd), dict(kind=0, lo=0, range=1000)], seed=42)
+    ops = [AGG_SUM, AGG_COUNT]
+    st, r = timed(env, lambda: env.join_groupby(fact, dim, 0, 0, 1, [1, 1], ops), reps)
+    keys, sums, cnts = r.columns()
+    fk, val = as_torch(fact, 0), as_torch(fact, 1)
+    hit = fk < nd
+    matched = int(hit.sum().item())
+    total = int(torch.where(hit, val, torch.zeros_like(val)).sum(dtype=torch.int64).item())
+    del hit
+    ok = (len(keys) == 1024 and int(cnts.sum()) == matched
+          and (int(sums.view(np.uint32).astype(np.uint64).sum()) - total) % (1 << 32) == 0)
+    d = line("join_groupby_cfg5_half_match", nf, st, {"dim_rows": nd, "matched_rows": matched, "check_ok": bool(ok)})
+    r.free(); dim.free(); fact.free()
+    return d
+
+
 def run_groupby_zipf(env, scale, reps):
     """Config 3 with skewed keys (HARK_GEN_LOGUNIFORM: P(k) ~ 1/(k+1), key 0 holds 5 % of the rows)."""
     import torch
@@ -246,6 +288,10 @@ def main():
                 res.append(run_groupby(env, args.scale, args.reps))
             elif op == "orderby":
                 res.append(run_orderby(env, args.scale, args.reps))
+            elif op == "groupby_f32":
+                res.append(run_groupby_f32(env, args.scale, args.reps))
+            elif op == "join_half":
+                res.append(run_join_half(env, args.join_scale or args.scale, args.reps))
             elif op == "groupby_zipf":
                 res.append(run_groupby_zipf(env, args.scale, args.reps))
             elif op == "filter_sweep":
