@@ -1027,40 +1027,36 @@ FixKey make_fix_key(const hk_sort_keyspec &ks, const KeyRange &r, const void *pt
     return f;
 }
 
-// Decides how many of the top bits of the composite key the LSD passes must cover.  T starts at ceil(log2 n) + slack
-// (a uniform key then leaves < 2^-slack of the rows tied with a neighbour) and grows by one digit at a time while an
-// evenly spaced sample of the key tuples still shows prefix ties between DIFFERENT tuples — clustered keys (floats
-// around one exponent, ids with a common high part) keep all their passes, duplicates cost nothing.
-int plan_truncation(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec> &keys, const std::vector<hk_sort_array> &arrays,
-                    const std::vector<KeyRange> &ranges, int full_passes, TruncPlan *out) {
-    const int nk = (int)keys.size();
+// Number of passes of the plan "keys 0..kstar, key kstar by its top q digits" (the loop structure of build_passes);
+// *low_shift = lowest sorted bit of key kstar.
+int count_passes(const int *bits, int kstar, int q, int *low_shift) {
+    int np = 0;
+    *low_shift = 0;
+    for (int k = kstar; k >= 0; k--) {
+        int sh0 = 0;
+        if (k == kstar && q > 0 && 8 * q < bits[k]) sh0 = bits[k] - 8 * q;
+        if (k == kstar) *low_shift = sh0;
+        for (int sh = sh0; sh < bits[k]; sh += 8) np++;
+    }
+    return np;
+}
+
+// Decides how many of the top bits of the composite key the LSD passes must cover — pure host code, also reachable
+// without a GPU through hark_debug_plan_truncation (tests/test_host_logic.py runs it against a Python restatement).
+// T starts at ceil(log2 n) + slack (a uniform key then leaves < 2^-slack of the rows tied with a neighbour) and grows
+// by one digit at a time while the sample (S normalised key tuples, row-major, evenly spaced rows) still shows prefix
+// ties between DIFFERENT tuples — clustered keys (floats around one exponent, ids with a common high part) keep all
+// their passes, duplicates cost nothing.
+void plan_from_sample(int64_t n, int nk, const int *bits, const uint64_t *row, int S, int slack, TruncPlan *out) {
     out->on = false;
-    int total_bits = 0;
-    for (int k = 0; k < nk; k++) total_bits += ranges[k].bits;
-    const int slack = (int)std::max<int64_t>(0, ctx->opt("sort.trunc_slack", 4));
+    int total_bits = 0, full_passes = 0;
+    for (int k = 0; k < nk; k++) {
+        total_bits += bits[k];
+        full_passes += (bits[k] + 7) / 8;
+    }
     int T = bit_width_u64((uint64_t)(n - 1)) + slack;
-    if (T + 8 > total_bits) return HARK_OK; // nothing to save
-    // ---- sample, sorted by the full tuple; per adjacent pair: first differing key and its highest differing bit ----
-    const int S = (int)std::min<int64_t>(n, 32768);
-    uint64_t *d_sample = nullptr;
-    HK_TRY(ctx->dalloc((void **)&d_sample, sizeof(uint64_t) * (size_t)S * nk));
-    SampleParams SP;
-    memset(&SP, 0, sizeof SP);
-    SP.nk = nk;
-    for (int k = 0; k < nk; k++) SP.key[k] = make_fix_key(keys[k], ranges[k], arrays[keys[k].array].in, arrays[keys[k].array].width);
-    SP.n = n;
-    SP.S = S;
-    SP.out = d_sample;
-    hk_sort_sample_kernel<<<(S + 255) / 256, 256, 0, ctx->stream>>>(SP);
-    cudaError_t e = cudaGetLastError();
-    ctx->count_launch();
-    std::vector<uint64_t> col((size_t)S * nk), row((size_t)S * nk);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(col.data(), d_sample, sizeof(uint64_t) * col.size(), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    ctx->dfree(d_sample);
-    if (e != cudaSuccess) return ctx->fail(HARK_ERR_CUDA, std::string("sort(sample): ") + cudaGetErrorString(e));
-    for (int s = 0; s < S; s++)
-        for (int k = 0; k < nk; k++) row[(size_t)s * nk + k] = col[(size_t)k * S + s];
+    if (T + 8 > total_bits || S < 1) return; // nothing to save
+    // ---- sample sorted by the full tuple; per adjacent pair: first differing key and its highest differing bit ----
     std::vector<int> order(S);
     for (int s = 0; s < S; s++) order[s] = s;
     std::sort(order.begin(), order.end(), [&](int a, int b) {
@@ -1081,7 +1077,7 @@ int plan_truncation(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec>
     }
     // A sample of S rows sees a prefix tie of the data only if it holds both rows: ties_sample ~ ties_data * (S/n)^2.
     // The repair stays cheaper than the passes it replaces while ties_data < n/8 (which is also the work list's size),
-    // and a uniform key at the default slack shows 1/8 of that.
+    // and a uniform key at the default slack shows 1/4 of that.
     const double expect = (double)S * (double)S / (8.0 * (double)n);
     const int64_t thr = (int64_t)std::max(4.0, expect);
     // ---- smallest digit-aligned prefix whose sample ties stay under the threshold ----
@@ -1093,7 +1089,7 @@ int plan_truncation(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec>
                 q = 0;
                 break;
             }
-            const int b = ranges[k].bits, qd = (T - acc + 7) / 8;
+            const int b = bits[k], qd = (T - acc + 7) / 8;
             if (8 * qd >= b) {
                 acc += b;
                 continue;
@@ -1102,10 +1098,9 @@ int plan_truncation(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec>
             q = qd;
             break;
         }
-        std::vector<Pass> tmp;
         int shift = 0;
-        const int np = build_passes(keys, ranges, kstar, q, tmp, &shift);
-        if (np >= full_passes) return HARK_OK;
+        const int np = count_passes(bits, kstar, q, &shift);
+        if (np >= full_passes) return;
         int64_t ties = 0;
         for (const auto &d : diff)
             if (d.first > kstar || (d.first == kstar && d.second <= shift)) ties++;
@@ -1114,9 +1109,43 @@ int plan_truncation(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec>
             out->kstar = kstar;
             out->q = q;
             out->shift = shift;
-            return HARK_OK;
+            return;
         }
     }
+}
+
+// Device part of the planning: an evenly spaced sample of the normalised key tuples, downloaded and handed to
+// plan_from_sample.
+int plan_truncation(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec> &keys, const std::vector<hk_sort_array> &arrays,
+                    const std::vector<KeyRange> &ranges, int full_passes, TruncPlan *out) {
+    const int nk = (int)keys.size();
+    out->on = false;
+    (void)full_passes;
+    int bits[FIX_MAXK], total_bits = 0;
+    for (int k = 0; k < nk; k++) total_bits += (bits[k] = ranges[k].bits);
+    const int slack = (int)std::max<int64_t>(0, ctx->opt("sort.trunc_slack", 4));
+    if (bit_width_u64((uint64_t)(n - 1)) + slack + 8 > total_bits) return HARK_OK; // nothing to save: skip the sample
+    const int S = (int)std::min<int64_t>(n, 32768);
+    uint64_t *d_sample = nullptr;
+    HK_TRY(ctx->dalloc((void **)&d_sample, sizeof(uint64_t) * (size_t)S * nk));
+    SampleParams SP;
+    memset(&SP, 0, sizeof SP);
+    SP.nk = nk;
+    for (int k = 0; k < nk; k++) SP.key[k] = make_fix_key(keys[k], ranges[k], arrays[keys[k].array].in, arrays[keys[k].array].width);
+    SP.n = n;
+    SP.S = S;
+    SP.out = d_sample;
+    hk_sort_sample_kernel<<<(S + 255) / 256, 256, 0, ctx->stream>>>(SP);
+    cudaError_t e = cudaGetLastError();
+    ctx->count_launch();
+    std::vector<uint64_t> col((size_t)S * nk), row((size_t)S * nk);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(col.data(), d_sample, sizeof(uint64_t) * col.size(), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    ctx->dfree(d_sample);
+    if (e != cudaSuccess) return ctx->fail(HARK_ERR_CUDA, std::string("sort(sample): ") + cudaGetErrorString(e));
+    for (int s = 0; s < S; s++)
+        for (int k = 0; k < nk; k++) row[(size_t)s * nk + k] = col[(size_t)k * S + s];
+    plan_from_sample(n, nk, bits, row.data(), S, slack, out);
     return HARK_OK;
 }
 
@@ -1485,4 +1514,24 @@ int hk_radix_sort(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec> &
         info->bytes_moved = 2 * n * wsum * npass;
     }
     return HARK_OK;
+}
+
+// The K3t planning decision without a device (tests): bits[k] = significant bits of key k (most significant key first),
+// sample = S normalised key tuples, row-major.  Returns 1 and fills kstar / q / shift / passes when the sort would run
+// truncated, 0 when it keeps every pass.
+extern "C" int hark_debug_plan_truncation(int64_t n, int32_t nk, const int32_t *bits, const uint64_t *sample, int32_t S,
+                                          int32_t slack, int32_t *kstar, int32_t *q, int32_t *shift, int32_t *passes) {
+    if (n < 2 || nk < 1 || nk > FIX_MAXK || !bits || (S > 0 && !sample)) return 0;
+    int b[FIX_MAXK];
+    for (int k = 0; k < nk; k++) b[k] = bits[k];
+    TruncPlan tp;
+    plan_from_sample(n, nk, b, sample, S, slack, &tp);
+    if (!tp.on) return 0;
+    int sh = 0;
+    const int np = count_passes(b, tp.kstar, tp.q, &sh);
+    if (kstar) *kstar = tp.kstar;
+    if (q) *q = tp.q;
+    if (shift) *shift = tp.shift;
+    if (passes) *passes = np;
+    return 1;
 }

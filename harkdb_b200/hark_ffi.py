@@ -111,6 +111,8 @@ SIGNATURES = {
     "hark_stats_total_launches": (C.c_int64, [_P]),
     "hark_context_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "hark_context_get_option": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int64)]),
+    "hark_debug_plan_truncation": (C.c_int, [C.c_int64, C.c_int32, _I32P, C.POINTER(C.c_uint64), C.c_int32, C.c_int32,
+                                             _I32P, _I32P, _I32P, _I32P]),
     "hark_host_alloc": (_P, [C.c_int64]),
     "hark_host_free": (None, [_P]),
 }

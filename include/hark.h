@@ -245,6 +245,13 @@ int hark_context_set_option(hark_ctx *ctx, const char *key, int64_t value);
  * HARK_ERR_ARG if the key was never set.                                                        */
 int hark_context_get_option(hark_ctx *ctx, const char *key, int64_t *value);
 
+/* The sort's pass-truncation decision as a pure host function, for tests without a device: bits[k] =
+ * significant bits of key k (most significant first), sample = S normalised key tuples (row-major).  Returns 1 and
+ * fills the outputs when the sort would run only the top digits (keys 0..kstar, key kstar by its top q digits, its
+ * bits below `shift` left to the tie repair), 0 when it keeps every pass.                                         */
+int hark_debug_plan_truncation(int64_t n, int32_t nk, const int32_t *bits, const uint64_t *sample, int32_t S,
+                               int32_t slack, int32_t *kstar, int32_t *q, int32_t *shift, int32_t *passes);
+
 /* ---- pinned host memory for callers that want DMA-speed uploads ---- */
 void *hark_host_alloc(int64_t bytes);
 void hark_host_free(void *p);

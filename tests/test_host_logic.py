@@ -353,6 +353,97 @@ def test_np_oracle_groupby_multi_against_pandas():
     assert np.array_equal(hv[2], cnt["n"].to_numpy())
 
 
+# ---- K3t: the sort's pass-truncation decision is pure host code inside libhark.so (no device needed) ----
+def _py_plan(norm_keys, n, slack=4):
+    """Python restatement of plan_from_sample (csrc/sort.cu): (kstar, q, shift, passes) or None."""
+    nk = len(norm_keys)
+    bits = [int(int(k.max()) - 0).bit_length() for k in norm_keys]
+    full, total = sum((b + 7) // 8 for b in bits), sum(bits)
+    T = int(n - 1).bit_length() + slack
+    if T + 8 > total:
+        return None
+    S = min(n, 32768)
+    rows = (np.arange(S, dtype=object) * n // S).astype(np.int64)
+    samp = [k[rows] for k in norm_keys]
+    order = np.lexsort(samp[::-1])
+    diff = []
+    for s in range(1, S):
+        a, b = order[s - 1], order[s]
+        for k in range(nk):
+            x, y = int(samp[k][a]), int(samp[k][b])
+            if x != y:
+                diff.append((k, (x ^ y).bit_length()))
+                break
+    thr = int(max(4.0, S * S / (8.0 * n)))
+    while True:
+        acc, kstar, q = 0, nk - 1, 0
+        for k in range(nk):
+            if acc >= T:
+                kstar, q = k - 1, 0
+                break
+            qd = (T - acc + 7) // 8
+            if 8 * qd >= bits[k]:
+                acc += bits[k]
+                continue
+            kstar, q = k, qd
+            break
+        np_, shift = 0, 0
+        for k in range(kstar, -1, -1):
+            sh0 = bits[k] - 8 * q if (k == kstar and q > 0 and 8 * q < bits[k]) else 0
+            if k == kstar:
+                shift = sh0
+            np_ += len(range(sh0, bits[k], 8))
+        if np_ >= full:
+            return None
+        ties = sum(1 for d in diff if d[0] > kstar or (d[0] == kstar and d[1] <= shift))
+        if ties <= thr:
+            return (kstar, q, shift, np_)
+        T += 8
+
+
+def _lib_plan(lib, norm_keys, n, slack=4):
+    import ctypes as C
+    nk = len(norm_keys)
+    bits = (C.c_int32 * nk)(*[int(int(k.max())).bit_length() for k in norm_keys])
+    S = min(n, 32768)
+    rows = (np.arange(S, dtype=object) * n // S).astype(np.int64)
+    sample = np.ascontiguousarray(np.stack([k[rows] for k in norm_keys], axis=1).astype(np.uint64))
+    out = [C.c_int32(0) for _ in range(4)]
+    on = lib.hark_debug_plan_truncation(n, nk, bits, sample.ctypes.data_as(C.POINTER(C.c_uint64)), S, slack,
+                                        *[C.byref(o) for o in out])
+    return tuple(o.value for o in out) if on else None
+
+
+def test_sort_truncation_planner_matches_its_python_restatement():
+    lib = hark_ffi.load_library()
+    rng = np.random.default_rng(23)
+
+    def norm(a):                      # ordkey - min for non-negative integer test data
+        a = a.astype(np.uint64)
+        return a - a.min()
+
+    n = 200003
+    cases = {
+        "config-4 shape": [norm(rng.integers(0, 1 << 20, n)), norm(rng.integers(0, 1 << 63, n, dtype=np.int64))],
+        "one wide key": [norm(rng.integers(0, 1 << 63, n, dtype=np.int64))],
+        "key boundary": [norm(rng.integers(0, 1 << 24, n)), norm(rng.integers(0, 1 << 62, n, dtype=np.int64))],
+        "duplicates": [norm(rng.integers(0, 1 << 62, 1000, dtype=np.int64)[rng.integers(0, 1000, n)])],
+        "two clusters": [norm(rng.integers(0, 1 << 20, n).astype(np.int64) + (np.arange(n) % 2) * (1 << 60))],
+        "narrow": [norm(rng.integers(0, 1 << 16, n)), norm(rng.integers(0, 1 << 8, n))],
+        "three keys": [norm(rng.integers(0, 8, n)), norm(rng.integers(0, 1 << 40, n, dtype=np.int64)),
+                       norm(rng.integers(0, 1 << 50, n, dtype=np.int64))],
+    }
+    got = {}
+    for name, keys in cases.items():
+        for slack in (0, 4):
+            exp = _py_plan(keys, n, slack)
+            got[(name, slack)] = _lib_plan(lib, keys, n, slack)
+            assert got[(name, slack)] == exp, (name, slack, got[(name, slack)], exp)
+    assert got[("config-4 shape", 4)] == (1, 1, 55, 4)        # 20 bits of key 0 (3 passes) + the top digit of the 63-bit key 1
+    assert got[("key boundary", 4)] == (0, 0, 0, 3)           # key 0 covers log2(n) + slack: key 1 is never sorted
+    assert got[("duplicates", 4)] is not None and got[("two clusters", 4)] is None and got[("narrow", 4)] is None
+
+
 # ---- table.py ----
 def test_table_loaders(tmp_path):
     assert getIndex(["a", "b"], "b") == 1 and getIndex(["a"], "z") == -1
