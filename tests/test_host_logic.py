@@ -444,6 +444,25 @@ def test_sort_truncation_planner_matches_its_python_restatement():
     assert got[("duplicates", 4)] is not None and got[("two clusters", 4)] is None and got[("narrow", 4)] is None
 
 
+def test_integration_c_example_compiles_and_links(tmp_path):
+    """INTEGRATION.md §C is a real C11 program against include/hark.h: compile it and link it against libhark.so."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    code = re.search(r"```c\n(.*?)```", text, re.S).group(1)
+    src = tmp_path / "client.c"
+    src.write_text(code)
+    libdir = os.path.join(ROOT, "harkdb_b200")
+    lib = tmp_path / "libhark.so"            # -lhark wants that name on the link line
+    os.symlink(os.path.join(libdir, "libhark.so"), lib)
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                        "-L", str(tmp_path), "-lhark", "-Wl,-rpath," + libdir, "-Wl,--allow-shlib-undefined",
+                        "-o", str(tmp_path / "client")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 # ---- table.py ----
 def test_table_loaders(tmp_path):
     assert getIndex(["a", "b"], "b") == 1 and getIndex(["a"], "z") == -1
