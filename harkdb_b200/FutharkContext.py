@@ -15,7 +15,7 @@ import numpy as np
 
 from .hark_ffi import DeviceTable, Futhark, I32, U32, I64
 from .parse import finalize_pred, sql_parse
-from .table import Table
+from .table import HostColumns, Table
 
 
 class FutharkContext:
@@ -47,11 +47,15 @@ class FutharkContext:
     def _is_int_col(self, t, col):
         if self._is_table(t):
             return t.dtypes[col] in (I32, U32, I64)
+        if isinstance(t, HostColumns):
+            return t[col].dtype.kind in "iub"
         return np.asarray(t).dtype.kind in "iub"
 
     def _is_u32_compatible(self, t):
         if self._is_table(t):
             return all(d in (I32, U32) for d in t.dtypes)
+        if isinstance(t, HostColumns):
+            return all(c.dtype in (np.int32, np.uint32) for c in t)
         a = np.asarray(t)
         return a.dtype.kind in "iub"
 
@@ -59,6 +63,8 @@ class FutharkContext:
         """(device table, temporary?)"""
         if self._is_table(t):
             return t, False
+        if isinstance(t, HostColumns):
+            return self.FutEnv.from_columns(list(t)), True
         from .table import entry_dtype
         return self.FutEnv.to_device(t, entry_dtype(np.asarray(t))), True
 
@@ -76,6 +82,16 @@ class FutharkContext:
     def sql(self, sql_statement):
         """sql_parse(tables, sql_statement) -> plan -> libhark entries -> 2-D ndarray."""
         val_dic = sql_parse(self.tables, sql_statement)
+        if isinstance(val_dic["table"], HostColumns) and "join" not in val_dic:
+            # not resident and one dtype per column: upload the columns for this query, then take the usual routes
+            dev, _ = self._as_device(val_dic["table"])
+            try:
+                return self._dispatch({**val_dic, "table": dev})
+            finally:
+                dev.free()
+        return self._dispatch(val_dic)
+
+    def _dispatch(self, val_dic):
         t1 = val_dic["table"]
         sel_cols = val_dic["select"]
         limit = val_dic.get("limit")

@@ -637,9 +637,13 @@ class ShardedEnv:
             if self.world == 1:
                 return self._wrap(self.engine.join(t1.local, t2.local, col1, col2, cols1, cols2))
             for t, c in ((t1, col1), (t2, col2)):
-                if t.dtypes[c] != U32:
-                    from .hark_ffi import HarkError
-                    raise HarkError(1, "sharded join: key columns must be stored as u32 (the reference's key order)")
+                # join.fut orders by the UNSIGNED key; the splitter exchange compares in the column's own order.  The two
+                # agree for u32 columns and for i32 columns without negative values (checked over all ranks).
+                if t.dtypes[c] == U32 or (t.dtypes[c] == I32 and self._all_nonnegative(t.local, c)):
+                    continue
+                from .hark_ffi import HarkError
+                raise HarkError(1, "sharded join: key columns must be u32, or i32 without negative values "
+                                   "(the reference orders by the unsigned key)")
             # splitters from both sides' keys, so neither side can overload a rank
             s1, w1 = self._samples(t1.local, [col1])
             s2, w2 = self._samples(t2.local, [col2])
@@ -660,6 +664,14 @@ class ShardedEnv:
                 t1.free()
             if tmp2:
                 t2.free()
+
+    def _all_nonnegative(self, local, col) -> bool:
+        import torch
+        k = self.engine.columns_torch(local)[col]
+        mn = torch.tensor([int(k.min().item()) if k.numel() else 0], dtype=torch.int64, device=k.device if k.numel() else self.engine.device)
+        if self.world > 1:
+            self.dist.all_reduce(mn, op=self.dist.ReduceOp.MIN, group=self.group)
+        return int(mn.item()) >= 0
 
     def _samples(self, local, key_cols):
         n_local = local.shape[0]

@@ -117,6 +117,12 @@ def entry_dtype(data: np.ndarray) -> np.dtype:
     raise Exception(f"Table dtype {data.dtype} is not numeric")
 
 
+class HostColumns(list):
+    """Handle of a table that is NOT resident and whose columns differ in dtype: its per-column host arrays (already
+    narrowed to their device dtypes).  FutharkContext uploads them for the one query, like the reference uploads its
+    homogeneous array on every query."""
+
+
 class Table:
     """A schema (list of column names) and a 2-D homogeneous array, optionally resident on the GPU."""
 
@@ -164,8 +170,13 @@ class Table:
         return [entry_dtype(self._data)] * self._data.shape[1]
 
     def get_handle(self):
-        """Resident device table if uploaded, else the host array (uploaded per query like the reference)."""
-        return self._device if self._device is not None else self._data
+        """Resident device table if uploaded, else the host data (uploaded per query like the reference): the
+        homogeneous array, or the per-column arrays when the columns differ in dtype."""
+        if self._device is not None:
+            return self._device
+        if self._columns is not None:
+            return HostColumns(c.astype(entry_dtype(c), copy=False) for c in self._columns)
+        return self._data
 
     def release(self):
         if self._device is not None:

@@ -315,6 +315,10 @@ def test_table_keeps_one_dtype_per_column(tmp_path):
     assert t.get_data().dtype == np.float64 and t.get_data().shape == (3, 4)      # what the reference would hold
     assert t.get_column_dtypes() == [np.int32, np.int64, np.float64, np.float32]
     assert Table("h", pd.DataFrame({"a": [1, 2], "b": [3, 4]})).get_column_dtypes() == [np.int32, np.int32]
+    from harkdb_b200.table import HostColumns
+    h = t.get_handle()                              # not resident: the per-column arrays, narrowed
+    assert isinstance(h, HostColumns) and [c.dtype for c in h] == [np.int32, np.int64, np.float64, np.float32]
+    assert isinstance(Table("h", pd.DataFrame({"a": [1, 2], "b": [3, 4]})).get_handle(), np.ndarray)
     at = pa.table({"a": [1, 2, 3], "b": [1.0, 2.0, 3.0]})
     ta = Table("a", at)
     assert ta.get_schema() == ["a", "b"] and ta.get_column_dtypes() == [np.int32, np.float64]

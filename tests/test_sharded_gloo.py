@@ -221,8 +221,6 @@ def _scn_sql_join(senv):
     g = j.groupby("attr", sort=True).agg(s=("val", "sum"), n=("val", "size")).reset_index()
     g = g[g.n > 50].sort_values(["s", "attr"], ascending=[False, True], kind="stable").head(5)
     assert out.tolist() == g[["attr", "s", "n"]].to_numpy().tolist(), (out.tolist(), g.to_numpy().tolist())
-    if senv.world > 1:        # the sharded reference join wants u32 key columns (unsigned splitter order); tables here are i32
-        return
     # plain join, reference row order (key, left row, right row), then ORDER BY over its output columns
     out = fc.sql("select f.fk, f.val, d.attr from fact f join dim d on f.fk = d.pk where f.qty = 19 and d.attr < 2 "
                  "order by d.attr desc, f.fk")          # (non-negative sort keys: the reference join's output is u32)
