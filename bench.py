@@ -17,7 +17,12 @@ Keys beyond the base contract:
                 uploaded (H2D), transposed, filtered and the result downloaded (D2H) inside every timed step
   cpu_baseline  oracle/oracle.c (a port of the reference's algorithm; Futhark cannot be built here) on the
                 box's host cores, bounded sample of the same workload
-`--impl reference` times that CPU port alone (all host threads) with the same metric/config.
+  queries       BASELINE configs 3, 4, 5 (GROUP BY / ORDER BY / JOIN + GROUP BY) and their §8(d) variants, each with rows,
+                ms, rows/s, roofline, check_ok and three CPU arms (cpu-ref-1t, cpu-ref-mt, cpu-best; tools/query_suite.py).
+                At WORLD_SIZE > 1 they run through harkdb_b200.sharded.ShardedEnv: weak and strong scaling, K8c peer
+                exchange and the NCCL exchange, per-phase ms, NVLink bytes, and `parity_ok` (sharded result == one-GPU
+                result on a reduced size, bit for bit).
+`--impl reference` times the CPU port alone (all host threads) with the same metric/config.
 """
 
 import argparse
@@ -140,14 +145,100 @@ def cpu_filter_setup(rows, threads):
 
 
 def cpu_filter_time(CO, db, out, threads, reps):
+    """cpu-ref: the reference's data model (one row-major table) filtered and projected in ONE pass per thread
+    (oracle/cpu_arms.c arm_filter_rowmajor_f32; the generic two-pass oracle_query_filter stays the checker)."""
     best = []
     n_out = 0
     for _ in range(reps):
         t0 = time.perf_counter()
-        res = CO.query_filter(db, SEL_COLS, PREDS, threads=threads, out=out)
+        _, _, _, n_out = CO.arm_filter_rowmajor_f32(db, PREDS[0][0], T_CONST, PREDS[1][0], U_CONST, SEL_COLS[0], SEL_COLS[1],
+                                                    threads, out=out)
         best.append(time.perf_counter() - t0)
-        n_out = res.shape[0]
     return best, n_out
+
+
+def cpu_filter_best(CO, rows, threads, reps=3):
+    """cpu-best: columnar (SoA) single pass with selection vectors; reads only the 3 columns the query touches."""
+    need = sorted(set(SEL_COLS) | {p[0] for p in PREDS})
+    cols = {c: CO.synth_column(F32, dict(kind=0), SEED, c, 0, rows, threads=threads) for c in need}
+    out = (np.empty(rows, np.float32), np.empty(rows, np.float32))
+    ts = []
+    for _ in range(reps + 1):
+        t0 = time.perf_counter()
+        CO.arm_filter_best_f32(cols, PREDS[0][0], T_CONST, PREDS[1][0], U_CONST, SEL_COLS[0], SEL_COLS[1], threads, out=out)
+        ts.append(time.perf_counter() - t0)
+    return rows / min(ts[1:])
+
+
+def _best_of(fn, reps=2):
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        ts.append(time.perf_counter() - t0)
+    return min(ts)
+
+
+def cpu_query_arms(which, threads, budget=1.0):
+    """The three CPU arms of BASELINE.md §3 for one query, on bounded samples of the same synthetic workload
+    (same generator and seeds).  rows/s each; N differs from the GPU run and is stated."""
+    from oracle import c_oracle as CO
+    I32_, I64_, F32_ = 0, 2, 3
+    n_ref, n_mt, n_best = int((1 << 21) * budget), int((1 << 23) * budget), int((1 << 25) * budget)
+    out = {"unit": "rows/s", "kind": "port", "cores": threads}
+    if which in ("groupby", "groupby_f32"):
+        kspec, vspec = dict(kind=0, lo=0, range=1 << 20), dict(kind=0, lo=0, range=1000)
+        key = CO.synth_column(I32_, kspec, 42, 0, 0, n_best, threads=threads)
+        if which == "groupby_f32":
+            val = CO.synth_column(F32_, dict(kind=0, flo=0.0, fhi=1.0), 42, 1, 0, n_best, threads=threads)
+        else:
+            val = CO.synth_column(I32_, vspec, 42, 1, 0, n_best, threads=threads)
+        out["best"] = {"rows": n_best, "rows_per_s": n_best / _best_of(lambda: CO.arm_groupby_best(key, val, 0, 1 << 20, threads)),
+                       "what": "dense-array aggregate, per-thread tables, SUM+COUNT (AVG = sum/count), OpenMP"}
+        ival = CO.synth_column(I32_, vspec, 42, 1, 0, n_mt, threads=threads)
+        rows = np.ascontiguousarray(np.stack([key[:n_mt].view(np.uint32), ival.view(np.uint32)], axis=1))
+        out["ref_mt"] = {"rows": n_mt, "rows_per_s": n_mt / _best_of(lambda: CO.arm_groupby_ref_mt(rows, [2], threads), 1),
+                         "what": "groupby.fut:8-22,55-58: 32 one-bit passes over rows, parallel split per pass, u32 SUM only"}
+        r1 = rows[:n_ref]
+        out["ref_1t"] = {"rows": n_ref, "rows_per_s": n_ref / _best_of(lambda: CO.query_groupby(r1, 0, [1], [2]), 1),
+                         "what": "oracle.c oracle_query_groupby_u32 (the same algorithm, 1 thread, like `futhark c`)"}
+    elif which == "orderby":
+        a = CO.synth_column(I64_, dict(kind=0, lo=-(2 ** 19), range=2 ** 20), 42, 0, 0, n_best, threads=threads)
+        b = CO.synth_column(I64_, dict(kind=0, lo=0, range=0), 42, 1, 0, n_best, threads=threads)
+        out["best"] = {"rows": n_best, "rows_per_s": n_best / _best_of(lambda: CO.arm_orderby_i64x2(a, b, 8, threads), 1),
+                       "what": "stable LSD radix sort, 8-bit digits trimmed to the key ranges, per-thread histograms, OpenMP"}
+        out["ref_mt"] = {"rows": n_mt, "rows_per_s": n_mt / _best_of(lambda: CO.arm_orderby_i64x2(a[:n_mt], b[:n_mt], 1, threads), 1),
+                         "what": "the reference's rsort (one stable split per key bit, groupby.fut:8-22) generalised to two i64 "
+                                 "keys, parallel split; the reference has no ORDER BY operator"}
+        out["ref_1t"] = {"rows": n_ref, "rows_per_s": n_ref / _best_of(lambda: CO.arm_orderby_i64x2(a[:n_ref], b[:n_ref], 1, 1), 1),
+                         "what": "same, 1 thread"}
+    elif which == "join_groupby":
+        nd = max(n_best // 40, 1024)
+        aa = 2654435761
+        while np.gcd(aa, nd) != 1:
+            aa += 2
+        pk = CO.synth_column(I32_, dict(kind=1, a=aa, b=12345, range=nd), 7, 0, 0, nd, threads=threads)
+        attr = CO.synth_column(I32_, dict(kind=0, lo=0, range=1024), 7, 1, 0, nd, threads=threads)
+        fk = CO.synth_column(I32_, dict(kind=0, lo=0, range=nd), 42, 0, 0, n_best, threads=threads)
+        val = CO.synth_column(I32_, dict(kind=0, lo=0, range=1000), 42, 1, 0, n_best, threads=threads)
+        out["best"] = {"rows": n_best, "dim_rows": nd,
+                       "rows_per_s": n_best / _best_of(lambda: CO.arm_join_groupby_best(fk, val, pk, attr, threads)),
+                       "what": "direct-address lookup build + probe, per-thread aggregate tables, OpenMP"}
+        n1 = n_ref // 2
+        nd1 = max(n1 // 40, 64)
+        db2 = np.ascontiguousarray(np.stack([(np.arange(nd1, dtype=np.uint64) * 48271 % nd1).astype(np.uint32),
+                                             attr[:nd1].view(np.uint32)], axis=1))
+        db1 = np.ascontiguousarray(np.stack([(fk[:n1].astype(np.int64) % nd1).astype(np.uint32), val[:n1].view(np.uint32)], axis=1))
+
+        def ref():
+            j = CO.join(db1, db2, 0, 0, [1], [1])            # join.fut:52-75 (sort of tagged triples, 32 passes)
+            CO.query_groupby(j, 1, [0], [2])                 # then groupby.fut on the joined rows
+        out["ref_1t"] = {"rows": n1, "dim_rows": nd1, "rows_per_s": n1 / _best_of(ref, 1),
+                         "what": "oracle.c oracle_join_u32 (join.fut:52-75) followed by oracle_query_groupby_u32, 1 thread"}
+        out["ref_mt"] = None
+    out["value"] = (out.get("ref_mt") or out["ref_1t"])["rows_per_s"]
+    out["sample"] = "bounded samples of the same synthetic workload; see rows in each arm"
+    return out
 
 
 def host_threads():
@@ -211,7 +302,9 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
 
     from harkdb_b200 import hark_ffi
-    env = hark_ffi.Futhark(device=local_rank, stream=hark_ffi.torch_stream_handle())   # torch events see libhark's kernels
+    from harkdb_b200.sharded import HarkEngine
+    eng = HarkEngine(local_rank)      # one libhark context per process, launching on torch's stream: torch events see its kernels
+    env = eng.env
     if args.filter_ctas_per_sm:
         env.set_option("filter.ctas_per_sm", args.filter_ctas_per_sm)
     if args.filter_impl:
@@ -358,6 +451,11 @@ def run_gpu_arm(args):
 
     table.free()
     env.sync()
+    torch.cuda.empty_cache()
+
+    queries = None
+    if not args.no_queries:
+        queries = run_queries(args, eng, world, rank)
 
     if rank != 0:
         if world > 1:
@@ -387,19 +485,95 @@ def run_gpu_arm(args):
     }
     if e2e:
         line["e2e"] = e2e
+    if queries is not None:
+        line["queries"] = queries
     if world == 1 and not args.no_cpu:
         threads = host_threads()
         COm, db, out = cpu_filter_setup(args.cpu_rows, threads)
         cpu_filter_time(COm, db, out, threads, 1)
         times, _ = cpu_filter_time(COm, db, out, threads, 3)
         t1, _ = cpu_filter_time(COm, db, out, 1, 1)
+        del db, out
         line["cpu_baseline"] = {"value": args.cpu_rows / min(times), "unit": "rows/s", "cores": threads, "kind": "port",
                                 "sample": f"{args.cpu_rows} rows x 8 f32 (same generator, seed {SEED}), best of 3",
-                                "value_1_thread": args.cpu_rows / min(t1)}
+                                "arm": "cpu-ref-mt: row-major table (the reference's data model), one pass per thread, OpenMP",
+                                "value_1_thread": args.cpu_rows / min(t1),
+                                "cpu_best": {"value": cpu_filter_best(COm, args.cpu_rows, threads), "cores": threads,
+                                             "what": "columnar single pass with selection vectors (reads 3 of the 8 columns)"}}
+        if queries is not None:
+            for name, arm in (("groupby_cfg3", "groupby"), ("groupby_cfg3_f32", "groupby_f32"), ("orderby_cfg4", "orderby"),
+                              ("join_groupby_cfg5", "join_groupby")):
+                if isinstance(queries.get(name), dict):
+                    try:
+                        queries[name]["cpu_baseline"] = cpu_query_arms(arm, threads, args.cpu_budget)
+                    except Exception as ex:
+                        queries[name]["cpu_baseline"] = {"error": repr(ex)[:200]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def run_queries(args, eng, world, rank):
+    """BASELINE configs 3-5 under the same clock discipline as the headline (tools/query_suite.py)."""
+    import torch
+    from tools.query_suite import Suite
+    peak, _ = measured_peak()
+    env = eng.env
+    out = {}
+
+    def guarded(name, fn):
+        try:
+            out[name] = fn()
+        except Exception as ex:       # one operator failing (e.g. out of memory) must not hide the others
+            out[name] = {"error": repr(ex)[:300]}
+        torch.cuda.empty_cache()
+
+    if world == 1:
+        su = Suite(env, 1, 0, None, peak, args.query_reps, args.query_scale)
+        guarded("groupby_cfg3", lambda: su.groupby())
+        guarded("groupby_cfg3_f32", lambda: su.groupby(f32=True))
+        guarded("groupby_cfg3_zipf", lambda: su.groupby(zipf=True))
+        guarded("orderby_cfg4", lambda: su.orderby())
+        guarded("join_groupby_cfg5", lambda: su.join_groupby())
+        guarded("join_groupby_cfg5_half_match", lambda: su.join_groupby(half=True))
+        guarded("join_groupby_cfg5_sparse_pk", lambda: su.join_groupby(sparse=True))
+        guarded("join_entry_ref_order", lambda: su.join_entry())
+        return out
+
+    from harkdb_b200.sharded import ShardedEnv
+    modes = [("k8c_peer", True)] + ([("nccl", False)] if not args.no_nccl_arm else [])
+    for label, peer in modes:
+        senv = ShardedEnv(eng, peer=peer)
+        su = Suite(env, world, rank, senv, peak, args.query_reps, args.query_scale)
+        res = {"exchange": "K8c peer stores over NVLink" if senv.peer else "K8b partition + NCCL all_to_all"}
+        if peer and not senv.peer:
+            res["note"] = "CUDA IPC peer arenas unavailable: this arm ran the NCCL exchange"
+
+        def sub(name, fn, res=res):
+            try:
+                res[name] = fn()
+            except Exception as ex:
+                res[name] = {"error": repr(ex)[:300]}
+            torch.cuda.empty_cache()
+
+        sub("parity_ok", su.parity)
+        for mode in ("weak", "strong"):
+            sub("groupby_cfg3_" + mode, lambda: su.groupby(mode))
+            sub("orderby_cfg4_" + mode, lambda: su.orderby(mode, weak_rows=5 * 10 ** 8))
+            sub("join_groupby_cfg5_" + mode, lambda: su.join_groupby(mode))
+        if peer:
+            sub("groupby_cfg3_f32_weak", lambda: su.groupby("weak", f32=True))
+        out[label] = res
+        if senv.peer:
+            try:
+                eng.env.peer_arena_close()
+            except Exception:
+                pass
+        del senv
+    out["note"] = ("weak: every GPU holds a whole single-GPU configuration (ORDER BY: 0.5e9 rows per GPU); strong: the "
+                   "configuration's rows divided over the GPUs.  ms = median of the runs, max over ranks.")
+    return out
 
 
 def main():
@@ -415,6 +589,11 @@ def main():
     ap.add_argument("--e2e-warmup", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-queries", action="store_true", help="skip the per-query suite (configs 3-5)")
+    ap.add_argument("--no-nccl-arm", action="store_true", help="N > 1: skip the second pass with the NCCL exchange")
+    ap.add_argument("--query-reps", type=int, default=3)
+    ap.add_argument("--query-scale", type=float, default=1.0, help="fraction of each BASELINE configuration's rows")
+    ap.add_argument("--cpu-budget", type=float, default=2.0, help="scales the CPU arms' sample sizes")
     ap.add_argument("--filter-ctas-per-sm", type=int, default=0)
     ap.add_argument("--filter-impl", type=int, default=0, help="0 = v2 (default), 1 = v1 per-tile kernel, 3 = v2 runtime counts")
     args = ap.parse_args()

@@ -567,6 +567,11 @@ __global__ void __launch_bounds__(256) hk_synth_kernel(void *__restrict__ out, i
             iv = v;
             fv = (double)v;
             ffv = (float)v;
+        } else if (spec.kind == HARK_GEN_AFFINE_UNIFORM) {
+            const uint64_t v = spec.a * __umul64hi(hk_mix64(seed, (uint64_t)col, r), spec.range) + spec.b;
+            iv = v;
+            fv = (double)v;
+            ffv = (float)v;
         } else if (spec.kind == HARK_GEN_LOGUNIFORM) {
             const uint64_t range = spec.range < 2 ? 2 : spec.range;
             const int nb = 63 - __clzll((long long)range); // floor(log2 range) >= 1
@@ -598,7 +603,7 @@ extern "C" int hark_table_synth(hark_ctx *ctx, hark_table **out, int64_t n, int6
     HK_ARG(ctx, out && n >= 0 && m >= 0 && (m == 0 || (dtypes && specs)), "table_synth: bad argument");
     for (int64_t c = 0; c < m; c++) {
         HK_ARG(ctx, hk_dtype_ok(dtypes[c]), "table_synth: bad dtype");
-        HK_ARG(ctx, specs[c].kind >= HARK_GEN_UNIFORM && specs[c].kind <= HARK_GEN_LOGUNIFORM, "table_synth: bad kind");
+        HK_ARG(ctx, specs[c].kind >= HARK_GEN_UNIFORM && specs[c].kind <= HARK_GEN_AFFINE_UNIFORM, "table_synth: bad kind");
     }
     hark_table *t = nullptr;
     HK_TRY(hk_table_alloc(ctx, &t, n, n, dtypes, m));

@@ -275,7 +275,8 @@ class ShardTable:
 class ShardedEnv:
     """Same call surface as hark_ffi.Futhark, over row-range shards (see module docstring)."""
 
-    def __init__(self, engine, group=None, oversample: int = 64, trace: Optional[bool] = None):
+    def __init__(self, engine, group=None, oversample: int = 64, trace: Optional[bool] = None,
+                 peer: Optional[bool] = None):
         import os
         import torch.distributed as dist
         self.dist = dist
@@ -290,7 +291,8 @@ class ShardedEnv:
         # K8c peer-memory exchange: on when the engine offers it and CUDA IPC works (HARK_PEER=0 forces NCCL;
         # HARK_PEER_ARENA_GB sizes the receive arena, default 24)
         self.peer = False
-        if self.world > 1 and hasattr(engine, "peer_setup") and os.environ.get("HARK_PEER", "1") != "0":
+        want_peer = os.environ.get("HARK_PEER", "1") != "0" if peer is None else bool(peer)
+        if self.world > 1 and hasattr(engine, "peer_setup") and want_peer:
             gb = float(os.environ.get("HARK_PEER_ARENA_GB", "24"))
             self.peer = bool(engine.peer_setup(self, int(gb * (1 << 30))))
 

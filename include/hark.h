@@ -86,6 +86,9 @@ typedef enum {
     HARK_GEN_AFFINE = 1,  /* ((a*r + b) mod 2^64) mod range (range 0: no mod) — unique keys when
                              gcd(a, range) = 1 and a*r+b does not wrap                       */
     HARK_GEN_CONST = 2,   /* lo (ints) / flo (floats)                                         */
+    HARK_GEN_AFFINE_UNIFORM = 4, /* a * mulhi64(h, range) + b (wrapping, truncated to the dtype): a uniform draw from the key
+                             set {a*j + b : 0 <= j < range} — the foreign keys of a dimension whose primary key is
+                             HARK_GEN_AFFINE with the same a, b and range 0 (sparse keys when a is large and odd)      */
     HARK_GEN_LOGUNIFORM = 3 /* skewed keys, integer arithmetic only: octave e = mulhi64(h, floor(log2 range))
                              uniform, then uniform inside the octave: k = 2^e + (h2 & (2^e - 1)) - 1, value =
                              lo + k mod range, h2 = hark_mix64(seed ^ 0x5851F42D4C957F2D, c, r).  P(k) ~ 1/(k+1):

@@ -191,3 +191,98 @@ def synth_column(dtype: int, spec: dict, seed: int, col: int, row0: int, n: int,
     if rc:
         raise ValueError("bad dtype")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arms timed by bench.py (oracle/cpu_arms.c): cpu-ref-mt and cpu-best.  Each returns what the query returns,
+# so tests/test_cpu_arms.py can hold them to np_oracle.
+# ------------------------------------------------------------------------------------------------
+def arm_filter_best_f32(cols, p0, c0, p1, c1, s0, s1, threads=1, out=None):
+    """SELECT s0, s1 WHERE p0 > c0 AND p1 < c1 over f32 SoA columns.  -> (out0, out1, chunk starts, chunk counts)."""
+    n = len(cols[0])
+    T = max(1, int(threads))
+    o0, o1 = out if out is not None else (np.empty(n, np.float32), np.empty(n, np.float32))
+    counts = np.zeros(T, dtype=np.int64)
+    f = lib().arm_filter_best_f32
+    f.restype = C.c_int64
+    total = f(_p(cols[p0]), C.c_float(c0), _p(cols[p1]), C.c_float(c1), _p(cols[s0]), _p(cols[s1]), C.c_int64(n), _p(o0),
+              _p(o1), _p(counts), C.c_int32(T))
+    starts = np.array([n * t // T for t in range(T)], dtype=np.int64)
+    return o0, o1, starts, counts, int(total)
+
+
+def arm_filter_rowmajor_f32(db, p0, c0, p1, c1, s0, s1, threads=1, out=None):
+    db = np.ascontiguousarray(db, dtype=np.float32)
+    n, m = db.shape
+    T = max(1, int(threads))
+    o = out if out is not None else np.empty((n, 2), np.float32)
+    counts = np.zeros(T, dtype=np.int64)
+    f = lib().arm_filter_rowmajor_f32
+    f.restype = C.c_int64
+    total = f(_p(db), C.c_int64(n), C.c_int64(m), C.c_int32(p0), C.c_float(c0), C.c_int32(p1), C.c_float(c1), C.c_int32(s0),
+              C.c_int32(s1), _p(o), _p(counts), C.c_int32(T))
+    starts = np.array([n * t // T for t in range(T)], dtype=np.int64)
+    return o, starts, counts, int(total)
+
+
+def chunks_concat(arr, starts, counts):
+    return np.concatenate([arr[s:s + c] for s, c in zip(starts, counts)]) if len(starts) else arr[:0]
+
+
+def arm_groupby_best(key, val, kmin, krange, threads=1):
+    """-> (count[krange] i64, sum[krange] i64 or f64) over the dense key range."""
+    key = np.ascontiguousarray(key, dtype=np.int32)
+    cnt = np.empty(krange, dtype=np.int64)
+    if val.dtype == np.float32:
+        s = np.empty(krange, dtype=np.float64)
+        rc = lib().arm_groupby_best_f32(_p(key), _p(np.ascontiguousarray(val)), C.c_int64(len(key)), C.c_int32(kmin),
+                                        C.c_int64(krange), _p(cnt), _p(s), C.c_int32(threads))
+    else:
+        s = np.empty(krange, dtype=np.int64)
+        rc = lib().arm_groupby_best_i32(_p(key), _p(np.ascontiguousarray(val, dtype=np.int32)), C.c_int64(len(key)),
+                                        C.c_int32(kmin), C.c_int64(krange), _p(cnt), _p(s), C.c_int32(threads))
+    if rc:
+        raise MemoryError("arm_groupby_best")
+    return cnt, s
+
+
+def arm_groupby_ref_mt(rows, t_cols, threads=1):
+    """rows [n][1+c] u32 (column 0 = key) -> [G][1+c] u32, groupby.fut semantics, 32 parallelised one-bit passes."""
+    rows = np.ascontiguousarray(rows, dtype=np.uint32)
+    n, s = rows.shape
+    t = _i32(t_cols)
+    out = np.empty((max(n, 1), s), dtype=np.uint32)
+    f = lib().arm_groupby_ref_mt
+    f.restype = C.c_int64
+    g = f(_p(rows), C.c_int64(n), C.c_int64(s), _p(t), _p(out), C.c_int32(threads))
+    if g < 0:
+        raise MemoryError("arm_groupby_ref_mt")
+    return out[:g].copy()
+
+
+def arm_orderby_i64x2(a, b, digit_bits=8, threads=1):
+    """Stable ORDER BY a, b (ascending, signed); returns sorted copies."""
+    a = np.array(a, dtype=np.int64)
+    b = np.array(b, dtype=np.int64)
+    ta, tb = np.empty_like(a), np.empty_like(b)
+    rc = lib().arm_orderby_i64x2(_p(a), _p(b), C.c_int64(len(a)), _p(ta), _p(tb), C.c_int32(digit_bits), C.c_int32(threads))
+    if rc:
+        raise MemoryError("arm_orderby")
+    return a, b
+
+
+def arm_join_groupby_best(fk, val, pk, attr, threads=1):
+    """-> (attr values present, sum i64, count i64), ascending attr; unmatched fact rows drop out."""
+    fk, val = np.ascontiguousarray(fk, np.int32), np.ascontiguousarray(val, np.int32)
+    pk, attr = np.ascontiguousarray(pk, np.int32), np.ascontiguousarray(attr, np.int32)
+    pk_min, pk_span = int(pk.min()), int(pk.max()) - int(pk.min()) + 1
+    g_min, g_range = int(attr.min()), int(attr.max()) - int(attr.min()) + 1
+    lut = np.empty(pk_span, dtype=np.int32)
+    cnt, s = np.empty(g_range, np.int64), np.empty(g_range, np.int64)
+    rc = lib().arm_join_groupby_best(_p(fk), _p(val), C.c_int64(len(fk)), _p(pk), _p(attr), C.c_int64(len(pk)),
+                                     C.c_int64(pk_min), C.c_int64(pk_span), C.c_int32(g_min), C.c_int64(g_range), _p(lut),
+                                     _p(cnt), _p(s), C.c_int32(threads))
+    if rc:
+        raise MemoryError("arm_join_groupby_best")
+    keep = cnt > 0
+    return (np.arange(g_range, dtype=np.int64) + g_min)[keep].astype(np.int32), s[keep], cnt[keep]

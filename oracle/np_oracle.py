@@ -31,7 +31,7 @@ DTYPE_CODES = {np.dtype(v): k for k, v in NP_DTYPES.items()}
 
 GT, GE, LT, LE, EQ, NE = 0, 1, 2, 3, 4, 5
 AGG_KEY, AGG_PROD, AGG_SUM, AGG_MAX, AGG_MIN, AGG_COUNT, AGG_AVG, AGG_SUMF64 = 0, 1, 2, 3, 4, 5, 6, 7
-GEN_UNIFORM, GEN_AFFINE, GEN_CONST, GEN_LOGUNIFORM = 0, 1, 2, 3
+GEN_UNIFORM, GEN_AFFINE, GEN_CONST, GEN_LOGUNIFORM, GEN_AFFINE_UNIFORM = 0, 1, 2, 3, 4
 
 Pred = Tuple[int, int, int, float]  # (col, op, ival, fval) — include/hark.h hark_pred
 
@@ -100,6 +100,10 @@ def synth_column(dtype: int, spec: dict, seed: int, col: int, row0: int, n: int)
             v = np.uint64(a) * rows + np.uint64(b)
             if rng:
                 v = v % np.uint64(rng)
+            if dtype in (F32, F64):
+                return v.astype(npdt)
+        elif kind == GEN_AFFINE_UNIFORM:
+            v = np.uint64(a) * _mulhi64(mix64(seed, col, rows), rng) + np.uint64(b)
             if dtype in (F32, F64):
                 return v.astype(npdt)
         elif kind == GEN_LOGUNIFORM:

@@ -467,6 +467,11 @@ int oracle_synth_column(int32_t dtype, const hark_colspec *spec, uint64_t seed, 
             iv = v; fv = (double)v; ffv = (float)v;
             break;
         }
+        case HARK_GEN_AFFINE_UNIFORM: {
+            uint64_t v = spec->a * mulhi64(oracle_mix64(seed, (uint64_t)col, r), spec->range) + spec->b;
+            iv = v; fv = (double)v; ffv = (float)v;
+            break;
+        }
         case HARK_GEN_LOGUNIFORM: {
             uint64_t range = spec->range < 2 ? 2 : spec->range;
             int nb = 63 - __builtin_clzll(range);

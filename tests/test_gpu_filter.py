@@ -70,7 +70,8 @@ def test_generator_matches_oracle(dtype):
     specs = [dict(kind=NO.GEN_UNIFORM, lo=-5, range=11), dict(kind=NO.GEN_UNIFORM, lo=0, range=0, flo=-2.0, fhi=3.0),
              dict(kind=NO.GEN_UNIFORM, lo=-(2 ** 19), range=2 ** 20), dict(kind=NO.GEN_AFFINE, a=7, b=3, range=1000),
              dict(kind=NO.GEN_CONST, lo=42, flo=4.25), dict(kind=NO.GEN_LOGUNIFORM, lo=-3, range=1 << 20),
-             dict(kind=NO.GEN_LOGUNIFORM, lo=5, range=1000)]
+             dict(kind=NO.GEN_LOGUNIFORM, lo=5, range=1000),
+             dict(kind=NO.GEN_AFFINE_UNIFORM, a=2654435761, b=977, range=100003)]
     n, row0 = 70001, 10 ** 9 - 5
     t = env.synth(n, [dtype] * len(specs), specs, seed=42, row0=row0)
     for c, spec in enumerate(specs):

@@ -116,7 +116,8 @@ def test_generator_c_vs_numpy(dtype):
              dict(kind=NO.GEN_UNIFORM, lo=-(2 ** 19), range=2 ** 20),
              dict(kind=NO.GEN_AFFINE, a=7, b=3, range=1000),
              dict(kind=NO.GEN_CONST, lo=42, flo=4.25), dict(kind=NO.GEN_LOGUNIFORM, lo=-3, range=1 << 20),
-             dict(kind=NO.GEN_LOGUNIFORM, lo=5, range=1000)]
+             dict(kind=NO.GEN_LOGUNIFORM, lo=5, range=1000),
+             dict(kind=NO.GEN_AFFINE_UNIFORM, a=2654435761, b=977, range=100003)]
     for col, spec in enumerate(specs):
         a = CO.synth_column(dtype, spec, 42, col, 10 ** 9 - 5, 300)
         b = NO.synth_column(dtype, spec, 42, col, 10 ** 9 - 5, 300)
