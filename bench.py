@@ -539,6 +539,8 @@ def run_queries(args, eng, world, rank):
         guarded("join_groupby_cfg5_half_match", lambda: su.join_groupby(half=True))
         guarded("join_groupby_cfg5_sparse_pk", lambda: su.join_groupby(sparse=True))
         guarded("join_entry_ref_order", lambda: su.join_entry())
+        guarded("join_hash_i32", lambda: su.join_hash())
+        guarded("join_hash_i64", lambda: su.join_hash(i64=True))
         return out
 
     from harkdb_b200.sharded import ShardedEnv

@@ -186,7 +186,8 @@ extern "C" int hark_context_set_option(hark_ctx *ctx, const char *key, int64_t v
     static const char *known[] = {"filter.impl", "filter.ctas_per_sm", "sort.ctas_per_sm", "groupby.impl",
                                   "join.impl",   "upload.chunk_mb",    "dense.log2_slots",  "dense.smem_bytes",
                                   "part.ctas_per_sm", "part.threads", "join.lut_slice_bytes", "sort.impl", "sort.rank", "stats.cache",
-                                  "sort.trunc", "sort.trunc_slack", nullptr};
+                                  "sort.trunc", "sort.trunc_slack", "dense.part_impl", "join.build", "dense.fixed_point",
+                                  "sort.digit_bits", nullptr};
     for (int i = 0; known[i]; i++)
         if (!strcmp(known[i], key)) {
             ctx->opts[key] = value;

@@ -81,6 +81,44 @@ __global__ void __launch_bounds__(256) hk_dminmax_kernel(const void *__restrict_
     }
 }
 
+// Zone map of an f32 column for exact fixed-point sums: out[0] = max exponent of the highest set bit, out[1] = min
+// exponent of the lowest set bit (both over non-zero values, biased by +1024 so that they fit unsigned atomics),
+// out[2] = number of non-finite values, out[3] = number of non-zero values.
+__global__ void __launch_bounds__(256) hk_f32_fxstats_kernel(const uint32_t *__restrict__ col, int64_t n, unsigned long long *out) {
+    int hi = -100000, lo = 100000;
+    unsigned long long bad = 0, any = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t b = __ldcs(col + i);
+        const uint32_t ex = (b >> 23) & 0xffu, fr = b & 0x7fffffu;
+        if (ex == 0xffu) {
+            bad++;
+            continue;
+        }
+        if (ex == 0u && fr == 0u) continue;
+        const uint32_t mant = ex ? (fr | 0x800000u) : fr;
+        const int e0 = (ex ? (int)ex : 1) - 127 - 23; // exponent of mantissa bit 0
+        hi = max(hi, e0 + 31 - __clz((int)mant));
+        lo = min(lo, e0 + __ffs((int)mant) - 1);
+        any++;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        hi = max(hi, __shfl_xor_sync(HK_FULL_MASK, hi, o));
+        lo = min(lo, __shfl_xor_sync(HK_FULL_MASK, lo, o));
+        bad += __shfl_xor_sync(HK_FULL_MASK, bad, o);
+        any += __shfl_xor_sync(HK_FULL_MASK, any, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (any) {
+            atomicMax(out, (unsigned long long)(hi + 1024));
+            atomicMin(out + 1, (unsigned long long)(lo + 1024));
+            atomicAdd(out + 3, any);
+        }
+        if (bad) atomicAdd(out + 2, bad);
+    }
+}
+
 constexpr int PMAXV = 3; // value arrays the partition pass can carry (partition.cu)
 
 // ------------------------------------------------------------------------------------------------
@@ -98,14 +136,17 @@ enum AccKind {
     A_FPROD,      // f32 -> f64 product
     A_MINU, A_MAXU, A_MINS, A_MAXS,   // 32-bit integer min / max
     A_MINF, A_MAXF,                   // f32 min / max (fminf / fmaxf: NaN ignored, like the sort path)
-    A_PROD32      // u32 wrap-around product
+    A_PROD32,     // u32 wrap-around product
+    A_FXSUM32,    // f32 -> exact fixed point, |v| / 2^lo < 2^31: one 32-bit addend per row (table and global as A_SUM64S)
+    A_FXSUM64     // f32 -> exact fixed point with 64-bit addends (two table atomics per row)
 };
 
 struct DAcc {
     int vcol;
     int kind;
-    int word;   // first table word (units of K u32)
-    void *gacc; // dense global accumulator [R]
+    int word;     // first table word (units of K u32)
+    void *gacc;   // dense global accumulator [R]
+    float fscale; // A_FXSUM*: 2^-lo, the value's fixed-point representation is v * fscale (an integer, exactly)
 };
 
 struct DAggParams {
@@ -126,6 +167,15 @@ struct DAggParams {
     DAcc acc[AMAXACC];
     unsigned long long *gcnt; // [R]
     int64_t chunk;            // rows per chunk (multiple of 4)
+    // K8t input (hk_dagg_tiles_kernel): the table as tile blocks sorted by bin + a directory (partition.cu)
+    const uint32_t *t_rows;
+    const uint32_t *t_dir;
+    long long t_num_tiles;
+    const unsigned long long *t_cum; // MODE 0: exclusive row prefix over (bin, block of TBLK tiles), bin-major, [nbins * t_nblk + 1]
+    long long t_nblk;
+    // hash mode (join + GROUP BY over sparse keys, join.cu): open addressing, slot + 1 in the entry, 0 = empty
+    const void *htab;
+    unsigned long long hmask;
 };
 
 __device__ __forceinline__ uint32_t acc_identity(int kind, int w /* 0 or 1 for two-word kinds */) {
@@ -152,7 +202,7 @@ __device__ __forceinline__ void smem_f64_update(unsigned long long *a, double v,
 
 // one row into the CTA's table (KIND is a compile-time AccKind: the switch over kinds sits outside the row loops)
 template <int KIND>
-__device__ __forceinline__ void acc_row(uint32_t *tab, uint32_t K, uint32_t idx, int word, uint32_t x) {
+__device__ __forceinline__ void acc_row(uint32_t *tab, uint32_t K, uint32_t idx, int word, uint32_t x, uint32_t xhi = 0) {
     uint32_t *w0 = tab + (size_t)word * K + idx;
     if constexpr (KIND == A_SUM32) {
         atomicAdd(w0, x);
@@ -163,6 +213,9 @@ __device__ __forceinline__ void acc_row(uint32_t *tab, uint32_t K, uint32_t idx,
     } else if constexpr (KIND == A_SUM64U) {
         const uint32_t old = atomicAdd(w0, x);
         if ((uint32_t)(old + x) < old) atomicAdd(w0 + K, 1u);
+    } else if constexpr (KIND == A_FXSUM64) { // x = low word here; the high word travels in `xhi`
+        const uint32_t old = atomicAdd(w0, x);
+        atomicAdd(w0 + K, xhi + (uint32_t)((uint32_t)(old + x) < old));
     } else if constexpr (KIND == A_FSUM || KIND == A_FPROD) {
         smem_f64_update(reinterpret_cast<unsigned long long *>(tab + (size_t)word * K) + idx, (double)__uint_as_float(x), KIND == A_FPROD);
     } else if constexpr (KIND == A_MINU) {
@@ -200,10 +253,30 @@ __device__ __forceinline__ void acc_rows(uint32_t *tab, uint32_t K, const uint32
             if (idx[u][e] != 0xffffffffu) acc_row<KIND>(tab, K, idx[u][e], word, x[u][e]);
 }
 
+// f32 bits -> the exact fixed-point integer v * fscale
+__device__ __forceinline__ long long fx_of(uint32_t bits, float fscale) { return __float2ll_rn(__uint_as_float(bits) * fscale); }
+
 template <int U>
 __device__ __forceinline__ void acc_dispatch(uint32_t *tab, uint32_t K, const uint32_t (&idx)[U][4], int kind, int word,
-                                             const uint32_t (&x)[U][4]) {
+                                             const uint32_t (&x)[U][4], float fscale) {
     switch (kind) {
+    case A_FXSUM32:
+#pragma unroll
+        for (int u = 0; u < U; u++)
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+                if (idx[u][e] != 0xffffffffu) acc_row<A_SUM64S>(tab, K, idx[u][e], word, (uint32_t)(int32_t)fx_of(x[u][e], fscale));
+        break;
+    case A_FXSUM64:
+#pragma unroll
+        for (int u = 0; u < U; u++)
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+                if (idx[u][e] != 0xffffffffu) {
+                    const unsigned long long v = (unsigned long long)fx_of(x[u][e], fscale);
+                    acc_row<A_FXSUM64>(tab, K, idx[u][e], word, (uint32_t)v, (uint32_t)(v >> 32));
+                }
+        break;
     case A_SUM32: acc_rows<A_SUM32, U>(tab, K, idx, word, x); break;
     case A_SUM64S: acc_rows<A_SUM64S, U>(tab, K, idx, word, x); break;
     case A_SUM64U: acc_rows<A_SUM64U, U>(tab, K, idx, word, x); break;
@@ -234,7 +307,9 @@ __device__ __forceinline__ void flush_slot(uint32_t *tab, uint32_t K, uint32_t i
             *w0 = 0;
             break;
         case A_SUM64S:
-        case A_SUM64U: {
+        case A_SUM64U:
+        case A_FXSUM32:
+        case A_FXSUM64: {
             const unsigned long long v = ((unsigned long long)(long long)(int32_t)w0[K] << 32) + (unsigned long long)*w0;
             atomicAdd(reinterpret_cast<unsigned long long *>(a.gacc) + r, v);
             *w0 = 0;
@@ -305,8 +380,12 @@ __device__ __forceinline__ void load_keys4(const typename KRaw<KW>::T *p, int64_
     }
 }
 
+template <int KW>
+__device__ __forceinline__ uint32_t hash_probe(const void *htab, uint64_t hmask, typename KRaw<KW>::T key);
+
 // One iteration of the row loop: U 4-row groups per thread.  CHECK = the groups may straddle [r0, r1).
-template <int KW, bool LUT, int NV, int U, bool CHECK>
+// MODE: 0 slot = key - first key of the bucket, 1 slot from the direct-address lookup, 2 slot from the hash table.
+template <int KW, int MODE, int NV, int U, bool CHECK>
 __device__ __forceinline__ void dagg_step(const DAggParams &P, uint32_t *tab, const typename KRaw<KW>::T *keyp, int64_t g0,
                                           int64_t r0, int64_t r1, uint64_t slot0, int tid) {
     using KT = typename KRaw<KW>::T;
@@ -334,11 +413,13 @@ __device__ __forceinline__ void dagg_step(const DAggParams &P, uint32_t *tab, co
         for (int e = 0; e < 4; e++) {
             idx[u][e] = 0xffffffffu;
             if (!CHECK || (rr[u] + e >= r0 && rr[u] + e < r1)) {
-                if (LUT) {
+                if constexpr (MODE == 1) {
                     long long v;
                     if constexpr (KW == 4) v = (P.key_dtype == HARK_U32 ? (long long)(uint32_t)k[u][e] : (long long)(int32_t)k[u][e]) - P.pk_min;
                     else v = (long long)k[u][e] - P.pk_min;
                     if (v >= 0 && v < P.pk_span) idx[u][e] = __ldg(P.lut + v) - 1u; // 0 (no match) -> 0xffffffff
+                } else if constexpr (MODE == 2) {
+                    idx[u][e] = hash_probe<KW>(P.htab, P.hmask, k[u][e]);
                 } else {
                     idx[u][e] = (uint32_t)(ordkey_of<KW>(k[u][e], P.key_dtype) - P.g_lo - slot0);
                 }
@@ -348,18 +429,19 @@ __device__ __forceinline__ void dagg_step(const DAggParams &P, uint32_t *tab, co
     for (int u = 0; u < U; u++)
 #pragma unroll
         for (int e = 0; e < 4; e++)
-            if ((!CHECK && !LUT) || idx[u][e] != 0xffffffffu) atomicAdd(&tab[idx[u][e]], 1u);
+            if ((!CHECK && MODE == 0) || idx[u][e] != 0xffffffffu) atomicAdd(&tab[idx[u][e]], 1u);
 #pragma unroll 1
     for (int ai = 0; ai < P.nacc; ai++) {
         const int kind = P.acc[ai].kind, word = P.acc[ai].word, vcol = P.acc[ai].vcol;
 #pragma unroll
         for (int v = 0; v < NV; v++)
-            if (v == vcol) acc_dispatch<U>(tab, P.K, idx, kind, word, x[v]);
+            if (v == vcol) acc_dispatch<U>(tab, P.K, idx, kind, word, x[v], P.acc[ai].fscale);
     }
 }
 
-template <int KW, bool LUT, int NV>
+template <int KW, int MODE, int NV>
 __global__ void __launch_bounds__(dagg_threads(NV), 1) hk_dagg_kernel(const __grid_constant__ DAggParams P) {
+    constexpr bool LUT = MODE != 0;
     using KT = typename KRaw<KW>::T;
     constexpr int AT = dagg_threads(NV);
     constexpr int U = NV <= 1 ? 2 : 2; // 4-row groups per thread and iteration (all their loads are in flight together)
@@ -373,7 +455,7 @@ __global__ void __launch_bounds__(dagg_threads(NV), 1) hk_dagg_kernel(const __gr
     for (uint32_t i = tid; i < K; i += AT) tab[i] = 0;
     for (int ai = 0; ai < P.nacc; ai++) {
         const DAcc &a = P.acc[ai];
-        const int two = (a.kind == A_SUM64S || a.kind == A_SUM64U) ? 2 : 1;
+        const int two = (a.kind == A_SUM64S || a.kind == A_SUM64U || a.kind == A_FXSUM32 || a.kind == A_FXSUM64) ? 2 : 1;
         if (a.kind == A_FSUM || a.kind == A_FPROD) {
             unsigned long long *p = reinterpret_cast<unsigned long long *>(tab + (size_t)a.word * K);
             for (uint32_t i = tid; i < K; i += AT) p[i] = a.kind == A_FPROD ? 0x3ff0000000000000ull : 0ull;
@@ -421,13 +503,255 @@ __global__ void __launch_bounds__(dagg_threads(NV), 1) hk_dagg_kernel(const __gr
         const uint64_t slot0 = LUT ? 0ull : ((uint64_t)b << P.shift);
         constexpr int64_t STEP = (int64_t)AT * 4 * U;
         for (int64_t g0 = r0 & ~(int64_t)3; g0 < r1; g0 += STEP) {
-            if (g0 >= r0 && g0 + STEP <= r1) dagg_step<KW, LUT, NV, U, false>(P, tab, keyp, g0, r0, r1, slot0, tid);
-            else dagg_step<KW, LUT, NV, U, true>(P, tab, keyp, g0, r0, r1, slot0, tid);
+            if (g0 >= r0 && g0 + STEP <= r1) dagg_step<KW, MODE, NV, U, false>(P, tab, keyp, g0, r0, r1, slot0, tid);
+            else dagg_step<KW, MODE, NV, U, true>(P, tab, keyp, g0, r0, r1, slot0, tid);
         }
     }
     __syncthreads();
     if (cur_bucket >= 0)
         for (uint32_t i = tid; i < K; i += AT) flush_slot(tab, K, i, ((uint64_t)cur_bucket << P.shift) + i, P);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 over K8t's tile blocks.  Work unit = the run of one bin inside one tile (a "segment", on average
+// 4096 / nbins rows, contiguous, array-of-structs); a warp takes TG segments of the same bin at a time and keeps the
+// directory words of all of them, then 2 row loads per segment and lane, in flight together.
+//   MODE 0 (GROUP BY)  units are bin-major; every CTA owns a contiguous range of them, so it changes bin (and merges
+//                      its table into the global accumulators) at most a few times; slot = key - bin's first key;
+//   MODE 1 (lookup)    slot + 1 = lut[fk - pk_min]; units are dealt round-robin in bin-major order so that all CTAs
+//                      probe the same slice of the lookup at the same time (the slice stays L2-resident);
+//   MODE 2 (hash)      slot + 1 = the entry of an open-addressing table keyed by hk_hash_key (join.cu), same dealing.
+// ------------------------------------------------------------------------------------------------
+constexpr int TG = 4;   // segments per warp and iteration
+constexpr int TU = 2;   // row loads per segment, lane and iteration
+
+template <int KW>
+__device__ __forceinline__ uint32_t hash_probe(const void *htab, uint64_t hmask, typename KRaw<KW>::T key) {
+    uint64_t h = hk_hash_key<KW>(key) & hmask;
+    if constexpr (KW == 4) {
+        const uint2 *t = reinterpret_cast<const uint2 *>(htab); // {key, slot + 1}
+        while (true) {
+            const uint2 e = __ldg(t + h);
+            if (e.y == 0u) return 0xffffffffu;
+            if (e.x == key) return e.y - 1u;
+            h = (h + 1) & hmask;
+        }
+    } else {
+        const ulonglong2 *t = reinterpret_cast<const ulonglong2 *>(htab); // {key, slot + 1 | row << 32}
+        while (true) {
+            const ulonglong2 e = __ldg(t + h);
+            if ((uint32_t)e.y == 0u) return 0xffffffffu;
+            if (e.x == key) return (uint32_t)e.y - 1u;
+            h = (h + 1) & hmask;
+        }
+    }
+}
+
+template <int KIND, int N>
+__device__ __forceinline__ void acc_rows1(uint32_t *tab, uint32_t K, const uint32_t (&idx)[N], int word, const uint32_t (&x)[N]) {
+#pragma unroll
+    for (int u = 0; u < N; u++)
+        if (idx[u] != 0xffffffffu) acc_row<KIND>(tab, K, idx[u], word, x[u]);
+}
+
+template <int N>
+__device__ __forceinline__ void acc_dispatch1(uint32_t *tab, uint32_t K, const uint32_t (&idx)[N], int kind, int word,
+                                              const uint32_t (&x)[N], float fscale) {
+    switch (kind) {
+    case A_FXSUM32:
+#pragma unroll
+        for (int u = 0; u < N; u++)
+            if (idx[u] != 0xffffffffu) acc_row<A_SUM64S>(tab, K, idx[u], word, (uint32_t)(int32_t)fx_of(x[u], fscale));
+        break;
+    case A_FXSUM64:
+#pragma unroll
+        for (int u = 0; u < N; u++)
+            if (idx[u] != 0xffffffffu) {
+                const unsigned long long v = (unsigned long long)fx_of(x[u], fscale);
+                acc_row<A_FXSUM64>(tab, K, idx[u], word, (uint32_t)v, (uint32_t)(v >> 32));
+            }
+        break;
+    case A_SUM32: acc_rows1<A_SUM32, N>(tab, K, idx, word, x); break;
+    case A_SUM64S: acc_rows1<A_SUM64S, N>(tab, K, idx, word, x); break;
+    case A_SUM64U: acc_rows1<A_SUM64U, N>(tab, K, idx, word, x); break;
+    case A_FSUM: acc_rows1<A_FSUM, N>(tab, K, idx, word, x); break;
+    case A_FPROD: acc_rows1<A_FPROD, N>(tab, K, idx, word, x); break;
+    case A_MINU: acc_rows1<A_MINU, N>(tab, K, idx, word, x); break;
+    case A_MAXU: acc_rows1<A_MAXU, N>(tab, K, idx, word, x); break;
+    case A_MINS: acc_rows1<A_MINS, N>(tab, K, idx, word, x); break;
+    case A_MAXS: acc_rows1<A_MAXS, N>(tab, K, idx, word, x); break;
+    case A_MINF: acc_rows1<A_MINF, N>(tab, K, idx, word, x); break;
+    case A_MAXF: acc_rows1<A_MAXF, N>(tab, K, idx, word, x); break;
+    default: acc_rows1<A_PROD32, N>(tab, K, idx, word, x); break;
+    }
+}
+
+// TG segments of bin `b`, tiles t0 .. t0+TG-1 (those < t_end), by one warp
+template <int KW, int MODE, int NV>
+__device__ __forceinline__ void dagg_segments(const DAggParams &P, uint32_t *tab, int b, long long t0, long long t_end, int lane) {
+    using KT = typename KRaw<KW>::T;
+    constexpr int RW = KW / 4 + NV;
+    constexpr int N = TG * TU;
+    uint32_t s[TG], e[TG];
+    uint32_t maxlen = 0;
+#pragma unroll
+    for (int g = 0; g < TG; g++) {
+        s[g] = e[g] = 0;
+        if (t0 + g < t_end) {
+            const uint32_t w = __ldg(P.t_dir + (size_t)(t0 + g) * P.nbins + b);
+            s[g] = w & 0xffffu;
+            e[g] = w >> 16;
+        }
+        maxlen = max(maxlen, e[g] - s[g]);
+    }
+    const uint64_t slot0 = MODE == 0 ? ((uint64_t)b << P.shift) : 0ull;
+    for (uint32_t j = 0; j < maxlen; j += 32 * TU) {
+        KT k[N];
+        uint32_t x[NV > 0 ? NV : 1][N];
+        uint32_t okm = 0; // bit q: row q of this lane exists
+#pragma unroll
+        for (int g = 0; g < TG; g++)
+#pragma unroll
+            for (int u = 0; u < TU; u++) {
+                const int q = g * TU + u;
+                const uint32_t r = s[g] + j + u * 32 + lane;
+                k[q] = 0;
+                if (r < e[g]) {
+                    okm |= 1u << q;
+                    const uint32_t *row = P.t_rows + ((size_t)(t0 + g) * HK_TPART_TILE + r) * RW;
+                    if constexpr (RW == 1) {
+                        k[q] = __ldcs(row);
+                    } else if constexpr (RW == 2) {
+                        const uint2 v = __ldcs(reinterpret_cast<const uint2 *>(row));
+                        if constexpr (KW == 4) { k[q] = v.x; x[0][q] = v.y; }
+                        else k[q] = (uint64_t)v.x | ((uint64_t)v.y << 32);
+                    } else if constexpr (RW == 4) {
+                        const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(row));
+                        if constexpr (KW == 4) { k[q] = v.x; x[0][q] = v.y; x[1][q] = v.z; x[2][q] = v.w; }
+                        else { k[q] = (uint64_t)v.x | ((uint64_t)v.y << 32); x[0][q] = v.z; x[1][q] = v.w; }
+                    } else {
+                        uint32_t w[RW];
+#pragma unroll
+                        for (int i = 0; i < RW; i++) w[i] = __ldcs(row + i);
+                        if constexpr (KW == 4) k[q] = w[0];
+                        else k[q] = (uint64_t)w[0] | ((uint64_t)w[1] << 32);
+#pragma unroll
+                        for (int v = 0; v < NV; v++) x[v][q] = w[KW / 4 + v];
+                    }
+                }
+            }
+        uint32_t idx[N];
+#pragma unroll
+        for (int q = 0; q < N; q++) {
+            idx[q] = 0xffffffffu;
+            if ((okm >> q) & 1u) {
+                if constexpr (MODE == 1) {
+                    long long v;
+                    if constexpr (KW == 4) v = (P.key_dtype == HARK_U32 ? (long long)(uint32_t)k[q] : (long long)(int32_t)k[q]) - P.pk_min;
+                    else v = (long long)k[q] - P.pk_min;
+                    if (v >= 0 && v < P.pk_span) idx[q] = __ldg(P.lut + v) - 1u;
+                } else if constexpr (MODE == 2) {
+                    idx[q] = hash_probe<KW>(P.htab, P.hmask, k[q]);
+                } else {
+                    idx[q] = (uint32_t)(ordkey_of<KW>(k[q], P.key_dtype) - P.g_lo - slot0);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < N; q++)
+            if (idx[q] != 0xffffffffu) atomicAdd(&tab[idx[q]], 1u);
+#pragma unroll 1
+        for (int ai = 0; ai < P.nacc; ai++) {
+            const int kind = P.acc[ai].kind, word = P.acc[ai].word, vcol = P.acc[ai].vcol;
+#pragma unroll
+            for (int v = 0; v < NV; v++)
+                if (v == vcol) acc_dispatch1<N>(tab, P.K, idx, kind, word, x[v], P.acc[ai].fscale);
+        }
+    }
+}
+
+// Rows of every (bin, block of TBLK tiles): what the GROUP BY mode balances its CTAs by (bins of skewed keys differ in
+// size by orders of magnitude).  Consecutive threads take consecutive bins of one block, so the directory reads coalesce.
+constexpr int TBLK = 64;
+static_assert(TBLK % TG == 0, "a block is a whole number of warp units");
+
+__global__ void __launch_bounds__(256) hk_tile_block_rows_kernel(const uint32_t *__restrict__ dir, long long num_tiles, int nbins,
+                                                                  long long nblk, uint32_t *__restrict__ blk_rows) {
+    const long long total = nblk * nbins;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long blk = i / nbins;
+        const int b = (int)(i - blk * nbins);
+        const long long t1 = min(num_tiles, (blk + 1) * TBLK);
+        uint32_t sum = 0;
+        for (long long t = blk * TBLK; t < t1; t++) {
+            const uint32_t w = __ldg(dir + (size_t)t * nbins + b);
+            sum += (w >> 16) - (w & 0xffffu);
+        }
+        blk_rows[(size_t)b * nblk + blk] = sum;
+    }
+}
+
+template <int KW, int MODE, int NV>
+__global__ void __launch_bounds__(dagg_threads(NV), 1) hk_dagg_tiles_kernel(const __grid_constant__ DAggParams P) {
+    constexpr int AT = dagg_threads(NV);
+    constexpr int NW = AT / 32;
+    extern __shared__ __align__(16) uint32_t tab[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t K = P.K;
+
+    for (uint32_t i = tid; i < K; i += AT) tab[i] = 0;
+    for (int ai = 0; ai < P.nacc; ai++) {
+        const DAcc &a = P.acc[ai];
+        const int two = (a.kind == A_SUM64S || a.kind == A_SUM64U || a.kind == A_FXSUM32 || a.kind == A_FXSUM64) ? 2 : 1;
+        if (a.kind == A_FSUM || a.kind == A_FPROD) {
+            unsigned long long *p = reinterpret_cast<unsigned long long *>(tab + (size_t)a.word * K);
+            for (uint32_t i = tid; i < K; i += AT) p[i] = a.kind == A_FPROD ? 0x3ff0000000000000ull : 0ull;
+        } else {
+            for (int w = 0; w < two; w++)
+                for (uint32_t i = tid; i < K; i += AT) tab[(size_t)(a.word + w) * K + i] = acc_identity(a.kind, 0);
+        }
+    }
+    __syncthreads();
+    const long long NT = P.t_num_tiles;
+    const long long groups_per_bin = (NT + TG - 1) / TG;            // unit = TG tiles of one bin
+    const long long total = groups_per_bin * (long long)P.nbins;
+    if constexpr (MODE == 0) {
+        // this CTA's share of the ROWS, in (bin, block) entries of the bin-major prefix P.t_cum
+        __shared__ long long s_e[2];
+        const long long NB = P.t_nblk, nent = NB * (long long)P.nbins;
+        if (tid < 2) {
+            const unsigned long long rows_total = P.t_cum[nent];
+            const unsigned long long target = rows_total / gridDim.x * (blockIdx.x + tid) +
+                                              rows_total % gridDim.x * (blockIdx.x + tid) / gridDim.x;
+            long long lo = 0, hi = nent; // first entry whose exclusive prefix is >= target
+            if (blockIdx.x + tid == gridDim.x) lo = nent;
+            while (lo < hi) {
+                const long long mid = (lo + hi) >> 1;
+                if (P.t_cum[mid] < target) lo = mid + 1; else hi = mid;
+            }
+            s_e[tid] = lo;
+        }
+        __syncthreads();
+        const long long e0 = s_e[0], e1 = s_e[1];
+        for (long long b = e0 / NB; b * NB < e1 && b < P.nbins; b++) {
+            const long long ba = max(e0, b * NB) - b * NB, bb = min(e1, (b + 1) * NB) - b * NB;
+            const long long t_lo = ba * TBLK, t_hi = min(NT, bb * TBLK);
+            for (long long t = t_lo + (long long)warp * TG; t < t_hi; t += (long long)NW * TG)
+                dagg_segments<KW, MODE, NV>(P, tab, (int)b, t, t_hi, lane);
+            __syncthreads();
+            if (t_lo < t_hi)
+                for (uint32_t i = tid; i < K; i += AT) flush_slot(tab, K, i, ((uint64_t)b << P.shift) + i, P);
+            __syncthreads();
+        }
+    } else {
+        for (long long u = (long long)blockIdx.x * NW + warp; u < total; u += (long long)gridDim.x * NW) {
+            const long long b = u / groups_per_bin;
+            dagg_segments<KW, MODE, NV>(P, tab, (int)b, (u - b * groups_per_bin) * TG, NT, lane);
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < K; i += AT) flush_slot(tab, K, i, (uint64_t)i, P);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -482,11 +806,13 @@ __global__ void __launch_bounds__(1024) hk_dense_scan_kernel(const uint32_t *cou
     }
 }
 
-enum OutKind { O_COUNT = 0, O_COPY32, O_LOW32_OF_U64, O_AVG_S64, O_AVG_U64, O_AVG_F64, O_F32_OF_F64, O_F64, O_F64_OF_S64, O_F64_OF_U64 };
+enum OutKind { O_COUNT = 0, O_COPY32, O_LOW32_OF_U64, O_AVG_S64, O_AVG_U64, O_AVG_F64, O_F32_OF_F64, O_F64, O_F64_OF_S64, O_F64_OF_U64,
+               O_F32_OF_FX, O_AVG_FX, O_F64_OF_FX };
 struct OutSpec {
     int kind;
     const void *src; // dense accumulator
     void *dst;       // output column
+    double oscale;   // O_*_FX: 2^lo, value = (double)fixed-point sum * oscale
 };
 struct CompactParams {
     uint64_t R;
@@ -538,6 +864,9 @@ __global__ void __launch_bounds__(CT) hk_dense_compact_kernel(const __grid_const
             case O_F32_OF_F64: reinterpret_cast<float *>(o.dst)[g] = (float)reinterpret_cast<const double *>(o.src)[r]; break;
             case O_F64_OF_S64: reinterpret_cast<double *>(o.dst)[g] = (double)reinterpret_cast<const long long *>(o.src)[r]; break;
             case O_F64_OF_U64: reinterpret_cast<double *>(o.dst)[g] = (double)reinterpret_cast<const unsigned long long *>(o.src)[r]; break;
+            case O_F32_OF_FX: reinterpret_cast<float *>(o.dst)[g] = (float)((double)reinterpret_cast<const long long *>(o.src)[r] * o.oscale); break;
+            case O_AVG_FX: reinterpret_cast<double *>(o.dst)[g] = (double)reinterpret_cast<const long long *>(o.src)[r] * o.oscale / (double)cnt[e]; break;
+            case O_F64_OF_FX: reinterpret_cast<double *>(o.dst)[g] = (double)reinterpret_cast<const long long *>(o.src)[r] * o.oscale; break;
             default: reinterpret_cast<double *>(o.dst)[g] = reinterpret_cast<const double *>(o.src)[r]; break;
             }
         }
@@ -616,7 +945,8 @@ int hk_col_minmax(hark_ctx *ctx, const void *col, int32_t dtype, int64_t n, uint
 }
 
 int hk_column_minmax(hark_ctx *ctx, const hark_col &col, int64_t n, int32_t dtype, uint64_t *lo, uint64_t *hi) {
-    const bool cacheable = dtype == col.dtype && ctx->opt("stats.cache", 1) != 0;
+    // borrowed columns (hark_table_from_device) can change under the table: their statistics are never kept
+    const bool cacheable = col.owned && dtype == col.dtype && ctx->opt("stats.cache", 1) != 0;
     if (cacheable && col.mm_valid) {
         *lo = col.mm_lo;
         *hi = col.mm_hi;
@@ -627,6 +957,48 @@ int hk_column_minmax(hark_ctx *ctx, const hark_col &col, int64_t n, int32_t dtyp
         col.mm_lo = *lo;
         col.mm_hi = *hi;
         col.mm_valid = true;
+    }
+    return HARK_OK;
+}
+
+// f32 zone map (see hk_f32_fxstats_kernel); cached on owned table columns like min / max
+struct FxStats {
+    bool finite = false, any = false;
+    int hi = 0, lo = 0;
+};
+
+static int hk_f32_fxstats(hark_ctx *ctx, const void *ptr, const hark_col *col, int64_t n, FxStats *st) {
+    const bool cacheable = col && col->owned && col->ptr == ptr && ctx->opt("stats.cache", 1) != 0;
+    if (cacheable && col->fx_valid) {
+        *st = FxStats{col->fx_finite, col->fx_any, col->fx_hi, col->fx_lo};
+        return HARK_OK;
+    }
+    unsigned long long *d = nullptr;
+    HK_TRY(ctx->dalloc((void **)&d, 4 * sizeof(unsigned long long)));
+    ctx->h_scalars[0] = 0;
+    ctx->h_scalars[1] = ~0ull;
+    ctx->h_scalars[2] = 0;
+    ctx->h_scalars[3] = 0;
+    cudaError_t e = cudaMemcpyAsync(d, ctx->h_scalars, 4 * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && n > 0) {
+        hk_f32_fxstats_kernel<<<grid_for(ctx, n, 8), 256, 0, ctx->stream>>>((const uint32_t *)ptr, n, d);
+        e = cudaGetLastError();
+        ctx->count_launch();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_scalars, d, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    ctx->dfree(d);
+    if (e != cudaSuccess) return ctx->fail(HARK_ERR_CUDA, std::string("f32 statistics: ") + cudaGetErrorString(e));
+    st->any = ctx->h_scalars[3] != 0;
+    st->finite = ctx->h_scalars[2] == 0;
+    st->hi = st->any ? (int)ctx->h_scalars[0] - 1024 : 0;
+    st->lo = st->any ? (int)ctx->h_scalars[1] - 1024 : 0;
+    if (cacheable) {
+        col->fx_valid = true;
+        col->fx_finite = st->finite;
+        col->fx_any = st->any;
+        col->fx_hi = st->hi;
+        col->fx_lo = st->lo;
     }
     return HARK_OK;
 }
@@ -658,6 +1030,38 @@ int hk_dense_groupby(hark_ctx *ctx, hark_table **out, const hk_dense_req &rq, bo
     std::vector<bool> col_needs_avg((size_t)std::max(rq.nvals, 1), false);
     for (int j = 0; j < rq.c; j++)
         if ((rq.agg_code[j] == HARK_AGG_AVG || rq.agg_code[j] == HARK_AGG_SUMF64) && rq.agg_val[j] >= 0) col_needs_avg[rq.agg_val[j]] = true;
+    // f32 SUM / AVG: exact fixed point when the column's zone map allows it (every value a multiple of 2^lo, below
+    // 2^(hi+1)): v / 2^lo is an integer of B = hi + 1 - lo bits.  B <= 31 -> one 32-bit addend per row (the integer
+    // path's cost); B + log2(n) <= 62 -> 64-bit addends; else (or non-finite values) the f64 compare-and-swap path.
+    struct FxPlan {
+        int kind = -1; // -1 none, else A_FXSUM32 / A_FXSUM64
+        float fscale = 1.0f;
+        double oscale = 1.0;
+    };
+    std::vector<FxPlan> fxp((size_t)std::max(rq.nvals, 1));
+    if (ctx->opt("dense.fixed_point", 1) != 0 && !rq.pinned_u32) {
+        for (int v = 0; v < rq.nvals; v++) {
+            if (rq.val_dtypes[v] != HARK_F32) continue;
+            bool wanted = false;
+            for (int j = 0; j < rq.c; j++)
+                wanted = wanted || (rq.agg_val[j] == v && (rq.agg_code[j] == HARK_AGG_SUM || rq.agg_code[j] == HARK_AGG_AVG ||
+                                                           rq.agg_code[j] == HARK_AGG_SUMF64));
+            if (!wanted) continue;
+            FxStats st;
+            HK_TRY(hk_f32_fxstats(ctx, rq.vals[v], rq.val_cols[v], n, &st));
+            if (!st.finite) continue;
+            if (!st.any) st.hi = st.lo = 0;
+            const int B = st.hi + 1 - st.lo;
+            int lg = 0;
+            while ((1ll << lg) < n) lg++;
+            if (st.lo < -126 || st.lo > 126) continue;
+            if (B <= 31) fxp[v].kind = A_FXSUM32;
+            else if (B + lg <= 62) fxp[v].kind = A_FXSUM64;
+            else continue;
+            fxp[v].fscale = ldexpf(1.0f, -st.lo);
+            fxp[v].oscale = ldexp(1.0, st.lo);
+        }
+    }
     struct OutPlan {
         int okind, acc;
         int32_t dtype;
@@ -674,16 +1078,19 @@ int hk_dense_groupby(hark_ctx *ctx, hark_table **out, const hk_dense_req &rq, bo
         const bool is_f = vdt == HARK_F32, is_s = vdt == HARK_I32;
         switch (code) {
         case HARK_AGG_SUM:
-            if (is_f) outs.push_back({O_F32_OF_F64, acc_index(vi, A_FSUM, 2), HARK_F32});
+            if (is_f && fxp[vi].kind >= 0) outs.push_back({O_F32_OF_FX, acc_index(vi, fxp[vi].kind, 2), HARK_F32});
+            else if (is_f) outs.push_back({O_F32_OF_F64, acc_index(vi, A_FSUM, 2), HARK_F32});
             else if (col_needs_avg[vi]) outs.push_back({O_LOW32_OF_U64, acc_index(vi, is_s ? A_SUM64S : A_SUM64U, 2), vdt});
             else outs.push_back({O_COPY32, acc_index(vi, A_SUM32, 1), vdt});
             break;
         case HARK_AGG_AVG:
-            if (is_f) outs.push_back({O_AVG_F64, acc_index(vi, A_FSUM, 2), HARK_F64});
+            if (is_f && fxp[vi].kind >= 0) outs.push_back({O_AVG_FX, acc_index(vi, fxp[vi].kind, 2), HARK_F64});
+            else if (is_f) outs.push_back({O_AVG_F64, acc_index(vi, A_FSUM, 2), HARK_F64});
             else outs.push_back({is_s ? O_AVG_S64 : O_AVG_U64, acc_index(vi, is_s ? A_SUM64S : A_SUM64U, 2), HARK_F64});
             break;
         case HARK_AGG_SUMF64:
-            if (is_f) outs.push_back({O_F64, acc_index(vi, A_FSUM, 2), HARK_F64});
+            if (is_f && fxp[vi].kind >= 0) outs.push_back({O_F64_OF_FX, acc_index(vi, fxp[vi].kind, 2), HARK_F64});
+            else if (is_f) outs.push_back({O_F64, acc_index(vi, A_FSUM, 2), HARK_F64});
             else outs.push_back({is_s ? O_F64_OF_S64 : O_F64_OF_U64, acc_index(vi, is_s ? A_SUM64S : A_SUM64U, 2), HARK_F64});
             break;
         case HARK_AGG_PROD:
@@ -719,7 +1126,8 @@ int hk_dense_groupby(hark_ctx *ctx, hark_table **out, const hk_dense_req &rq, bo
     if (force_shift > 0) shift = (int)std::min<int64_t>(shift, force_shift);
     if (shift < 8) return HARK_OK;
     const uint64_t K = 1ull << shift;
-    const bool lut_mode = rq.lut != nullptr;
+    const bool hash_mode = rq.htab != nullptr;
+    const bool lut_mode = rq.lut != nullptr || hash_mode; // the slot comes from a lookup: one table of R <= K slots
     const uint64_t nbins64 = (R + K - 1) >> shift;
     if (lut_mode ? (R > K) : (nbins64 > 256)) return HARK_OK;
     if (!lut_mode && R > 16ull * (uint64_t)n + (1ull << 16)) return HARK_OK; // sparse keys: dense slots would dominate
@@ -736,8 +1144,17 @@ int hk_dense_groupby(hark_ctx *ctx, hark_table **out, const hk_dense_req &rq, bo
     int agg_nbins = nbins;
     // lut mode: slice the lookup so that the slice being probed stays L2-resident
     int lut_bins = 1, lut_shift = 0;
-    if (lut_mode) {
-        const int64_t slice_bytes = ctx->opt("join.lut_slice_bytes", 16ll << 20);
+    const int64_t slice_bytes = ctx->opt("join.lut_slice_bytes", 16ll << 20);
+    if (hash_mode) {
+        // slices of the hash table: entries [s << lut_shift, (s + 1) << lut_shift)
+        const int esz = kw == 4 ? 8 : 16;
+        const uint64_t tab_bytes = (rq.hmask + 1) * (uint64_t)esz;
+        if ((int64_t)tab_bytes > slice_bytes * 3 / 2 && rq.nvals <= PMAXV) {
+            lut_shift = floor_log2_u64((uint64_t)slice_bytes / esz);
+            while ((rq.hmask >> lut_shift) + 1 > 256) lut_shift++;
+            lut_bins = (int)((rq.hmask >> lut_shift) + 1);
+        }
+    } else if (lut_mode) {
         const uint64_t lut_bytes = (uint64_t)rq.pk_span * 4ull;
         if ((int64_t)lut_bytes > slice_bytes * 3 / 2 && rq.nvals <= PMAXV) {
             lut_shift = floor_log2_u64((uint64_t)slice_bytes / 4);
@@ -745,7 +1162,34 @@ int hk_dense_groupby(hark_ctx *ctx, hark_table **out, const hk_dense_req &rq, bo
             lut_bins = (int)((((uint64_t)rq.pk_span - 1) >> lut_shift) + 1);
         }
     }
-    if (nbins > 1 || lut_bins > 1) {
+    const bool use_tiles = (nbins > 1 || lut_bins > 1) && (hash_mode || ctx->opt("dense.part_impl", 0) == 0);
+    hk_tpart tp;
+    if (use_tiles) {
+        hk_part_spec ps;
+        ps.dtype = rq.key_dtype;
+        if (hash_mode) {
+            ps.base = 0;
+            ps.span = 0;
+            ps.shift = lut_shift;
+            ps.nbins = lut_bins;
+            agg_nbins = lut_bins;
+        } else if (lut_mode) {
+            ps.base = kw == 4 ? (uint64_t)(rq.key_dtype == HARK_U32 ? (uint32_t)rq.pk_min : ((uint32_t)(int32_t)rq.pk_min ^ 0x80000000u))
+                              : ((uint64_t)rq.pk_min ^ 0x8000000000000000ull);
+            ps.span = (uint64_t)rq.pk_span;
+            ps.shift = lut_shift;
+            ps.nbins = lut_bins;
+            agg_nbins = lut_bins;
+        } else {
+            ps.base = rq.g_lo;
+            ps.span = R;
+            ps.shift = shift;
+            ps.nbins = nbins;
+        }
+        HK_TRY(hk_tile_partition(ctx, n, key, kw, ps, hash_mode ? rq.hmask : 0ull, rq.nvals, vals, &tp));
+        scratch.adopt(tp.rows);
+        scratch.adopt(tp.dir);
+    } else if (nbins > 1 || lut_bins > 1) {
         hk_part_spec ps;
         if (lut_mode) {
             // order key of pk_min in the fact key's dtype (signed dtypes: sign-bit flip)
@@ -797,6 +1241,25 @@ int hk_dense_groupby(hark_ctx *ctx, hark_table **out, const hk_dense_req &rq, bo
     P.lut = rq.lut;
     P.pk_min = rq.pk_min;
     P.pk_span = rq.pk_span;
+    P.htab = rq.htab;
+    P.hmask = rq.hmask;
+    P.t_rows = tp.rows;
+    P.t_dir = tp.dir;
+    P.t_num_tiles = tp.num_tiles;
+    if (use_tiles && !lut_mode) {
+        const long long nblk = (tp.num_tiles + TBLK - 1) / TBLK, nent = nblk * nbins;
+        uint32_t *blk_rows = nullptr;
+        unsigned long long *cum = nullptr;
+        HK_TRY(scratch.alloc((void **)&blk_rows, sizeof(uint32_t) * (size_t)nent));
+        HK_TRY(scratch.alloc((void **)&cum, sizeof(unsigned long long) * (size_t)(nent + 1)));
+        hk_tile_block_rows_kernel<<<grid_for(ctx, nent), 256, 0, ctx->stream>>>(tp.dir, tp.num_tiles, nbins, nblk, blk_rows);
+        HK_CHECK_LAUNCH(ctx);
+        hk_dense_scan_kernel<<<1, 1024, 0, ctx->stream>>>(blk_rows, cum, nent);
+        HK_CHECK_LAUNCH(ctx);
+        ctx->count_launch(2);
+        P.t_cum = cum;
+        P.t_nblk = nblk;
+    }
     P.nvals = rq.nvals;
     for (int v = 0; v < rq.nvals; v++) P.vals[v] = (const uint32_t *)vals[v];
     P.nacc = (int)accs.size();
@@ -804,7 +1267,7 @@ int hk_dense_groupby(hark_ctx *ctx, hark_table **out, const hk_dense_req &rq, bo
     std::vector<void *> gacc(accs.size(), nullptr);
     for (size_t i = 0; i < accs.size(); i++) {
         const int kind = accs[i].kind;
-        const bool wide = kind == A_SUM64S || kind == A_SUM64U || kind == A_FSUM || kind == A_FPROD;
+        const bool wide = kind == A_SUM64S || kind == A_SUM64U || kind == A_FSUM || kind == A_FPROD || kind == A_FXSUM32 || kind == A_FXSUM64;
         HK_TRY(scratch.alloc(&gacc[i], R * (wide ? 8 : 4)));
         switch (kind) {
         case A_FPROD: HK_TRY(dfill<double>(ctx, gacc[i], 1.0, R)); break;
@@ -816,7 +1279,7 @@ int hk_dense_groupby(hark_ctx *ctx, hark_table **out, const hk_dense_req &rq, bo
         case A_PROD32: HK_TRY(dfill<uint32_t>(ctx, gacc[i], 1u, R)); break;
         default: HK_CUDA(ctx, cudaMemsetAsync(gacc[i], 0, R * (wide ? 8 : 4), ctx->stream)); break;
         }
-        P.acc[i] = DAcc{accs[i].vcol, kind, word_of[i], gacc[i]};
+        P.acc[i] = DAcc{accs[i].vcol, kind, word_of[i], gacc[i], fxp[(size_t)accs[i].vcol].fscale};
     }
     const unsigned grid = (unsigned)ctx->num_sms;
     {
@@ -828,18 +1291,20 @@ int hk_dense_groupby(hark_ctx *ctx, hark_table **out, const hk_dense_req &rq, bo
     {
         cudaError_t e;
         void (*kern)(const DAggParams) = nullptr;
-#define HK_DAGG_PICK(KWv, LUTv)                                                        \
-    switch (rq.nvals) {                                                                \
-    case 0: kern = hk_dagg_kernel<KWv, LUTv, 0>; break;                                \
-    case 1: kern = hk_dagg_kernel<KWv, LUTv, 1>; break;                                \
-    case 2: kern = hk_dagg_kernel<KWv, LUTv, 2>; break;                                \
-    case 3: kern = hk_dagg_kernel<KWv, LUTv, 3>; break;                                \
-    default: kern = hk_dagg_kernel<KWv, LUTv, 4>; break;                               \
+#define HK_DAGG_PICK(KWv, MODEv)                                                                       \
+    switch (rq.nvals) {                                                                                \
+    case 0: kern = use_tiles ? hk_dagg_tiles_kernel<KWv, MODEv, 0> : hk_dagg_kernel<KWv, MODEv, 0>; break; \
+    case 1: kern = use_tiles ? hk_dagg_tiles_kernel<KWv, MODEv, 1> : hk_dagg_kernel<KWv, MODEv, 1>; break; \
+    case 2: kern = use_tiles ? hk_dagg_tiles_kernel<KWv, MODEv, 2> : hk_dagg_kernel<KWv, MODEv, 2>; break; \
+    case 3: kern = use_tiles ? hk_dagg_tiles_kernel<KWv, MODEv, 3> : hk_dagg_kernel<KWv, MODEv, 3>; break; \
+    default: kern = hk_dagg_kernel<KWv, MODEv, 4>; break;                                              \
     }
-        if (lut_mode) {
-            if (kw == 4) { HK_DAGG_PICK(4, true) } else { HK_DAGG_PICK(8, true) }
+        if (hash_mode) {
+            if (kw == 4) { HK_DAGG_PICK(4, 2) } else { HK_DAGG_PICK(8, 2) }
+        } else if (lut_mode) {
+            if (kw == 4) { HK_DAGG_PICK(4, 1) } else { HK_DAGG_PICK(8, 1) }
         } else {
-            if (kw == 4) { HK_DAGG_PICK(4, false) } else { HK_DAGG_PICK(8, false) }
+            if (kw == 4) { HK_DAGG_PICK(4, 0) } else { HK_DAGG_PICK(8, 0) }
         }
 #undef HK_DAGG_PICK
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -880,7 +1345,9 @@ int hk_dense_groupby(hark_ctx *ctx, hark_table **out, const hk_dense_req &rq, bo
         C.key_dtype = rq.out_key_dtype;
         C.out_key = t->cols[0].ptr;
         C.nout = rq.c;
-        for (int j = 0; j < rq.c; j++) C.o[j] = OutSpec{outs[j].okind, outs[j].acc >= 0 ? gacc[outs[j].acc] : nullptr, t->cols[1 + j].ptr};
+        for (int j = 0; j < rq.c; j++)
+            C.o[j] = OutSpec{outs[j].okind, outs[j].acc >= 0 ? gacc[outs[j].acc] : nullptr, t->cols[1 + j].ptr,
+                             outs[j].acc >= 0 ? fxp[(size_t)accs[(size_t)outs[j].acc].vcol].oscale : 1.0};
         hk_dense_compact_kernel<<<(unsigned)nblk, CT, 0, ctx->stream>>>(C);
         cudaError_t e = cudaGetLastError();
         ctx->count_launch();

@@ -88,6 +88,16 @@ extern "C" int hark_entry_join(hark_ctx *ctx, hark_table **out, const hark_table
     HK_ABI_END(ctx)
 }
 
+extern "C" int hark_entry_join_ex(hark_ctx *ctx, hark_table **out, const hark_table *db1, const hark_table *db2,
+                                  int32_t col1, int32_t col2, const int32_t *cols1, int64_t l, const int32_t *cols2,
+                                  int64_t k, int32_t order) {
+    HK_ENTER(ctx);
+    HK_ABI_BEGIN
+    HK_ARG(ctx, out && db1 && db2 && l >= 0 && k >= 0 && (l == 0 || cols1) && (k == 0 || cols2), "join_ex: bad argument");
+    return hk_join_ex(ctx, out, db1, db2, col1, col2, cols1, l, cols2, k, order, false);
+    HK_ABI_END(ctx)
+}
+
 extern "C" int hark_entry_join_groupby(hark_ctx *ctx, hark_table **out, const hark_table *fact, const hark_table *dim,
                                        int32_t fk_col, int32_t pk_col, int32_t g_col, const int32_t *s_cols,
                                        const int32_t *ops, int64_t c) {

@@ -626,6 +626,7 @@ int hk_groupby(hark_ctx *ctx, hark_table **out, const hark_table *db, int32_t g_
                 }
                 val_of_col[col] = rq.nvals;
                 rq.vals[rq.nvals] = db->cols[col].ptr;
+                rq.val_cols[rq.nvals] = &db->cols[col];
                 rq.val_dtypes[rq.nvals] = pinned_u32 ? HARK_U32 : db->cols[col].dtype;
                 rq.nvals++;
             }

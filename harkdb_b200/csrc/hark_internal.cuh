@@ -28,6 +28,11 @@ struct hark_col {
     // with the column (columns are immutable once built)
     mutable bool mm_valid = false;
     mutable uint64_t mm_lo = 0, mm_hi = 0;
+    // f32 columns: exponent of the highest / lowest set bit over all non-zero values, and whether every value is finite
+    // (dense_agg.cu: proves when a SUM can be accumulated EXACTLY in fixed point)
+    mutable bool fx_valid = false;
+    mutable int fx_hi = 0, fx_lo = 0;
+    mutable bool fx_finite = false, fx_any = false;
 };
 
 struct hark_table {
@@ -143,6 +148,8 @@ int hk_orderby(hark_ctx *ctx, hark_table **out, const hark_table *db, const int3
                const int32_t *key_cols, const int32_t *desc, int64_t nk);
 int hk_join(hark_ctx *ctx, hark_table **out, const hark_table *db1, const hark_table *db2, int32_t col1, int32_t col2,
             const int32_t *cols1, int64_t l, const int32_t *cols2, int64_t k);
+int hk_join_ex(hark_ctx *ctx, hark_table **out, const hark_table *db1, const hark_table *db2, int32_t col1, int32_t col2,
+               const int32_t *cols1, int64_t l, const int32_t *cols2, int64_t k, int32_t order, bool pinned_u32);
 int hk_join_groupby(hark_ctx *ctx, hark_table **out, const hark_table *fact, const hark_table *dim, int32_t fk_col,
                     int32_t pk_col, int32_t g_col, const int32_t *s_cols, const int32_t *ops, int64_t c);
 int hk_partition_by_hash(hark_ctx *ctx, hark_table **out, const hark_table *db, int32_t key_col, int32_t nparts,

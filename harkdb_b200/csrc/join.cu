@@ -29,84 +29,6 @@ namespace {
 
 constexpr int JMAXC = 16;
 
-// match range of every sorted left key in the sorted right keys
-__global__ void __launch_bounds__(256) hk_join_bounds_kernel(const uint32_t *__restrict__ k1, int64_t n1,
-                                                              const uint32_t *__restrict__ k2, int64_t n2,
-                                                              uint32_t *__restrict__ lb_out, uint32_t *__restrict__ cnt_out) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n1; i += stride) {
-        const uint32_t key = k1[i];
-        int64_t lo = 0, hi = n2; // first index with k2 >= key
-        while (lo < hi) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (k2[mid] < key) lo = mid + 1; else hi = mid;
-        }
-        const int64_t lb = lo;
-        hi = n2; // first index with k2 > key
-        while (lo < hi) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (k2[mid] <= key) lo = mid + 1; else hi = mid;
-        }
-        lb_out[i] = (uint32_t)lb;
-        cnt_out[i] = (uint32_t)(lo - lb);
-    }
-}
-
-// exclusive scan of u32 counts -> u64 offsets, total in offs[count]; one CTA of 1024 threads
-__global__ void __launch_bounds__(1024) hk_join_scan_kernel(const uint32_t *counts, unsigned long long *offs, int64_t count) {
-    __shared__ unsigned long long s_part[1024];
-    const int t = threadIdx.x;
-    const int64_t per = (count + 1023) / 1024;
-    const int64_t b = (int64_t)t * per, e = min(count, b + per);
-    unsigned long long sum = 0;
-    for (int64_t i = b; i < e; i++) sum += counts[i];
-    s_part[t] = sum;
-    __syncthreads();
-    if (t == 0) {
-        unsigned long long run = 0;
-        for (int i = 0; i < 1024; i++) {
-            const unsigned long long v = s_part[i];
-            s_part[i] = run;
-            run += v;
-        }
-        offs[count] = run;
-    }
-    __syncthreads();
-    unsigned long long run = s_part[t];
-    for (int64_t i = b; i < e; i++) {
-        offs[i] = run;
-        run += counts[i];
-    }
-}
-
-struct ExpandParams {
-    int64_t P, n1;
-    const unsigned long long *offs; // [n1+1]
-    const uint32_t *lb;             // [n1]
-    const uint32_t *rid1, *rid2;    // sorted row ids
-    int l, k;
-    const uint32_t *src1[JMAXC];
-    const uint32_t *src2[JMAXC];
-    uint32_t *dst[2 * JMAXC];
-};
-
-__global__ void __launch_bounds__(256) hk_join_expand_kernel(const __grid_constant__ ExpandParams E) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < E.P; p += stride) {
-        int64_t lo = 0, hi = E.n1; // last i with offs[i] <= p  (offs is non-decreasing, offs[n1] = P > p)
-        while (hi - lo > 1) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (E.offs[mid] <= (unsigned long long)p) lo = mid; else hi = mid;
-        }
-        const int64_t i = lo;
-        const int64_t j = p - (int64_t)E.offs[i];
-        const uint32_t r1 = E.rid1[i];
-        const uint32_t r2 = E.rid2[(int64_t)E.lb[i] + j];
-        for (int c = 0; c < E.l; c++) E.dst[c][p] = E.src1[c][r1];
-        for (int c = 0; c < E.k; c++) E.dst[E.l + c][p] = E.src2[c][r2];
-    }
-}
-
 // ---- join + group by: dimension lookup ----
 __device__ __forceinline__ long long load_int(const void *col, int dtype, int64_t i) {
     switch (dtype) {
@@ -191,6 +113,127 @@ __global__ void __launch_bounds__(256) hk_minmax_int_kernel(const void *col, int
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// hash build (sparse keys): open addressing with linear probing over hk_hash_key(key) & hmask, load factor <= 1/2.
+//   4-byte keys: 8-byte entries {key, payload + 1}; an entry is claimed with ONE 64-bit compare-and-swap, so a second
+//                row with the same key meets the first one's entry and is reported as a duplicate on the spot;
+//   8-byte keys: 16-byte entries {key, payload + 1 | (row + 1) << 32}; the payload word is claimed by CAS, the key is
+//                stored after it, and hk_hash_verify_kernel (a second launch) checks that every row finds ITSELF
+//                first — a duplicate key finds the other row.
+// payload = group slot (ordkey(g) - g_lo) for the fused probe + aggregate, or the dimension row for the
+// materialising path.  The probe side is hash_probe in dense_agg.cu / hk_hash_probe_kernel below.
+// ------------------------------------------------------------------------------------------------
+template <int KW>
+__device__ __forceinline__ uint32_t build_payload(const void *g, int g_dtype, unsigned long long g_lo, int64_t i, int payload_row) {
+    if (payload_row) return (uint32_t)i;
+    unsigned long long ord;
+    if (g_dtype == HARK_I64) ord = hk_ordkey64(reinterpret_cast<const unsigned long long *>(g)[i], g_dtype);
+    else ord = hk_ordkey32(reinterpret_cast<const uint32_t *>(g)[i], g_dtype);
+    return (uint32_t)(ord - g_lo);
+}
+
+template <int KW>
+__global__ void __launch_bounds__(256) hk_hash_build_kernel(const void *pk, const void *g, int g_dtype, int64_t n_dim,
+                                                             unsigned long long g_lo, int payload_row, void *htab,
+                                                             unsigned long long hmask, unsigned int *dup_flag) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_dim; i += stride) {
+        const uint32_t pay1 = build_payload<KW>(g, g_dtype, g_lo, i, payload_row) + 1u;
+        if constexpr (KW == 4) {
+            const uint32_t key = reinterpret_cast<const uint32_t *>(pk)[i];
+            unsigned long long *t = reinterpret_cast<unsigned long long *>(htab);
+            const unsigned long long packed = (unsigned long long)key | ((unsigned long long)pay1 << 32);
+            unsigned long long h = hk_hash_key<4>(key) & hmask;
+            while (true) {
+                const unsigned long long old = atomicCAS(t + h, 0ull, packed);
+                if (old == 0ull) break;
+                if ((uint32_t)old == key) {
+                    *dup_flag = 1u;
+                    break;
+                }
+                h = (h + 1) & hmask;
+            }
+        } else {
+            const unsigned long long key = reinterpret_cast<const unsigned long long *>(pk)[i];
+            unsigned long long *t = reinterpret_cast<unsigned long long *>(htab); // entry h = words 2h (key), 2h+1 (payload)
+            const unsigned long long packed = (unsigned long long)pay1 | ((unsigned long long)(i + 1) << 32);
+            unsigned long long h = hk_hash_key<8>(key) & hmask;
+            while (true) {
+                const unsigned long long old = atomicCAS(t + 2 * h + 1, 0ull, packed);
+                if (old == 0ull) {
+                    t[2 * h] = key;
+                    break;
+                }
+                h = (h + 1) & hmask;
+            }
+        }
+    }
+}
+
+// 8-byte keys: every row must be the first entry with its key on its probe sequence
+__global__ void __launch_bounds__(256) hk_hash_verify_kernel(const void *pk, int64_t n_dim, const void *htab, unsigned long long hmask,
+                                                              unsigned int *dup_flag) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const ulonglong2 *t = reinterpret_cast<const ulonglong2 *>(htab);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_dim; i += stride) {
+        const unsigned long long key = reinterpret_cast<const unsigned long long *>(pk)[i];
+        unsigned long long h = hk_hash_key<8>(key) & hmask;
+        while (true) {
+            const ulonglong2 e = t[h];
+            if ((uint32_t)e.y == 0u) { // cannot happen for an inserted key; treat as corruption
+                *dup_flag = 1u;
+                break;
+            }
+            if (e.x == key) {
+                if ((e.y >> 32) != (unsigned long long)(i + 1)) *dup_flag = 1u;
+                break;
+            }
+            h = (h + 1) & hmask;
+        }
+    }
+}
+
+// materialising probe: gkey[i] = dim.g[row(fk[i])], hit[i] = 1 when fk[i] has a match
+template <int KW>
+__global__ void __launch_bounds__(256) hk_hash_probe_kernel(const void *fk, int64_t n_fact, const void *htab, unsigned long long hmask,
+                                                             const void *g, int g_width, void *gkey_out, uint32_t *hit_out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_fact; i += stride) {
+        uint32_t row = 0xffffffffu;
+        if constexpr (KW == 4) {
+            const uint32_t key = reinterpret_cast<const uint32_t *>(fk)[i];
+            const uint2 *t = reinterpret_cast<const uint2 *>(htab);
+            unsigned long long h = hk_hash_key<4>(key) & hmask;
+            while (true) {
+                const uint2 e = __ldg(t + h);
+                if (e.y == 0u) break;
+                if (e.x == key) {
+                    row = e.y - 1u;
+                    break;
+                }
+                h = (h + 1) & hmask;
+            }
+        } else {
+            const unsigned long long key = reinterpret_cast<const unsigned long long *>(fk)[i];
+            const ulonglong2 *t = reinterpret_cast<const ulonglong2 *>(htab);
+            unsigned long long h = hk_hash_key<8>(key) & hmask;
+            while (true) {
+                const ulonglong2 e = __ldg(t + h);
+                if ((uint32_t)e.y == 0u) break;
+                if (e.x == key) {
+                    row = (uint32_t)e.y - 1u;
+                    break;
+                }
+                h = (h + 1) & hmask;
+            }
+        }
+        const bool hit = row != 0xffffffffu;
+        hit_out[i] = hit;
+        if (g_width == 4) reinterpret_cast<uint32_t *>(gkey_out)[i] = hit ? reinterpret_cast<const uint32_t *>(g)[row] : 0u;
+        else reinterpret_cast<uint64_t *>(gkey_out)[i] = hit ? reinterpret_cast<const uint64_t *>(g)[row] : 0ull;
+    }
+}
+
 unsigned grid_for(hark_ctx *ctx, int64_t n, int per_sm = 8) {
     return (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx->num_sms * per_sm));
 }
@@ -212,18 +255,355 @@ struct Bufs {
     }
 };
 
-// (key, row id) of one side, sorted by key as u32, stable
-int sort_side(hark_ctx *ctx, Bufs &bufs, const hark_table *db, int32_t col, void **keys_out, void **rid_out) {
+} // namespace
+
+// ================================================================================================
+// Plain inner equi-join, typed (hk_join_ex).  Two strategies:
+//   order = 1  reference order (join.fut:55-75: key ascending, then left row, then right row): both sides are sorted
+//              as (key, row id) by K3; hk_mj_bounds_kernel walks tiles of the sorted left side, narrows the right
+//              side to the tile's key range with two searches per CTA, finds every left row's match range inside
+//              it, and turns the counts into output offsets with ONE decoupled look-back per tile; the expand kernel
+//              is balanced over OUTPUT rows (a CTA owns a fixed slice of the result, whatever the duplication).
+//   order = 0  hash build on db2 + probe with db1 in row order (multiset result, matches of one left row in
+//              unspecified order): count -> look-back scan per tile -> expand; nothing is sorted, the probe side
+//              needs no row ids and may exceed 2^32 rows.
+// ================================================================================================
+namespace {
+
+constexpr int MJ_T = 256, MJ_I = 8, MJ_TILE = MJ_T * MJ_I;
+
+template <int KW> struct JRaw;
+template <> struct JRaw<4> { using T = uint32_t; };
+template <> struct JRaw<8> { using T = uint64_t; };
+
+template <int KW>
+__device__ __forceinline__ uint64_t j_ord(typename JRaw<KW>::T raw, int dtype) {
+    if constexpr (KW == 4) return (uint64_t)hk_ordkey32(raw, dtype);
+    else return hk_ordkey64(raw, dtype);
+}
+
+// block-wide exclusive scan of one u64 per thread (MJ_T threads); returns the exclusive prefix, *total = block sum
+__device__ __forceinline__ unsigned long long mj_block_excl_scan(unsigned long long v, unsigned long long *s_w /* [MJ_T/32] */,
+                                                                 unsigned long long *total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(HK_FULL_MASK, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    unsigned long long off = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < MJ_T / 32; w++) {
+        const unsigned long long x = s_w[w];
+        if (w < warp) off += x;
+        tot += x;
+    }
+    *total = tot;
+    __syncthreads();
+    return off + inc - v;
+}
+
+struct MjParams {
+    const void *k1, *k2; // sorted keys
+    int64_t n1, n2;
+    int dtype;           // order of the keys (HARK_U32 for the pinned entry)
+    uint32_t *lb;        // [n1] first matching position in k2
+    unsigned long long *offs; // [n1 + 1] exclusive output offsets
+    uint64_t *state;     // look-back words, one per tile
+    unsigned long long *ticket;
+    int64_t num_tiles;
+};
+
+template <int KW>
+__global__ void __launch_bounds__(MJ_T) hk_mj_bounds_kernel(const __grid_constant__ MjParams P) {
+    using KT = typename JRaw<KW>::T;
+    __shared__ unsigned long long s_w[MJ_T / 32];
+    __shared__ long long s_tile;
+    __shared__ long long s_range[2];
+    __shared__ unsigned long long s_excl;
+    const KT *k1 = reinterpret_cast<const KT *>(P.k1), *k2 = reinterpret_cast<const KT *>(P.k2);
+    while (true) {
+        if (threadIdx.x == 0) s_tile = (long long)atomicAdd(P.ticket, 1ull);
+        __syncthreads();
+        const int64_t tile = s_tile;
+        if (tile >= P.num_tiles) break;
+        const int64_t i0 = tile * MJ_TILE, i1 = min(P.n1, i0 + MJ_TILE);
+        // ---- the slice of the right side that can match this tile: [lb(first key), ub(last key)) ----
+        if (threadIdx.x < 2) {
+            const uint64_t key = j_ord<KW>(threadIdx.x == 0 ? k1[i0] : k1[i1 - 1], P.dtype);
+            int64_t lo = 0, hi = P.n2;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                const uint64_t x = j_ord<KW>(k2[mid], P.dtype);
+                if (threadIdx.x == 0 ? (x < key) : (x <= key)) lo = mid + 1; else hi = mid;
+            }
+            s_range[threadIdx.x] = lo;
+        }
+        __syncthreads();
+        const int64_t L = s_range[0], U = s_range[1];
+        uint32_t lbv[MJ_I];
+        unsigned long long cnt[MJ_I], mine = 0;
+#pragma unroll
+        for (int e = 0; e < MJ_I; e++) {
+            const int64_t i = i0 + (int64_t)threadIdx.x * MJ_I + e; // thread-contiguous rows: offsets come out in row order
+            lbv[e] = 0;
+            cnt[e] = 0;
+            if (i < i1) {
+                const uint64_t key = j_ord<KW>(k1[i], P.dtype);
+                int64_t lo = L, hi = U;
+                while (lo < hi) {
+                    const int64_t mid = (lo + hi) >> 1;
+                    if (j_ord<KW>(k2[mid], P.dtype) < key) lo = mid + 1; else hi = mid;
+                }
+                const int64_t lb = lo;
+                hi = U;
+                while (lo < hi) {
+                    const int64_t mid = (lo + hi) >> 1;
+                    if (j_ord<KW>(k2[mid], P.dtype) <= key) lo = mid + 1; else hi = mid;
+                }
+                lbv[e] = (uint32_t)lb;
+                cnt[e] = (unsigned long long)(lo - lb);
+            }
+            mine += cnt[e];
+        }
+        unsigned long long total;
+        const unsigned long long excl_in_tile = mj_block_excl_scan(mine, s_w, &total);
+        if (threadIdx.x < 32) {
+            const unsigned long long ex = hk_lookback_u64(P.state, tile, total);
+            if (threadIdx.x == 0) s_excl = ex;
+        }
+        __syncthreads();
+        unsigned long long run = s_excl + excl_in_tile;
+#pragma unroll
+        for (int e = 0; e < MJ_I; e++) {
+            const int64_t i = i0 + (int64_t)threadIdx.x * MJ_I + e;
+            if (i < i1) {
+                P.lb[i] = lbv[e];
+                P.offs[i] = run;
+                run += cnt[e];
+            }
+        }
+        if (tile == P.num_tiles - 1 && threadIdx.x == MJ_T - 1) P.offs[P.n1] = s_excl + total;
+        __syncthreads();
+    }
+}
+
+struct JoinCols {
+    int l, k;
+    const void *src1[JMAXC];
+    const void *src2[JMAXC];
+    int w1[JMAXC], w2[JMAXC];
+    void *dst[2 * JMAXC];
+};
+
+__device__ __forceinline__ void join_emit(const JoinCols &C, int64_t p, int64_t r1, int64_t r2) {
+    for (int c = 0; c < C.l; c++) {
+        if (C.w1[c] == 4) reinterpret_cast<uint32_t *>(C.dst[c])[p] = reinterpret_cast<const uint32_t *>(C.src1[c])[r1];
+        else reinterpret_cast<uint64_t *>(C.dst[c])[p] = reinterpret_cast<const uint64_t *>(C.src1[c])[r1];
+    }
+    for (int c = 0; c < C.k; c++) {
+        if (C.w2[c] == 4) reinterpret_cast<uint32_t *>(C.dst[C.l + c])[p] = reinterpret_cast<const uint32_t *>(C.src2[c])[r2];
+        else reinterpret_cast<uint64_t *>(C.dst[C.l + c])[p] = reinterpret_cast<const uint64_t *>(C.src2[c])[r2];
+    }
+}
+
+struct MjExpandParams {
+    int64_t P, n1;
+    const unsigned long long *offs; // [n1 + 1]
+    const uint32_t *lb;
+    const uint32_t *rid1, *rid2;
+    int64_t slice;                  // output rows per CTA iteration
+    JoinCols C;
+};
+
+// balanced over the OUTPUT: a CTA owns result rows [q * slice, (q + 1) * slice), finds the left rows that produce them
+// with two searches, and every thread then searches only inside that (small, cached) range
+__global__ void __launch_bounds__(256) hk_mj_expand_kernel(const __grid_constant__ MjExpandParams E) {
+    __shared__ long long s_r[2];
+    const int64_t nslices = (E.P + E.slice - 1) / E.slice;
+    for (int64_t q = blockIdx.x; q < nslices; q += gridDim.x) {
+        const int64_t p0 = q * E.slice, p1 = min(E.P, p0 + E.slice);
+        if (threadIdx.x < 2) { // last i with offs[i] <= p, for p = p0 and p = p1 - 1
+            const unsigned long long p = (unsigned long long)(threadIdx.x == 0 ? p0 : p1 - 1);
+            int64_t lo = 0, hi = E.n1;
+            while (hi - lo > 1) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (E.offs[mid] <= p) lo = mid; else hi = mid;
+            }
+            s_r[threadIdx.x] = lo;
+        }
+        __syncthreads();
+        const int64_t ia = s_r[0], ib = s_r[1];
+        for (int64_t p = p0 + threadIdx.x; p < p1; p += 256) {
+            int64_t lo = ia, hi = ib + 1;
+            while (hi - lo > 1) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (E.offs[mid] <= (unsigned long long)p) lo = mid; else hi = mid;
+            }
+            const int64_t i = lo, j = p - (int64_t)E.offs[i];
+            join_emit(E.C, p, (int64_t)E.rid1[i], (int64_t)E.rid2[(int64_t)E.lb[i] + j]);
+        }
+        __syncthreads();
+    }
+}
+
+// ---- hash join (order = 0) ----
+constexpr int HJ_T = 256, HJ_I = 4, HJ_TILE = HJ_T * HJ_I;
+
+// multiset build: every row gets its own entry (duplicates share a probe sequence)
+template <int KW>
+__global__ void __launch_bounds__(256) hk_hj_build_kernel(const void *key_col, int64_t n, void *htab, unsigned long long hmask) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long *t = reinterpret_cast<unsigned long long *>(htab);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if constexpr (KW == 4) {
+            const uint32_t key = reinterpret_cast<const uint32_t *>(key_col)[i];
+            const unsigned long long packed = (unsigned long long)key | ((unsigned long long)(uint32_t)(i + 1) << 32);
+            unsigned long long h = hk_hash_key<4>(key) & hmask;
+            while (atomicCAS(t + h, 0ull, packed) != 0ull) h = (h + 1) & hmask;
+        } else {
+            const unsigned long long key = reinterpret_cast<const unsigned long long *>(key_col)[i];
+            unsigned long long h = hk_hash_key<8>(key) & hmask;
+            while (atomicCAS(t + 2 * h + 1, 0ull, (unsigned long long)(uint32_t)(i + 1)) != 0ull) h = (h + 1) & hmask;
+            t[2 * h] = key;
+        }
+    }
+}
+
+// visits the build rows matching `key`; F(row) for each
+template <int KW, typename F>
+__device__ __forceinline__ void hj_for_matches(const void *htab, unsigned long long hmask, typename JRaw<KW>::T key, F f) {
+    unsigned long long h = hk_hash_key<KW>(key) & hmask;
+    if constexpr (KW == 4) {
+        const uint2 *t = reinterpret_cast<const uint2 *>(htab);
+        while (true) {
+            const uint2 e = __ldg(t + h);
+            if (e.y == 0u) return;
+            if (e.x == key) f((int64_t)e.y - 1);
+            h = (h + 1) & hmask;
+        }
+    } else {
+        const ulonglong2 *t = reinterpret_cast<const ulonglong2 *>(htab);
+        while (true) {
+            const ulonglong2 e = __ldg(t + h);
+            if ((uint32_t)e.y == 0u) return;
+            if (e.x == key) f((int64_t)(uint32_t)e.y - 1);
+            h = (h + 1) & hmask;
+        }
+    }
+}
+
+struct HjParams {
+    const void *k1;      // probe keys, table row order
+    int64_t n1;
+    const void *htab;
+    unsigned long long hmask;
+    unsigned long long *tile_base; // [num_tiles + 1] exclusive output offset of every probe tile
+    uint64_t *state;
+    unsigned long long *ticket;
+    int64_t num_tiles;
+    JoinCols C;
+};
+
+template <int KW>
+__global__ void __launch_bounds__(HJ_T) hk_hj_count_kernel(const __grid_constant__ HjParams P) {
+    using KT = typename JRaw<KW>::T;
+    __shared__ unsigned long long s_w[HJ_T / 32];
+    __shared__ long long s_tile;
+    const KT *k1 = reinterpret_cast<const KT *>(P.k1);
+    while (true) {
+        if (threadIdx.x == 0) s_tile = (long long)atomicAdd(P.ticket, 1ull);
+        __syncthreads();
+        const int64_t tile = s_tile;
+        if (tile >= P.num_tiles) break;
+        const int64_t i0 = tile * HJ_TILE;
+        unsigned long long mine = 0;
+#pragma unroll
+        for (int e = 0; e < HJ_I; e++) {
+            const int64_t i = i0 + e * HJ_T + threadIdx.x;
+            if (i < P.n1) hj_for_matches<KW>(P.htab, P.hmask, k1[i], [&](int64_t) { mine++; });
+        }
+        unsigned long long total;
+        mj_block_excl_scan(mine, s_w, &total);
+        if (threadIdx.x < 32) {
+            const unsigned long long ex = hk_lookback_u64(P.state, tile, total);
+            if (threadIdx.x == 0) {
+                P.tile_base[tile] = ex;
+                if (tile == P.num_tiles - 1) P.tile_base[P.num_tiles] = ex + total;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int KW>
+__global__ void __launch_bounds__(HJ_T) hk_hj_expand_kernel(const __grid_constant__ HjParams P) {
+    using KT = typename JRaw<KW>::T;
+    __shared__ unsigned long long s_w[HJ_T / 32];
+    const KT *k1 = reinterpret_cast<const KT *>(P.k1);
+    for (int64_t tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+        const int64_t i0 = tile * HJ_TILE;
+        // thread-contiguous rows so that the result is grouped by probe row in row order
+        KT key[HJ_I];
+        unsigned long long cnt[HJ_I], mine = 0;
+#pragma unroll
+        for (int e = 0; e < HJ_I; e++) {
+            const int64_t i = i0 + (int64_t)threadIdx.x * HJ_I + e;
+            cnt[e] = 0;
+            key[e] = 0;
+            if (i < P.n1) {
+                key[e] = k1[i];
+                hj_for_matches<KW>(P.htab, P.hmask, key[e], [&](int64_t) { cnt[e]++; });
+            }
+            mine += cnt[e];
+        }
+        unsigned long long total;
+        unsigned long long run = P.tile_base[tile] + mj_block_excl_scan(mine, s_w, &total);
+#pragma unroll
+        for (int e = 0; e < HJ_I; e++) {
+            const int64_t i = i0 + (int64_t)threadIdx.x * HJ_I + e;
+            if (i < P.n1 && cnt[e]) {
+                hj_for_matches<KW>(P.htab, P.hmask, key[e], [&](int64_t r2) {
+                    join_emit(P.C, (int64_t)run, i, r2);
+                    run++;
+                });
+            }
+        }
+    }
+}
+
+int fill_join_cols(hark_ctx *ctx, JoinCols &C, hark_table *t, const hark_table *db1, const hark_table *db2, const int32_t *cols1, int64_t l,
+                   const int32_t *cols2, int64_t k) {
+    C.l = (int)l;
+    C.k = (int)k;
+    for (int64_t j = 0; j < l; j++) {
+        C.src1[j] = db1->cols[cols1[j]].ptr;
+        C.w1[j] = hk_dtype_size(db1->cols[cols1[j]].dtype);
+    }
+    for (int64_t j = 0; j < k; j++) {
+        C.src2[j] = db2->cols[cols2[j]].ptr;
+        C.w2[j] = hk_dtype_size(db2->cols[cols2[j]].dtype);
+    }
+    for (int64_t j = 0; j < l + k; j++) C.dst[j] = t->cols[j].ptr;
+    (void)ctx;
+    return HARK_OK;
+}
+
+// (key, row id) of one side, sorted by key in `dtype` order, stable
+int sort_side_typed(hark_ctx *ctx, Bufs &bufs, const hark_table *db, int32_t col, int32_t dtype, void **keys_out, void **rid_out) {
     const int64_t n = db->n;
     void *iota = nullptr;
     HK_TRY(bufs.alloc(&iota, sizeof(uint32_t) * (size_t)std::max<int64_t>(n, 1)));
     HK_TRY(hk_iota(ctx, iota, n, 4));
     std::vector<hk_sort_array> arrays(2);
     arrays[0].in = db->cols[col].ptr;
-    arrays[0].width = 4;
+    arrays[0].width = hk_dtype_size(dtype);
     arrays[1].in = iota;
     arrays[1].width = 4;
-    std::vector<hk_sort_keyspec> keys{hk_sort_keyspec{0, HARK_U32, 0}};
+    std::vector<hk_sort_keyspec> keys{hk_sort_keyspec{0, dtype, 0}};
     HK_TRY(hk_radix_sort(ctx, n, keys, arrays, 0, nullptr, nullptr));
     bufs.adopt(arrays[0].result);
     bufs.adopt(arrays[1].result);
@@ -234,77 +614,201 @@ int sort_side(hark_ctx *ctx, Bufs &bufs, const hark_table *db, int32_t col, void
 
 } // namespace
 
-int hk_join(hark_ctx *ctx, hark_table **out, const hark_table *db1, const hark_table *db2, int32_t col1, int32_t col2,
-            const int32_t *cols1, int64_t l, const int32_t *cols2, int64_t k) {
+int hk_join_ex(hark_ctx *ctx, hark_table **out, const hark_table *db1, const hark_table *db2, int32_t col1, int32_t col2,
+               const int32_t *cols1, int64_t l, const int32_t *cols2, int64_t k, int32_t order, bool pinned_u32) {
     const int64_t n1 = db1->n, n2 = db2->n;
     const int64_t m1 = (int64_t)db1->cols.size(), m2 = (int64_t)db2->cols.size();
     HK_ARG(ctx, l <= JMAXC && k <= JMAXC, "join: at most 16 projected columns per side");
     // join.fut:55-56 slices db1[:,col1] / db2[:,col2] whenever the table has rows
-    if (n1 > 0) HK_ARG(ctx, col1 >= 0 && col1 < m1, "join: col1 out of bounds");
-    if (n2 > 0) HK_ARG(ctx, col2 >= 0 && col2 < m2, "join: col2 out of bounds");
-    for (auto *t : {db1, db2})
-        for (auto &c : t->cols)
-            HK_ARG(ctx, c.dtype == HARK_I32 || c.dtype == HARK_U32, "join: the reference entry takes u32 tables");
+    if (n1 > 0 || !pinned_u32) HK_ARG(ctx, col1 >= 0 && col1 < m1, "join: col1 out of bounds");
+    if (n2 > 0 || !pinned_u32) HK_ARG(ctx, col2 >= 0 && col2 < m2, "join: col2 out of bounds");
+    int32_t kdt = HARK_U32;
+    if (pinned_u32) {
+        for (auto *t : {db1, db2})
+            for (auto &c : t->cols)
+                HK_ARG(ctx, c.dtype == HARK_I32 || c.dtype == HARK_U32, "join: the reference entry takes u32 tables (use hark_entry_join_ex for typed tables)");
+    } else {
+        kdt = db1->cols[col1].dtype;
+        HK_ARG(ctx, hk_dtype_int(kdt) && db2->cols[col2].dtype == kdt, "join_ex: both key columns must have the same integer dtype");
+        // the projected columns are part of the call, whether or not any row comes out
+        for (int64_t j = 0; j < l; j++) HK_ARG(ctx, cols1[j] >= 0 && cols1[j] < m1, "join: cols1 index out of bounds");
+        for (int64_t j = 0; j < k; j++) HK_ARG(ctx, cols2[j] >= 0 && cols2[j] < m2, "join: cols2 index out of bounds");
+    }
+    const int kw = hk_dtype_size(kdt);
     ctx->entry_begin();
     std::vector<int32_t> odt((size_t)(l + k), HARK_U32);
+    if (!pinned_u32) {
+        for (int64_t j = 0; j < l; j++) odt[(size_t)j] = db1->cols[cols1[j]].dtype;
+        for (int64_t j = 0; j < k; j++) odt[(size_t)(l + j)] = db2->cols[cols2[j]].dtype;
+    }
     if (n1 == 0 || n2 == 0) {
         HK_TRY(hk_table_alloc(ctx, out, 0, 0, odt.data(), l + k));
         ctx->entry_end(0, n1 + n2, 0);
         return HARK_OK;
     }
-    HK_ARG(ctx, n1 < 0xffffffffll && n2 < 0xffffffffll, "join: more than 2^32-1 rows per side is not supported");
+    HK_ARG(ctx, n2 < 0xffffffffll, "join: more than 2^32-2 rows in db2 is not supported");
     Bufs bufs(ctx);
-    void *k1 = nullptr, *r1 = nullptr, *k2 = nullptr, *r2 = nullptr;
-    HK_TRY(sort_side(ctx, bufs, db1, col1, &k1, &r1));
-    HK_TRY(sort_side(ctx, bufs, db2, col2, &k2, &r2));
-    uint32_t *lb = nullptr, *cnt = nullptr;
-    unsigned long long *offs = nullptr;
-    HK_TRY(bufs.alloc((void **)&lb, sizeof(uint32_t) * (size_t)n1));
-    HK_TRY(bufs.alloc((void **)&cnt, sizeof(uint32_t) * (size_t)n1));
-    HK_TRY(bufs.alloc((void **)&offs, sizeof(unsigned long long) * (size_t)(n1 + 1)));
-    ctx->kernel_begin();
-    hk_join_bounds_kernel<<<grid_for(ctx, n1, 16), 256, 0, ctx->stream>>>((const uint32_t *)k1, n1, (const uint32_t *)k2, n2, lb, cnt);
-    HK_CHECK_LAUNCH(ctx);
-    hk_join_scan_kernel<<<1, 1024, 0, ctx->stream>>>(cnt, offs, n1);
-    HK_CHECK_LAUNCH(ctx);
-    ctx->count_launch(2);
-    HK_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, offs + n1, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    HK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    const int64_t P = (int64_t)ctx->h_scalars[0];
-    if (P > 0) { // join.fut:69-73 index rows of both tables with the projected columns
+    auto check_proj = [&]() -> int { // join.fut:69-73 index rows of both tables with the projected columns (only when rows come out)
         for (int64_t j = 0; j < l; j++) HK_ARG(ctx, cols1[j] >= 0 && cols1[j] < m1, "join: cols1 index out of bounds");
         for (int64_t j = 0; j < k; j++) HK_ARG(ctx, cols2[j] >= 0 && cols2[j] < m2, "join: cols2 index out of bounds");
-    }
+        return HARK_OK;
+    };
+    int64_t rowbytes = 0;
     hark_table *t = nullptr;
-    HK_TRY(hk_table_alloc(ctx, &t, P, P, odt.data(), l + k));
-    if (P > 0) {
-        ExpandParams E;
-        memset(&E, 0, sizeof E);
-        E.P = P;
-        E.n1 = n1;
-        E.offs = offs;
-        E.lb = lb;
-        E.rid1 = (const uint32_t *)r1;
-        E.rid2 = (const uint32_t *)r2;
-        E.l = (int)l;
-        E.k = (int)k;
-        for (int64_t j = 0; j < l; j++) E.src1[j] = (const uint32_t *)db1->cols[cols1[j]].ptr;
-        for (int64_t j = 0; j < k; j++) E.src2[j] = (const uint32_t *)db2->cols[cols2[j]].ptr;
-        for (int64_t j = 0; j < l + k; j++) E.dst[j] = (uint32_t *)t->cols[j].ptr;
-        hk_join_expand_kernel<<<grid_for(ctx, P, 16), 256, 0, ctx->stream>>>(E);
-        cudaError_t e = cudaGetLastError();
+    int64_t P = 0;
+
+    if (order != 0) {
+        // ---- sort both sides, merge ----
+        HK_ARG(ctx, n1 < 0xffffffffll, "join (ordered): more than 2^32-2 rows in db1 is not supported; use order = 0");
+        void *k1 = nullptr, *r1 = nullptr, *k2 = nullptr, *r2 = nullptr;
+        HK_TRY(sort_side_typed(ctx, bufs, db1, col1, kdt, &k1, &r1));
+        HK_TRY(sort_side_typed(ctx, bufs, db2, col2, kdt, &k2, &r2));
+        MjParams M;
+        memset(&M, 0, sizeof M);
+        M.k1 = k1;
+        M.k2 = k2;
+        M.n1 = n1;
+        M.n2 = n2;
+        M.dtype = kdt;
+        M.num_tiles = (n1 + MJ_TILE - 1) / MJ_TILE;
+        HK_TRY(bufs.alloc((void **)&M.lb, sizeof(uint32_t) * (size_t)n1));
+        HK_TRY(bufs.alloc((void **)&M.offs, sizeof(unsigned long long) * (size_t)(n1 + 1)));
+        HK_TRY(bufs.alloc((void **)&M.state, sizeof(uint64_t) * (size_t)(M.num_tiles + 1)));
+        HK_CUDA(ctx, cudaMemsetAsync(M.state, 0, sizeof(uint64_t) * (size_t)(M.num_tiles + 1), ctx->stream));
+        M.ticket = (unsigned long long *)(M.state + M.num_tiles);
+        ctx->kernel_begin();
+        const unsigned g = (unsigned)std::min<int64_t>(M.num_tiles, (int64_t)ctx->num_sms * 8);
+        if (kw == 4) hk_mj_bounds_kernel<4><<<g, MJ_T, 0, ctx->stream>>>(M);
+        else hk_mj_bounds_kernel<8><<<g, MJ_T, 0, ctx->stream>>>(M);
+        HK_CHECK_LAUNCH(ctx);
         ctx->count_launch();
-        if (e != cudaSuccess) {
-            hark_table_free(ctx, t);
-            return ctx->fail(HARK_ERR_CUDA, std::string("join(expand): ") + cudaGetErrorString(e));
+        HK_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, M.offs + n1, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        HK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        P = (int64_t)ctx->h_scalars[0];
+        if (P > 0) HK_TRY(check_proj());
+        HK_TRY(hk_table_alloc(ctx, &t, P, P, odt.data(), l + k));
+        if (P > 0) {
+            MjExpandParams E;
+            memset(&E, 0, sizeof E);
+            E.P = P;
+            E.n1 = n1;
+            E.offs = M.offs;
+            E.lb = M.lb;
+            E.rid1 = (const uint32_t *)r1;
+            E.rid2 = (const uint32_t *)r2;
+            E.slice = 4096;
+            fill_join_cols(ctx, E.C, t, db1, db2, cols1, l, cols2, k);
+            const int64_t nslices = (P + E.slice - 1) / E.slice;
+            hk_mj_expand_kernel<<<(unsigned)std::min<int64_t>(nslices, (int64_t)ctx->num_sms * 16), 256, 0, ctx->stream>>>(E);
+            cudaError_t e = cudaGetLastError();
+            ctx->count_launch();
+            if (e != cudaSuccess) {
+                hark_table_free(ctx, t);
+                return ctx->fail(HARK_ERR_CUDA, std::string("join(expand): ") + cudaGetErrorString(e));
+            }
         }
+        ctx->kernel_end();
+    } else {
+        // ---- hash build on db2, probe with db1 ----
+        uint64_t H = 1024;
+        while (H < 2ull * (uint64_t)n2) H <<= 1;
+        const size_t esz = kw == 4 ? 8 : 16;
+        void *tab = nullptr;
+        HK_TRY(bufs.alloc(&tab, (size_t)H * esz));
+        HK_CUDA(ctx, cudaMemsetAsync(tab, 0, (size_t)H * esz, ctx->stream));
+        ctx->kernel_begin();
+        if (kw == 4) hk_hj_build_kernel<4><<<grid_for(ctx, n2), 256, 0, ctx->stream>>>(db2->cols[col2].ptr, n2, tab, H - 1);
+        else hk_hj_build_kernel<8><<<grid_for(ctx, n2), 256, 0, ctx->stream>>>(db2->cols[col2].ptr, n2, tab, H - 1);
+        HK_CHECK_LAUNCH(ctx);
+        HjParams J;
+        memset(&J, 0, sizeof J);
+        J.k1 = db1->cols[col1].ptr;
+        J.n1 = n1;
+        J.htab = tab;
+        J.hmask = H - 1;
+        J.num_tiles = (n1 + HJ_TILE - 1) / HJ_TILE;
+        HK_TRY(bufs.alloc((void **)&J.tile_base, sizeof(unsigned long long) * (size_t)(J.num_tiles + 1)));
+        HK_TRY(bufs.alloc((void **)&J.state, sizeof(uint64_t) * (size_t)(J.num_tiles + 1)));
+        HK_CUDA(ctx, cudaMemsetAsync(J.state, 0, sizeof(uint64_t) * (size_t)(J.num_tiles + 1), ctx->stream));
+        J.ticket = (unsigned long long *)(J.state + J.num_tiles);
+        const unsigned g = (unsigned)std::min<int64_t>(J.num_tiles, (int64_t)ctx->num_sms * 8);
+        if (kw == 4) hk_hj_count_kernel<4><<<g, HJ_T, 0, ctx->stream>>>(J);
+        else hk_hj_count_kernel<8><<<g, HJ_T, 0, ctx->stream>>>(J);
+        HK_CHECK_LAUNCH(ctx);
+        ctx->count_launch(2);
+        HK_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, J.tile_base + J.num_tiles, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        HK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        P = (int64_t)ctx->h_scalars[0];
+        HK_TRY(hk_table_alloc(ctx, &t, P, P, odt.data(), l + k));
+        if (P > 0) {
+            fill_join_cols(ctx, J.C, t, db1, db2, cols1, l, cols2, k);
+            if (kw == 4) hk_hj_expand_kernel<4><<<g, HJ_T, 0, ctx->stream>>>(J);
+            else hk_hj_expand_kernel<8><<<g, HJ_T, 0, ctx->stream>>>(J);
+            cudaError_t e = cudaGetLastError();
+            ctx->count_launch();
+            if (e != cudaSuccess) {
+                hark_table_free(ctx, t);
+                return ctx->fail(HARK_ERR_CUDA, std::string("join(hash expand): ") + cudaGetErrorString(e));
+            }
+        }
+        ctx->kernel_end();
     }
-    ctx->kernel_end();
-    ctx->entry_end(4 * (n1 + n2) + 4 * P * (l + k) * 2, n1 + n2, P);
+    for (auto &c : t->cols) rowbytes += hk_dtype_size(c.dtype);
+    ctx->entry_end((int64_t)kw * (n1 + n2) + P * rowbytes * 2, n1 + n2, P);
     *out = t;
     return HARK_OK;
 }
 
+int hk_join(hark_ctx *ctx, hark_table **out, const hark_table *db1, const hark_table *db2, int32_t col1, int32_t col2,
+            const int32_t *cols1, int64_t l, const int32_t *cols2, int64_t k) {
+    return hk_join_ex(ctx, out, db1, db2, col1, col2, cols1, l, cols2, k, 1, true);
+}
+
+namespace {
+
+// The open-addressing table of a dimension's key column (see hk_hash_build_kernel).  payload_row: entries carry the
+// dimension row instead of the group slot.  Fails with HARK_ERR_ARG when the key is not unique.
+int build_hash_table(hark_ctx *ctx, Bufs &bufs, const hark_table *dim, int32_t pk_col, int32_t g_col, unsigned long long g_lo,
+                     int payload_row, void **htab_out, uint64_t *hmask_out) {
+    const int64_t nd = dim->n;
+    const int kw = hk_dtype_size(dim->cols[pk_col].dtype);
+    uint64_t H = 1024;
+    while (H < 2ull * (uint64_t)nd) H <<= 1;
+    const size_t esz = kw == 4 ? 8 : 16;
+    void *tab = nullptr;
+    unsigned int *dup = nullptr;
+    HK_TRY(bufs.alloc(&tab, (size_t)H * esz));
+    HK_TRY(bufs.alloc((void **)&dup, sizeof(unsigned int)));
+    HK_CUDA(ctx, cudaMemsetAsync(tab, 0, (size_t)H * esz, ctx->stream));
+    HK_CUDA(ctx, cudaMemsetAsync(dup, 0, sizeof(unsigned int), ctx->stream));
+    const void *pk = dim->cols[pk_col].ptr, *g = dim->cols[g_col].ptr;
+    const int g_dtype = dim->cols[g_col].dtype;
+    if (kw == 4) {
+        hk_hash_build_kernel<4><<<grid_for(ctx, nd), 256, 0, ctx->stream>>>(pk, g, g_dtype, nd, g_lo, payload_row, tab, H - 1, dup);
+        HK_CHECK_LAUNCH(ctx);
+        ctx->count_launch();
+    } else {
+        hk_hash_build_kernel<8><<<grid_for(ctx, nd), 256, 0, ctx->stream>>>(pk, g, g_dtype, nd, g_lo, payload_row, tab, H - 1, dup);
+        HK_CHECK_LAUNCH(ctx);
+        hk_hash_verify_kernel<<<grid_for(ctx, nd), 256, 0, ctx->stream>>>(pk, nd, tab, H - 1, dup);
+        HK_CHECK_LAUNCH(ctx);
+        ctx->count_launch(2);
+    }
+    HK_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, dup, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+    HK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (((unsigned int *)ctx->h_scalars)[0] != 0) return ctx->fail(HARK_ERR_ARG, "join_groupby: dim.pk is not unique");
+    *htab_out = tab;
+    *hmask_out = H - 1;
+    return HARK_OK;
+}
+
+} // namespace
+
+// SELECT d.g, agg(f.s...) FROM fact f JOIN dim d ON f.fk = d.pk GROUP BY d.g, dim.pk unique.
+// Build side: a direct-address lookup over [pk_min, pk_max] when the keys are dense (span <= 16 x rows), else an
+// open-addressing hash table ("join.build": 0 auto, 1 lookup, 2 hash).  Probe side: fused into K2 (probe + aggregate in
+// one pass over the fact columns, partitioned by slices of the build structure so the slice being probed is
+// L2-resident) when the group domain fits one shared-memory table; otherwise probe -> filter -> GROUP BY.
 int hk_join_groupby(hark_ctx *ctx, hark_table **out, const hark_table *fact, const hark_table *dim, int32_t fk_col,
                     int32_t pk_col, int32_t g_col, const int32_t *s_cols, const int32_t *ops, int64_t c) {
     const int64_t nf = fact->n, nd = dim->n;
@@ -320,17 +824,21 @@ int hk_join_groupby(hark_ctx *ctx, hark_table **out, const hark_table *fact, con
     Bufs bufs(ctx);
     const int32_t g_dtype = dim->cols[g_col].dtype;
     const int gw = hk_dtype_size(g_dtype);
+    const int32_t fk_dtype = fact->cols[fk_col].dtype, pk_dtype = dim->cols[pk_col].dtype;
 
-    // ---- build: direct-address lookup pk -> dim row over [pk_min, pk_max] ----
     long long *d_mm = nullptr;
     HK_TRY(bufs.alloc((void **)&d_mm, 2 * sizeof(long long)));
     long long pk_min = 0, pk_span = 0;
     uint32_t *lut = nullptr;
+    void *htab = nullptr;
+    uint64_t hmask = 0;
+    bool use_hash = false;
     if (nd > 0) {
+        // ---- key range of the build side ----
         ((long long *)ctx->h_scalars)[0] = LLONG_MAX;
         ((long long *)ctx->h_scalars)[1] = LLONG_MIN;
         HK_CUDA(ctx, cudaMemcpyAsync(d_mm, ctx->h_scalars, 2 * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-        hk_minmax_int_kernel<<<grid_for(ctx, nd), 256, 0, ctx->stream>>>(dim->cols[pk_col].ptr, dim->cols[pk_col].dtype, nd, d_mm);
+        hk_minmax_int_kernel<<<grid_for(ctx, nd), 256, 0, ctx->stream>>>(dim->cols[pk_col].ptr, pk_dtype, nd, d_mm);
         HK_CHECK_LAUNCH(ctx);
         ctx->count_launch();
         HK_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, d_mm, 2 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
@@ -338,63 +846,79 @@ int hk_join_groupby(hark_ctx *ctx, hark_table **out, const hark_table *fact, con
         pk_min = ((long long *)ctx->h_scalars)[0];
         const long long pk_max = ((long long *)ctx->h_scalars)[1];
         const unsigned long long span = (unsigned long long)pk_max - (unsigned long long)pk_min + 1ull;
-        if (span == 0 || span > (unsigned long long)nd * 16ull + (1ull << 22))
-            return ctx->fail(HARK_ERR_UNSUPPORTED, "join_groupby: dimension keys too sparse for the direct-address build "
-                                                   "(span > 16 x rows); a hashed build is not implemented yet");
+        const bool dense_ok = span != 0 && span <= (unsigned long long)nd * 16ull + (1ull << 22);
+        const int64_t build = ctx->opt("join.build", 0);
+        use_hash = build == 2 || (build != 1 && !dense_ok);
+        if (!use_hash && !dense_ok)
+            return ctx->fail(HARK_ERR_UNSUPPORTED, "join_groupby: join.build=1 (direct-address lookup) needs dense keys (span <= 16 x rows)");
+        if (use_hash) {
+            // the probe hashes the raw bits of fk: both key columns must have one representation
+            const bool same = fk_dtype == pk_dtype || (hk_dtype_size(fk_dtype) == 4 && hk_dtype_size(pk_dtype) == 4 && pk_min >= 0 &&
+                                                       pk_max <= 0x7fffffffll);
+            if (!same)
+                return ctx->fail(HARK_ERR_UNSUPPORTED, "join_groupby (hash build): fk and pk must have the same dtype");
+        }
         pk_span = (long long)span;
-        HK_TRY(bufs.alloc((void **)&lut, sizeof(uint32_t) * (size_t)span));
-        HK_CUDA(ctx, cudaMemsetAsync(lut, 0, sizeof(uint32_t) * (size_t)span, ctx->stream));
-        unsigned int *dup = (unsigned int *)(d_mm); // reuse: [0] as the duplicate flag
+    }
+    ctx->counters["join.last_build"] = nd == 0 ? 0 : (use_hash ? 2 : 1);
 
-        // ---- K2 in lookup mode: probe and aggregate in one pass over the fact columns, no materialised join ----
-        if (ctx->opt("groupby.impl", 0) != 1 && nf > 0 && c <= HK_DENSE_MAX_AGGS) {
-            hk_dense_req rq;
-            rq.n = nf;
-            rq.key = fact->cols[fk_col].ptr;
-            rq.key_dtype = fact->cols[fk_col].dtype;
-            rq.out_key_dtype = g_dtype;
-            rq.c = (int)c;
-            bool eligible = true;
-            std::vector<int> val_of_col((size_t)mf, -1);
-            for (int64_t j = 0; j < c && eligible; j++) {
-                int code = ops[j];
-                if (code < HARK_AGG_PROD || code > HARK_AGG_SUMF64) code = HARK_AGG_MIN;
-                rq.agg_code[j] = code;
-                if (code == HARK_AGG_COUNT) {
-                    rq.agg_val[j] = -1;
-                    continue;
-                }
-                const int col = s_cols[j];
-                if (val_of_col[col] < 0) {
-                    if (rq.nvals == HK_DENSE_MAX_VALS) {
-                        eligible = false;
-                        break;
-                    }
-                    val_of_col[col] = rq.nvals;
-                    rq.vals[rq.nvals] = fact->cols[col].ptr;
-                    rq.val_dtypes[rq.nvals] = fact->cols[col].dtype;
-                    rq.nvals++;
-                }
-                rq.agg_val[j] = val_of_col[col];
+    // ---- K2 in lookup / hash mode: probe and aggregate in one pass over the fact columns, no materialised join ----
+    if (nd > 0 && ctx->opt("groupby.impl", 0) != 1 && nf > 0 && c <= HK_DENSE_MAX_AGGS) {
+        hk_dense_req rq;
+        rq.n = nf;
+        rq.key = fact->cols[fk_col].ptr;
+        rq.key_dtype = fk_dtype;
+        rq.out_key_dtype = g_dtype;
+        rq.c = (int)c;
+        bool eligible = true;
+        std::vector<int> val_of_col((size_t)mf, -1);
+        for (int64_t j = 0; j < c && eligible; j++) {
+            int code = ops[j];
+            if (code < HARK_AGG_PROD || code > HARK_AGG_SUMF64) code = HARK_AGG_MIN;
+            rq.agg_code[j] = code;
+            if (code == HARK_AGG_COUNT) {
+                rq.agg_val[j] = -1;
+                continue;
             }
-            if (eligible) {
-                HK_TRY(hk_column_minmax(ctx, dim->cols[g_col], nd, g_dtype, &rq.g_lo, &rq.g_hi));
-                if (rq.g_hi - rq.g_lo < (1ull << 20)) {
+            const int col = s_cols[j];
+            if (val_of_col[col] < 0) {
+                if (rq.nvals == HK_DENSE_MAX_VALS) {
+                    eligible = false;
+                    break;
+                }
+                val_of_col[col] = rq.nvals;
+                rq.vals[rq.nvals] = fact->cols[col].ptr;
+                rq.val_cols[rq.nvals] = &fact->cols[col];
+                rq.val_dtypes[rq.nvals] = fact->cols[col].dtype;
+                rq.nvals++;
+            }
+            rq.agg_val[j] = val_of_col[col];
+        }
+        if (eligible) {
+            HK_TRY(hk_column_minmax(ctx, dim->cols[g_col], nd, g_dtype, &rq.g_lo, &rq.g_hi));
+            if (rq.g_hi - rq.g_lo < (1ull << 20)) {
+                if (use_hash) {
+                    HK_TRY(build_hash_table(ctx, bufs, dim, pk_col, g_col, (unsigned long long)rq.g_lo, 0, &htab, &hmask));
+                    rq.htab = htab;
+                    rq.hmask = hmask;
+                } else {
+                    HK_TRY(bufs.alloc((void **)&lut, sizeof(uint32_t) * (size_t)pk_span));
+                    HK_CUDA(ctx, cudaMemsetAsync(lut, 0, sizeof(uint32_t) * (size_t)pk_span, ctx->stream));
                     unsigned long long *nz = (unsigned long long *)d_mm;
                     HK_CUDA(ctx, cudaMemsetAsync(nz, 0, sizeof(unsigned long long), ctx->stream));
                     // a lookup much larger than L2: bring the dimension rows into lookup-slice order first, so the
                     // scattered stores below complete whole sectors while the slice is still L2-resident
                     const void *pk_src = dim->cols[pk_col].ptr, *g_src = dim->cols[g_col].ptr;
-                    const int pkw = hk_dtype_size(dim->cols[pk_col].dtype);
-                    if ((uint64_t)span * 4ull > (96ull << 20) && gw == 4) {
+                    const int pkw = hk_dtype_size(pk_dtype);
+                    if ((uint64_t)pk_span * 4ull > (96ull << 20) && gw == 4) {
                         hk_part_spec ps;
-                        ps.dtype = dim->cols[pk_col].dtype;
+                        ps.dtype = pk_dtype;
                         ps.base = pkw == 4 ? (uint64_t)(ps.dtype == HARK_U32 ? (uint32_t)pk_min : ((uint32_t)(int32_t)pk_min ^ 0x80000000u))
                                            : ((uint64_t)pk_min ^ 0x8000000000000000ull);
-                        ps.span = (uint64_t)span;
+                        ps.span = (uint64_t)pk_span;
                         ps.shift = 22; // 4 Mi entries = 16 MB of lookup per bin
-                        while ((((uint64_t)span - 1) >> ps.shift) + 1 > 256) ps.shift++;
-                        ps.nbins = (int)((((uint64_t)span - 1) >> ps.shift) + 1);
+                        while ((((uint64_t)pk_span - 1) >> ps.shift) + 1 > 256) ps.shift++;
+                        ps.nbins = (int)((((uint64_t)pk_span - 1) >> ps.shift) + 1);
                         void *pko = nullptr, *go[3] = {nullptr, nullptr, nullptr};
                         unsigned long long *offs = nullptr;
                         const void *gv[1] = {g_src};
@@ -406,52 +930,74 @@ int hk_join_groupby(hark_ctx *ctx, hark_table **out, const hark_table *fact, con
                         g_src = go[0];
                     }
                     hk_slot_lut_build_kernel<<<grid_for(ctx, nd), 256, 0, ctx->stream>>>(
-                        pk_src, dim->cols[pk_col].dtype, g_src, g_dtype, nd, pk_min, (unsigned long long)rq.g_lo, lut);
+                        pk_src, pk_dtype, g_src, g_dtype, nd, pk_min, (unsigned long long)rq.g_lo, lut);
                     HK_CHECK_LAUNCH(ctx);
-                    hk_count_nonzero_kernel<<<grid_for(ctx, (int64_t)span / 4 + 1), 256, 0, ctx->stream>>>(lut, (int64_t)span, nz);
+                    hk_count_nonzero_kernel<<<grid_for(ctx, (int64_t)pk_span / 4 + 1), 256, 0, ctx->stream>>>(lut, (int64_t)pk_span, nz);
                     HK_CHECK_LAUNCH(ctx);
                     ctx->count_launch(2);
                     HK_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, nz, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
                     HK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                    if ((int64_t)ctx->h_scalars[0] != nd)
-                        return ctx->fail(HARK_ERR_ARG, "join_groupby: dim.pk is not unique");
+                    if ((int64_t)ctx->h_scalars[0] != nd) return ctx->fail(HARK_ERR_ARG, "join_groupby: dim.pk is not unique");
                     rq.lut = lut;
                     rq.pk_min = pk_min;
                     rq.pk_span = pk_span;
-                    bool handled = false;
-                    hark_table *t = nullptr;
-                    HK_TRY(hk_dense_groupby(ctx, &t, rq, &handled));
-                    if (handled) {
-                        int64_t alg = nf * hk_dtype_size(rq.key_dtype) + nf * 4 * rq.nvals;
-                        alg += nd * (hk_dtype_size(dim->cols[pk_col].dtype) + gw);
-                        ctx->entry_end(alg, nf + nd, t->n);
-                        *out = t;
-                        return HARK_OK;
-                    }
-                    HK_CUDA(ctx, cudaMemsetAsync(lut, 0, sizeof(uint32_t) * (size_t)span, ctx->stream)); // rebuild as row lut below
                 }
+                bool handled = false;
+                hark_table *t = nullptr;
+                HK_TRY(hk_dense_groupby(ctx, &t, rq, &handled));
+                if (handled) {
+                    int64_t alg = nf * hk_dtype_size(rq.key_dtype) + nf * 4 * rq.nvals;
+                    alg += nd * (hk_dtype_size(pk_dtype) + gw);
+                    ctx->entry_end(alg, nf + nd, t->n);
+                    *out = t;
+                    return HARK_OK;
+                }
+                htab = nullptr; // built with group slots: the materialising path below needs dimension rows
             }
         }
-        HK_CUDA(ctx, cudaMemsetAsync(dup, 0, sizeof(unsigned int), ctx->stream));
-        hk_lut_build_kernel<<<grid_for(ctx, nd), 256, 0, ctx->stream>>>(dim->cols[pk_col].ptr, dim->cols[pk_col].dtype, nd, pk_min, lut, dup);
-        HK_CHECK_LAUNCH(ctx);
-        ctx->count_launch();
-        HK_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, dup, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
-        HK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (((unsigned int *)ctx->h_scalars)[0] != 0)
-            return ctx->fail(HARK_ERR_ARG, "join_groupby: dim.pk is not unique");
     }
-    // ---- probe: group key + hit flag per fact row ----
+
+    // ---- materialising path: row lookup / hash table, probe -> (group key, hit) per fact row ----
+    if (nd > 0) {
+        if (use_hash) {
+            HK_TRY(build_hash_table(ctx, bufs, dim, pk_col, g_col, 0ull, 1, &htab, &hmask));
+        } else {
+            if (!lut) HK_TRY(bufs.alloc((void **)&lut, sizeof(uint32_t) * (size_t)pk_span));
+            HK_CUDA(ctx, cudaMemsetAsync(lut, 0, sizeof(uint32_t) * (size_t)pk_span, ctx->stream));
+            unsigned int *dup = (unsigned int *)(d_mm);
+            HK_CUDA(ctx, cudaMemsetAsync(dup, 0, sizeof(unsigned int), ctx->stream));
+            hk_lut_build_kernel<<<grid_for(ctx, nd), 256, 0, ctx->stream>>>(dim->cols[pk_col].ptr, pk_dtype, nd, pk_min, lut, dup);
+            HK_CHECK_LAUNCH(ctx);
+            ctx->count_launch();
+            HK_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, dup, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+            HK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (((unsigned int *)ctx->h_scalars)[0] != 0) return ctx->fail(HARK_ERR_ARG, "join_groupby: dim.pk is not unique");
+        }
+    }
     void *gkey = nullptr;
     uint32_t *hit = nullptr;
     HK_TRY(bufs.alloc(&gkey, (size_t)std::max<int64_t>(nf, 1) * gw));
     HK_TRY(bufs.alloc((void **)&hit, sizeof(uint32_t) * (size_t)std::max<int64_t>(nf, 1)));
     ctx->kernel_begin();
     if (nf > 0) {
-        hk_probe_kernel<<<grid_for(ctx, nf, 16), 256, 0, ctx->stream>>>(fact->cols[fk_col].ptr, fact->cols[fk_col].dtype, nf, pk_min,
-                                                                       pk_span, lut, dim->cols[g_col].ptr, gw, gkey, hit);
-        HK_CHECK_LAUNCH(ctx);
-        ctx->count_launch();
+        if (nd == 0) {
+            HK_CUDA(ctx, cudaMemsetAsync(hit, 0, sizeof(uint32_t) * (size_t)nf, ctx->stream));
+            HK_CUDA(ctx, cudaMemsetAsync(gkey, 0, (size_t)nf * gw, ctx->stream));
+        } else if (use_hash) {
+            if (hk_dtype_size(fk_dtype) == 4)
+                hk_hash_probe_kernel<4><<<grid_for(ctx, nf, 16), 256, 0, ctx->stream>>>(fact->cols[fk_col].ptr, nf, htab, hmask,
+                                                                                      dim->cols[g_col].ptr, gw, gkey, hit);
+            else
+                hk_hash_probe_kernel<8><<<grid_for(ctx, nf, 16), 256, 0, ctx->stream>>>(fact->cols[fk_col].ptr, nf, htab, hmask,
+                                                                                      dim->cols[g_col].ptr, gw, gkey, hit);
+            HK_CHECK_LAUNCH(ctx);
+            ctx->count_launch();
+        } else {
+            hk_probe_kernel<<<grid_for(ctx, nf, 16), 256, 0, ctx->stream>>>(fact->cols[fk_col].ptr, fk_dtype, nf, pk_min, pk_span, lut,
+                                                                           dim->cols[g_col].ptr, gw, gkey, hit);
+            HK_CHECK_LAUNCH(ctx);
+            ctx->count_launch();
+        }
     }
     // ---- keep the matched rows (K1), then GROUP BY the looked-up key ----
     hark_table tmp; // borrowed view: [gkey, hit, distinct fact value columns]
@@ -488,9 +1034,9 @@ int hk_join_groupby(hark_ctx *ctx, hark_table **out, const hark_table *fact, con
     hark_table_free(ctx, matched);
     if (rc != HARK_OK) return rc;
     int64_t alg = 0;
-    alg += nf * hk_dtype_size(fact->cols[fk_col].dtype);
+    alg += nf * hk_dtype_size(fk_dtype);
     for (size_t j = 2; j < tmp.cols.size(); j++) alg += nf * hk_dtype_size(tmp.cols[j].dtype);
-    alg += nd * (hk_dtype_size(dim->cols[pk_col].dtype) + gw);
+    alg += nd * (hk_dtype_size(pk_dtype) + gw);
     ctx->entry_end(alg, nf + nd, res->n);
     *out = res;
     return HARK_OK;

@@ -320,6 +320,166 @@ int launch_part(hark_ctx *ctx, const PartParams &P) {
     return HARK_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// K8t — tile-local partition with a directory (the default producer of K2's input since round 2).
+//
+// The consumers of a partition here only AGGREGATE, so rows of a bin need not be contiguous across the whole table —
+// only findable.  Every 4096-row tile is therefore sorted by bin INSIDE shared memory and leaves as ONE contiguous,
+// 16-byte aligned block of the scratch table (tile t -> rows [t·4096, (t+1)·4096)), rows stored array-of-structs
+// ([key words | value words], RW = KW/4 + NV words per row), together with a directory word per (tile, bin) =
+// start | end << 16 of the bin's run inside the tile.  Consequences against K8a above:
+//   * no histogram pre-pass (one streaming read of the key column saved) and no scan kernel — the layout is static;
+//   * the write-out is a TMA bulk copy shared -> global (cp.async.bulk, SASS UBLKCP.G.S) issued by one thread: no
+//     per-row shared-memory read, no per-row address look-up, no per-row store instruction;
+//   * one shared-memory store per row (the packed row) instead of one per carried array.
+// HBM bytes: n·(KW + 4·NV) read + the same written + 4·nbins per tile of directory.  The consumer walks, for bin b,
+// the segments (t, b) of all tiles (dense_agg.cu, hk_dagg_tiles_kernel).
+// ------------------------------------------------------------------------------------------------
+constexpr int TP_T = 512;             // threads per CTA, two CTAs per SM
+constexpr int TP_TILE = TP_T * PI;    // rows per tile (4096: bin ends fit the directory's 16-bit halves)
+static_assert(TP_TILE == HK_TPART_TILE, "tile size is part of the directory format");
+
+struct TPartParams {
+    DigitFn f;
+    int hash;            // 1: bin = (hk_hash_key(raw) & hmask) >> f.shift  (slices of a hash table, join.cu)
+    uint64_t hmask;
+    const void *key_in;
+    const uint32_t *val_in[PMAXV];
+    uint32_t *rows_out;  // [num_tiles * TP_TILE][RW]
+    uint32_t *dir;       // [num_tiles][nbins]
+    int64_t n;
+    int64_t num_tiles;
+    int64_t tiles_per_cta;
+    int nbins;
+};
+
+__device__ __forceinline__ void tp_bulk_store(void *gdst, const void *ssrc, uint32_t bytes) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(gdst)), "r"(s),
+                 "r"(bytes)
+                 : "memory");
+}
+
+template <int KW>
+__device__ __forceinline__ uint32_t tpart_digit(typename KRaw<KW>::T raw, const TPartParams &P) {
+    if (P.hash) return (uint32_t)((hk_hash_key<KW>(raw) & P.hmask) >> P.f.shift);
+    return part_digit<KW>(raw, P.f);
+}
+
+template <int KW, int NV>
+__global__ void __launch_bounds__(TP_T, 2) hk_tpart_kernel(const __grid_constant__ TPartParams P) {
+    using KT = typename KRaw<KW>::T;
+    constexpr int RW = KW / 4 + NV;
+    extern __shared__ __align__(128) uint32_t s_stage[]; // TP_TILE rows x RW words
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint32_t s_binstart[256];
+    __shared__ uint32_t s_wtot[8];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t t0 = (int64_t)blockIdx.x * P.tiles_per_cta;
+    const int64_t t1 = min(P.num_tiles, t0 + P.tiles_per_cta);
+    if (tid < 256) s_hist[tid] = 0;
+    if (t0 >= t1) return;
+
+    PartParams L; // the loader of K8a, reused: it only looks at the input pointers and n
+    L.key_in = P.key_in;
+    for (int v = 0; v < PMAXV; v++) L.val_in[v] = P.val_in[v];
+    KT key[PI];
+    uint32_t val[NV > 0 ? NV : 1][PI];
+    int count = (int)min((int64_t)TP_TILE, P.n - t0 * TP_TILE);
+    part_load_tile<KW, NV, TP_T>(L, t0 * TP_TILE, count, tid, key, val);
+    __syncthreads();
+
+    for (int64_t tile = t0; tile < t1; tile++) {
+        // ---- rank inside the tile: one shared-memory atomic per row (bin << 16 | rank) ----
+        uint32_t rd[PI];
+#pragma unroll
+        for (int i = 0; i < PI; i++) {
+            const int idx = ((i >> 2) * TP_T + tid) * 4 + (i & 3);
+            if (count == TP_TILE || idx < count) {
+                const uint32_t d = tpart_digit<KW>(key[i], P);
+                rd[i] = (d << 16) | atomicAdd(&s_hist[d], 1u);
+            } else {
+                rd[i] = 0xffffffffu;
+            }
+        }
+        // the bulk copy of the previous tile must have finished READING the stage before anyone overwrites it
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncthreads();
+        // ---- thread b owns bin b: start of the bin's run inside the tile, directory word ----
+        {
+            const uint32_t sum = tid < 256 ? s_hist[tid] : 0u;
+            if (tid < 256) s_hist[tid] = 0;
+            const uint32_t inc = hk_warp_incl_scan_u32(sum);
+            if (lane == 31 && warp < 8) s_wtot[warp] = inc;
+            __syncthreads();
+            if (tid < 256) {
+                uint32_t woff = 0;
+                for (int w = 0; w < warp; w++) woff += s_wtot[w];
+                const uint32_t binstart = woff + inc - sum;
+                s_binstart[tid] = binstart;
+                if (tid < P.nbins) P.dir[(size_t)tile * P.nbins + tid] = binstart | ((binstart + sum) << 16);
+            }
+        }
+        __syncthreads();
+        // ---- the packed rows go to their slot of the stage ----
+#pragma unroll
+        for (int i = 0; i < PI; i++) {
+            if (rd[i] != 0xffffffffu) {
+                const uint32_t pos = s_binstart[rd[i] >> 16] + (rd[i] & 0xffffu);
+                uint32_t w[RW];
+                if constexpr (KW == 4) {
+                    w[0] = key[i];
+                } else {
+                    w[0] = (uint32_t)key[i];
+                    w[1] = (uint32_t)(key[i] >> 32);
+                }
+#pragma unroll
+                for (int v = 0; v < NV; v++) w[KW / 4 + v] = val[v][i];
+                if constexpr (RW == 2) {
+                    reinterpret_cast<uint2 *>(s_stage)[pos] = make_uint2(w[0], w[1]);
+                } else if constexpr (RW == 4) {
+                    reinterpret_cast<uint4 *>(s_stage)[pos] = make_uint4(w[0], w[1], w[2], w[3]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < RW; q++) s_stage[pos * RW + q] = w[q];
+                }
+            }
+        }
+        // ---- the registers are free: request the next tile before this one leaves ----
+        const int cur_count = count;
+        if (tile + 1 < t1) {
+            count = (int)min((int64_t)TP_TILE, P.n - (tile + 1) * TP_TILE);
+            part_load_tile<KW, NV, TP_T>(L, (tile + 1) * TP_TILE, count, tid, key, val);
+        }
+        (void)cur_count;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy stores -> visible to the bulk copy
+        __syncthreads();
+        if (tid == 0) {
+            // the whole tile block is written (rows past a ragged last tile's count are never read: the directory
+            // bounds every run); 16 KB pieces
+            constexpr uint32_t BYTES = (uint32_t)TP_TILE * RW * 4;
+            unsigned char *g = reinterpret_cast<unsigned char *>(P.rows_out) + (size_t)tile * BYTES;
+            const unsigned char *sm = reinterpret_cast<const unsigned char *>(s_stage);
+#pragma unroll 1
+            for (uint32_t o = 0; o < BYTES; o += 16384u) tp_bulk_store(g + o, sm + o, min(16384u, BYTES - o));
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // shared memory must outlive the copy
+}
+
+template <int KW, int NV>
+int launch_tpart(hark_ctx *ctx, const TPartParams &P, unsigned grid) {
+    const size_t smem = (size_t)TP_TILE * (KW / 4 + NV) * 4;
+    auto kern = hk_tpart_kernel<KW, NV>;
+    HK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, TP_T, smem, ctx->stream>>>(P);
+    HK_CHECK_LAUNCH(ctx);
+    ctx->count_launch();
+    return HARK_OK;
+}
+
 #define HK_PART_DISPATCH_NV(fn, KWv, PTv, ...)                                                                  \
     (nv == 0 ? fn<KWv, 0, PTv>(__VA_ARGS__) : nv == 1 ? fn<KWv, 1, PTv>(__VA_ARGS__)                            \
                                             : nv == 2 ? fn<KWv, 2, PTv>(__VA_ARGS__) : fn<KWv, 3, PTv>(__VA_ARGS__))
@@ -391,5 +551,55 @@ int hk_partition_pass(hark_ctx *ctx, int64_t n, const void *key, int kw, const h
     for (int v = 0; v < nv; v++) vals_out[v] = P.val_out[v];
     *d_offsets = P.offsets;
     own.v.clear(); // ownership moves to the caller
+    return HARK_OK;
+}
+
+int hk_tile_partition(hark_ctx *ctx, int64_t n, const void *key, int kw, const hk_part_spec &spec, uint64_t hash_mask, int nv,
+                      const void *const *vals, hk_tpart *out) {
+    if (nv > PMAXV || nv < 0 || spec.nbins < 1 || spec.nbins > 256 || (kw != 4 && kw != 8) || n <= 0)
+        return ctx->fail(HARK_ERR_UNSUPPORTED, "tile_partition: unsupported shape");
+    if (!hk_dtype_int(spec.dtype)) return ctx->fail(HARK_ERR_UNSUPPORTED, "tile_partition: integer keys only");
+    *out = hk_tpart{};
+    TPartParams P;
+    memset(&P, 0, sizeof P);
+    P.f.xmask = spec.dtype == HARK_I32 ? 0x80000000ull : spec.dtype == HARK_I64 ? 0x8000000000000000ull : 0ull;
+    P.f.base = spec.base;
+    P.f.last = spec.span == 0 ? ~0ull : spec.span - 1;
+    if (kw == 4 && P.f.last > 0xffffffffull) P.f.last = 0xffffffffull;
+    P.f.shift = spec.shift;
+    P.hash = hash_mask != 0;
+    P.hmask = hash_mask;
+    P.key_in = key;
+    for (int v = 0; v < nv; v++) P.val_in[v] = (const uint32_t *)vals[v];
+    P.n = n;
+    P.nbins = spec.nbins;
+    P.num_tiles = (n + TP_TILE - 1) / TP_TILE;
+    const int64_t max_ctas = (int64_t)ctx->num_sms * 2;
+    P.tiles_per_cta = std::max<int64_t>(1, (P.num_tiles + max_ctas - 1) / max_ctas);
+    const unsigned grid = (unsigned)((P.num_tiles + P.tiles_per_cta - 1) / P.tiles_per_cta);
+    const int rw = kw / 4 + nv;
+    void *rows = nullptr, *dir = nullptr;
+    HK_TRY(ctx->dalloc(&rows, (size_t)P.num_tiles * TP_TILE * rw * 4));
+    int rc = ctx->dalloc(&dir, (size_t)P.num_tiles * spec.nbins * 4);
+    if (rc != HARK_OK) {
+        ctx->dfree(rows);
+        return rc;
+    }
+    P.rows_out = (uint32_t *)rows;
+    P.dir = (uint32_t *)dir;
+#define HK_TPART_NV(KWv) (nv == 0 ? launch_tpart<KWv, 0>(ctx, P, grid) : nv == 1 ? launch_tpart<KWv, 1>(ctx, P, grid) \
+                          : nv == 2 ? launch_tpart<KWv, 2>(ctx, P, grid) : launch_tpart<KWv, 3>(ctx, P, grid))
+    rc = kw == 4 ? HK_TPART_NV(4) : HK_TPART_NV(8);
+#undef HK_TPART_NV
+    if (rc != HARK_OK) {
+        ctx->dfree(rows);
+        ctx->dfree(dir);
+        return rc;
+    }
+    out->rows = (uint32_t *)rows;
+    out->dir = (uint32_t *)dir;
+    out->num_tiles = P.num_tiles;
+    out->nbins = spec.nbins;
+    out->rw = rw;
     return HARK_OK;
 }

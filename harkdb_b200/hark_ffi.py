@@ -83,6 +83,8 @@ SIGNATURES = {
     "hark_entry_query_groupby": (C.c_int, [_P, C.POINTER(_P), _P, C.c_int32, _I32P, _I32P, C.c_int64]),
     "hark_entry_join": (C.c_int, [_P, C.POINTER(_P), _P, _P, C.c_int32, C.c_int32, _I32P, C.c_int64, _I32P,
                                   C.c_int64]),
+    "hark_entry_join_ex": (C.c_int, [_P, C.POINTER(_P), _P, _P, C.c_int32, C.c_int32, _I32P, C.c_int64, _I32P,
+                                     C.c_int64, C.c_int32]),
     "hark_entry_query_filter": (C.c_int, [_P, C.POINTER(_P), _P, _I32P, C.c_int64, C.POINTER(HarkPred), C.c_int64]),
     "hark_entry_query_groupby_ex": (C.c_int, [_P, C.POINTER(_P), _P, C.c_int32, _I32P, _I32P, C.c_int64,
                                               C.POINTER(HarkPred), C.c_int64]),
@@ -415,6 +417,23 @@ class Futhark:
             h = C.c_void_p()
             self._check(self.lib.hark_entry_join(self.ctx, C.byref(h), t1.handle, t2.handle, int(col1), int(col2),
                                                  _i32p(c1), len(c1), _i32p(c2), len(c2)))
+            return DeviceTable(self, h.value)
+        finally:
+            if tmp1:
+                t1.free()
+            if tmp2:
+                t2.free()
+
+    def join_ex(self, db1: TableLike, db2: TableLike, col1, col2, cols1, cols2, order: int = 1) -> DeviceTable:
+        """Typed join: integer key columns of one dtype, projected columns keep their dtypes.  order=1: reference order
+        (key, r1, r2) by sort + merge; order=0: hash build on db2 + probe with db1 (multiset, grouped by db1 row)."""
+        t1, tmp1 = self._as_table(db1)
+        t2, tmp2 = self._as_table(db2)
+        try:
+            c1, c2 = _i32arr(cols1), _i32arr(cols2)
+            h = C.c_void_p()
+            self._check(self.lib.hark_entry_join_ex(self.ctx, C.byref(h), t1.handle, t2.handle, int(col1), int(col2),
+                                                    _i32p(c1), len(c1), _i32p(c2), len(c2), int(order)))
             return DeviceTable(self, h.value)
         finally:
             if tmp1:

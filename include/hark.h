@@ -190,6 +190,15 @@ int hark_entry_join_groupby(hark_ctx *ctx, hark_table **out, const hark_table *f
                             int32_t fk_col, int32_t pk_col, int32_t g_col, const int32_t *s_cols, const int32_t *ops,
                             int64_t c);
 
+/* Typed inner equi-join: the key columns are any integer dtype (the same on both sides, compared in that dtype's own
+ * order), the projected columns keep their dtypes.
+ *   order = 1: rows ordered as hark_entry_join does (join.fut:55-75: key ascending, then db1 row, then db2 row) — both
+ *              sides sorted (K3) and merged; db1 and db2 below 2^32-1 rows;
+ *   order = 0: hash build on db2 + probe with db1: rows grouped by db1 row, ascending, the matches of one db1 row in
+ *              unspecified order (a multiset result); db1 of any size, db2 below 2^32-1 rows.                        */
+int hark_entry_join_ex(hark_ctx *ctx, hark_table **out, const hark_table *db1, const hark_table *db2, int32_t col1,
+                       int32_t col2, const int32_t *cols1, int64_t l, const int32_t *cols2, int64_t k, int32_t order);
+
 /* ---- building blocks exported for the multi-GPU layer and for tests ---- */
 /* Stable LSD radix sort of whole rows by one column (ascending; signedness of the dtype).      */
 int hark_table_sort_by(hark_ctx *ctx, hark_table **out, const hark_table *db, int32_t key_col);

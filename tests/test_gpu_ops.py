@@ -449,6 +449,67 @@ def test_join_empty_and_errors():
         env.join(a, a, 0, 0, [9], [1])
 
 
+def _rows_sorted(cols):
+    """Rows of a column list in lexicographic order (for multiset comparison); floats by their bit patterns."""
+    if not cols or len(cols[0]) == 0:
+        return cols
+    keys = [c.view(np.uint32) if c.dtype == np.float32 else c.view(np.uint64) if c.dtype == np.float64 else c for c in cols]
+    o = np.lexsort(tuple(keys[::-1]))
+    return [c[o] for c in cols]
+
+
+@pytest.mark.parametrize("kdt", [NO.I32, NO.U32, NO.I64])
+@pytest.mark.parametrize("order", [1, 0])
+@pytest.mark.parametrize("n1,n2,krange", [(1, 1, 1), (300, 200, 7), (5000, 3000, 40), (100003, 50021, 10 ** 9),
+                                          (20000, 20000, 20000), (4097, 2049, 3), (70001, 9, 5)])
+def test_join_ex_typed(kdt, order, n1, n2, krange):
+    """hark_entry_join_ex: signed / unsigned / 64-bit keys (negative values, sparse ranges, duplicates on both sides, no
+    match at all), mixed-dtype projected columns; order=1 bit-exact row order, order=0 the same multiset grouped by r1."""
+    env = get_env()
+    rng = np.random.default_rng(n1 * 5 + n2 + kdt + order)
+    npdt = NO.NP_DTYPES[kdt]
+    lo = {NO.I32: -krange // 2, NO.U32: 2 ** 31 - krange // 2, NO.I64: -2 ** 40}[kdt]
+    step = 2 ** 30 if (kdt == NO.I64 and krange > 10 ** 6) else 1           # i64: span >= 1000 x rows
+    k1 = (lo + step * rng.integers(0, krange, n1)).astype(npdt)
+    k2 = (lo + step * rng.integers(0, krange, n2)).astype(npdt)
+    t1 = [rng.integers(-100, 100, n1).astype(np.int32), k1, rng.random(n1).astype(np.float64), np.arange(n1, dtype=np.int64)]
+    t2 = [k2, rng.random(n2).astype(np.float32), np.arange(n2, dtype=np.uint32)]
+    d1, d2 = env.from_columns(t1), env.from_columns(t2)
+    exp = NO.join_ex(t1, t2, 1, 0, [3, 1, 2, 0], [2, 1])
+    if len(exp[0]) > 30_000_000:
+        pytest.skip("too many pairs")
+    r = env.join_ex(d1, d2, 1, 0, [3, 1, 2, 0], [2, 1], order)
+    got = r.columns()
+    assert [g.dtype for g in got] == [e.dtype for e in exp] and r.shape[0] == len(exp[0])
+    if order == 1:
+        for g, e in zip(got, exp):
+            assert np.array_equal(g, e)
+    else:
+        assert np.all(np.diff(got[0]) >= 0)                                   # grouped by db1 row, ascending
+        for g, e in zip(_rows_sorted(got), _rows_sorted(exp)):
+            assert np.array_equal(g, e)
+    for x in (r, d1, d2):
+        x.free()
+
+
+def test_join_ex_no_overlap_empty_and_errors():
+    env = get_env()
+    from harkdb_b200.hark_ffi import HarkError
+    a = env.from_columns([np.arange(10, dtype=np.int64), np.arange(10, dtype=np.int32)])
+    b = env.from_columns([np.arange(100, 110, dtype=np.int64), np.ones(10, dtype=np.float32)])
+    e = env.from_columns([np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.float32)])
+    for order in (0, 1):
+        assert env.join_ex(a, b, 0, 0, [0, 1], [1], order).shape == (0, 3)
+        assert env.join_ex(a, e, 0, 0, [0], [1], order).shape == (0, 2)
+        assert env.join_ex(e, a, 0, 0, [1], [0, 1], order).dtypes == [NO.F32, NO.I64, NO.I32]
+        with pytest.raises(HarkError, match="same integer dtype"):
+            env.join_ex(a, b, 1, 0, [0], [1], order)                          # i32 key against i64 key
+        with pytest.raises(HarkError, match="out of bounds"):
+            env.join_ex(a, b, 0, 0, [5], [1], order)
+    for x in (a, b, e):
+        x.free()
+
+
 def test_join_groupby_config5_shape(gb_impl):
     """BASELINE config 5 at an oracle-checkable size: fact(fk,val) JOIN dim(pk unique,attr) GROUP BY attr."""
     env = get_env()
@@ -481,6 +542,181 @@ def test_join_groupby_duplicate_dim_key_and_misses(gb_impl):
     assert k.tolist() == [-2, 40] and s.tolist() == [2, 8] and c.tolist() == [1, 3]
     for x in (r, dim, dim2, fact):
         x.free()
+
+
+@pytest.fixture(params=["one_slice", "many_slices"])
+def slices(request):
+    """`many_slices`: 8 KB build-structure slices, so that small inputs run K8t (the tile-local partition by lookup /
+    hash-table slice) in front of the probe; `one_slice`: the whole structure is one slice (no partition)."""
+    env = get_env()
+    env.set_option("join.lut_slice_bytes", 8192 if request.param == "many_slices" else 16 << 20)
+    yield request.param
+    env.set_option("join.lut_slice_bytes", 16 << 20)
+
+
+def _sparse_keys(rng, nd, kdt):
+    """nd unique keys spread over (almost) the whole value range of the dtype: span >= 1000 x rows for i64."""
+    if kdt == NO.I64:
+        k = rng.integers(-2 ** 62, 2 ** 62, int(nd * 1.2)).astype(np.int64)
+    elif kdt == NO.U32:
+        k = rng.integers(0, 2 ** 32, int(nd * 1.2), dtype=np.uint64).astype(np.uint32)
+    else:
+        k = rng.integers(-2 ** 31, 2 ** 31, int(nd * 1.2)).astype(np.int32)
+    k = np.unique(k)
+    rng.shuffle(k)
+    assert len(k) >= nd
+    return np.ascontiguousarray(k[:nd])
+
+
+@pytest.mark.parametrize("kdt", [NO.I32, NO.U32, NO.I64])
+@pytest.mark.parametrize("match", [0.0, 0.5, 1.0])
+@pytest.mark.parametrize("nd,nf", [(1, 5), (1000, 20000), (50021, 300007)])
+def test_join_groupby_hash_build_sparse_keys(gb_impl, slices, kdt, match, nd, nf):
+    """Sparse build keys (negative, unsigned above 2^31, 64-bit): the open-addressing hash build + probe, fused into K2
+    when the group domain fits (auto / tiny_tables) and through probe -> filter -> GROUP BY otherwise (sort)."""
+    env = get_env()
+    rng = np.random.default_rng(nd * 3 + nf + int(match * 10) + kdt)
+    pk = _sparse_keys(rng, nd, kdt)
+    attr = rng.integers(-5, 40, nd).astype(np.int32)
+    hit = pk[rng.integers(0, nd, nf)]
+    miss = _sparse_keys(rng, nf, kdt)
+    miss = miss[~np.isin(miss, pk)]
+    miss = np.resize(miss, nf) if len(miss) else hit.copy()
+    fk = np.where(rng.random(nf) < match, hit, miss).astype(pk.dtype)
+    val = rng.integers(-1000, 1000, nf).astype(np.int32)
+    fval = rng.random(nf).astype(np.float32)
+    dim = env.from_columns([pk, attr])
+    fact = env.from_columns([fk, val, fval])
+    ops = [NO.AGG_SUM, NO.AGG_COUNT, NO.AGG_AVG, NO.AGG_MIN, NO.AGG_SUM]
+    sc = [1, 1, 1, 1, 2]
+    r = env.join_groupby(fact, dim, 0, 0, 1, sc, ops)
+    assert env.get_option("join.last_build") == (2 if nd > 1 else 1)     # span > 16 x rows: the hash build ran
+    _check_cols(r.columns(), NO.join_groupby([fk, val, fval], [pk, attr], 0, 0, 1, sc, ops))
+    for x in (r, dim, fact):
+        x.free()
+
+
+def test_join_groupby_hash_build_equals_lookup_build_and_rejects_duplicates(gb_impl, slices):
+    env = get_env()
+    from harkdb_b200.hark_ffi import HarkError
+    rng = np.random.default_rng(5)
+    nd, nf = 30011, 200003
+    pk = rng.permutation(nd).astype(np.int32) - 7000            # dense keys with negative values
+    attr = rng.integers(0, 300, nd).astype(np.int32)
+    fk = rng.integers(-9000, nd, nf).astype(np.int32)
+    val = rng.integers(0, 1000, nf).astype(np.int32)
+    dim, fact = env.from_columns([pk, attr]), env.from_columns([fk, val])
+    ops = [NO.AGG_SUM, NO.AGG_COUNT, NO.AGG_MAX]
+    exp = NO.join_groupby([fk, val], [pk, attr], 0, 0, 1, [1, 1, 1], ops)
+    try:
+        for build in (1, 2):
+            env.set_option("join.build", build)
+            r = env.join_groupby(fact, dim, 0, 0, 1, [1, 1, 1], ops)
+            assert env.get_option("join.last_build") == build
+            _check_cols(r.columns(), exp)
+            r.free()
+        env.set_option("join.build", 2)
+        for kdt in (np.int32, np.int64):
+            d2 = env.from_columns([np.array([5, 9, 5, 7], dtype=kdt), np.array([1, 2, 3, 4], dtype=np.int32)])
+            f2 = env.from_columns([np.array([5, 7, 9], dtype=kdt), np.array([1, 2, 3], dtype=np.int32)])
+            with pytest.raises(HarkError, match="not unique"):
+                env.join_groupby(f2, d2, 0, 0, 1, [1], [NO.AGG_SUM])
+            d2.free(); f2.free()
+    finally:
+        env.set_option("join.build", 0)
+    dim.free(); fact.free()
+
+
+def test_join_groupby_config5_shape_many_slices(gb_impl, slices):
+    """Config 5's shape with the lookup cut into many slices: K8t + the segment-walking aggregation (lookup mode)."""
+    env = get_env()
+    from oracle import c_oracle as CO
+    nd, nf = 100003, (1 << 19) + 77
+    dspec = [dict(kind=NO.GEN_AFFINE, a=48271, b=11, range=nd), dict(kind=NO.GEN_UNIFORM, lo=0, range=1024)]
+    fspec = [dict(kind=NO.GEN_UNIFORM, lo=-5, range=2 * nd), dict(kind=NO.GEN_UNIFORM, lo=-100, range=200)]
+    dim = env.synth(nd, [NO.I32, NO.I32], dspec, seed=7)
+    fact = env.synth(nf, [NO.I32, NO.I32], fspec, seed=8)
+    dcols = [CO.synth_column(NO.I32, dspec[c], 7, c, 0, nd) for c in range(2)]
+    fcols = [CO.synth_column(NO.I32, fspec[c], 8, c, 0, nf) for c in range(2)]
+    ops = [NO.AGG_SUM, NO.AGG_COUNT, NO.AGG_AVG, NO.AGG_MAX]
+    r = env.join_groupby(fact, dim, 0, 0, 1, [1, 1, 1, 1], ops)
+    _check_cols(r.columns(), NO.join_groupby(fcols, dcols, 0, 0, 1, [1, 1, 1, 1], ops))
+    r.free(); dim.free(); fact.free()
+
+
+@pytest.mark.parametrize("shape", ["u24", "signed_u24", "wide64", "too_wide", "nonfinite", "denormal", "zeros"])
+def test_groupby_f32_sum_exact_fixed_point_and_fallback(gb_impl, shape):
+    """f32 SUM / AVG in K2: exact fixed-point accumulation when the column's zone map proves it exact (32-bit addends
+    for values on a 2^-24 grid, 64-bit addends for wider mantissa spreads), the f64 compare-and-swap path otherwise
+    (dynamic range too wide, NaN / inf present).  All within the stated 1e-5 (f32 SUM) / 1e-12 (f64 AVG of exact sums
+    is looser: compared at 1e-5 like the oracle's f64 accumulation allows)."""
+    env = get_env()
+    rng = np.random.default_rng(len(shape))
+    n = 200003
+    key = rng.integers(-50, 450, n).astype(np.int32)
+    if shape == "u24":
+        val = (rng.integers(0, 2 ** 24, n).astype(np.float32) * np.float32(2.0 ** -24))
+    elif shape == "signed_u24":
+        val = ((rng.integers(0, 2 ** 24, n) - 2 ** 23).astype(np.float32) * np.float32(2.0 ** -20))
+    elif shape == "wide64":
+        val = (rng.random(n) * 10.0 ** rng.integers(-3, 4, n)).astype(np.float32)
+    elif shape == "too_wide":
+        val = (rng.random(n) * 10.0 ** rng.integers(-30, 30, n)).astype(np.float32)
+    elif shape == "nonfinite":
+        val = rng.random(n).astype(np.float32)
+        val[::1000] = np.inf
+        val[5::1000] = np.nan
+    elif shape == "denormal":
+        val = (rng.integers(1, 1000, n).astype(np.float32) * np.float32(1e-42))
+    else:
+        val = np.zeros(n, dtype=np.float32)
+    cols = [key, val]
+    t = env.from_columns(cols)
+    ops = [NO.AGG_SUM, NO.AGG_AVG, NO.AGG_COUNT, NO.AGG_MAX]
+    r = env.query_groupby_ex(t, 0, [1, 1, 1, 1], ops)
+    exp = NO.query_groupby_ex(cols, 0, [1, 1, 1, 1], ops)
+    got = r.columns()
+    assert np.array_equal(got[0], exp[0]) and np.array_equal(got[3], exp[3])
+    if shape == "nonfinite":
+        for g, e in zip(got[1:3], exp[1:3]):
+            assert np.array_equal(np.isnan(g), np.isnan(e)) and np.array_equal(np.isinf(g), np.isinf(e))
+            ok = np.isfinite(e)
+            assert np.allclose(g[ok], e[ok], rtol=1e-5, atol=0)
+    else:
+        assert np.allclose(got[1], exp[1], rtol=1e-5, atol=0) and np.allclose(got[2], exp[2], rtol=1e-5, atol=0)
+    if shape != "nonfinite":
+        assert np.array_equal(got[4], exp[4])
+    r.free(); t.free()
+
+
+@pytest.mark.parametrize("part_impl", [0, 1])
+@pytest.mark.parametrize("kdt,vdts", [(NO.I32, [NO.I32]), (NO.I64, [NO.I32, NO.F32]), (NO.U32, [NO.U32, NO.I32, NO.F32]), (NO.I32, [])])
+@pytest.mark.parametrize("n", [1, 4095, 4096, 4097, 8193, 300007])
+def test_groupby_tile_partition_vs_chunk_partition(part_impl, kdt, vdts, n):
+    """K8t (tile-local partition + directory, dense.part_impl=0) and K8a (chunked partition, =1) in front of K2, tiny
+    tables so that every size partitions: ragged last tiles, 4- and 8-byte keys, 0 to 3 carried value columns."""
+    env = get_env()
+    rng = np.random.default_rng(n + kdt + len(vdts))
+    key = (rng.integers(0, 5000, n) - 2000).astype(NO.NP_DTYPES[kdt]) if kdt != NO.U32 else \
+        (rng.integers(0, 5000, n) + 2 ** 31 - 2500).astype(np.uint32)
+    cols = [key]
+    for vd in vdts:
+        cols.append(rng.random(n).astype(np.float32) if vd == NO.F32 else rng.integers(0, 2 ** 31, n).astype(NO.NP_DTYPES[vd]))
+    sc, ops = [], []
+    for j, vd in enumerate(vdts):
+        sc += [j + 1, j + 1]
+        ops += [NO.AGG_SUM, NO.AGG_MAX if vd != NO.F32 else NO.AGG_AVG]
+    sc.append(0); ops.append(NO.AGG_COUNT)
+    t = env.from_columns(cols)
+    env.set_option("dense.log2_slots", 8)
+    env.set_option("dense.part_impl", part_impl)
+    try:
+        r = env.query_groupby_ex(t, 0, sc, ops)
+    finally:
+        env.set_option("dense.log2_slots", 0)
+        env.set_option("dense.part_impl", 0)
+    _check_cols(r.columns(), NO.query_groupby_ex(cols, 0, sc, ops))
+    r.free(); t.free()
 
 
 # ---------------------------------------------------------------- SQL through FutharkContext

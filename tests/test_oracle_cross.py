@@ -154,3 +154,13 @@ def test_groupby_ex_and_orderby_semantics():
     assert np.signbit(o[1][3]) and o[1][4] == 0.5          # -0.0 before 0.5
     d = NO.query_orderby([a, b], [0], [0], [1])
     assert d[0].tolist() == [2, 2, 1, 1, -5]
+
+
+def test_join_ex_restates_the_pinned_join_on_u32_data():
+    """np_oracle.join_ex (typed extension) == np_oracle.join (join.fut:52-75 restatement) == the SOAC simulation on u32."""
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 30, (200, 3)).astype(np.uint32)
+    b = rng.integers(0, 30, (150, 2)).astype(np.uint32)
+    ref = NO.join(a, b, 1, 0, [0, 2], [1])
+    got = NO.join_ex([a[:, c].copy() for c in range(3)], [b[:, c].copy() for c in range(2)], 1, 0, [0, 2], [1])
+    assert np.array_equal(np.stack(got, axis=1), ref)

@@ -366,6 +366,30 @@ class Suite:
         db2.free()
         return d
 
+    # ---- typed join through the hash build + probe (multiset result, hark_entry_join_ex order = 0) ----
+    def join_hash(self, n1=1 << 27, n2=1 << 24, i64=False):
+        torch, env = self.torch, self.env
+        n1, n2 = max(1024, int(n1 * self.scale)), max(256, int(n2 * self.scale))
+        kdt = I64 if i64 else I32
+        a = 2654435761 if not i64 else 0x9E3779B97F4A7C15       # odd: j -> a*j + b is injective mod 2^32 / 2^64 (sparse keys)
+        db2 = env.synth(n2, [kdt, I32], [dict(kind=GEN_AFFINE, a=a, b=7, range=0), dict(kind=0, lo=0, range=1024)], seed=7)
+        db1 = env.synth(n1, [kdt, I32], [dict(kind=GEN_AFFINE_UNIFORM, a=a, b=7, range=n2), dict(kind=0, lo=0, range=1000)], seed=42)
+        run = lambda: env.join_ex(db1, db2, 0, 0, [0, 1], [1], 0)
+        ms, ms_all, r, st = self.timed(run)
+        k, v = as_torch(r, 0), as_torch(r, 1)
+        env.sync()
+        k0, v0 = as_torch(db1, 0), as_torch(db1, 1)
+        ok = r.shape[0] == n1 and bool(torch.equal(k, k0)) and bool(torch.equal(v, v0))    # unique build keys: one match per row, row order kept
+        alg = (8 if i64 else 4) * (n1 + n2) + r.shape[0] * ((8 if i64 else 4) + 8) * 2
+        d = {"rows": n1 + n2, "rows_out": r.shape[0], "ms": ms, "ms_all": ms_all, "rows_per_s": (n1 + n2) / (ms * 1e-3),
+             "key_dtype": "i64" if i64 else "i32", "check_ok": bool(ok),
+             "roofline": self.roofline(alg, ms, st, "hk_hj_build_kernel + hk_hj_count_kernel + hk_hj_expand_kernel")}
+        del k, v, k0, v0
+        r.free()
+        db1.free()
+        db2.free()
+        return d
+
     # ---- N > 1: sharded result == single-GPU result on a reduced size, bit for bit ----
     def parity(self):
         """Every rank builds the FULL reduced-size tables too and runs the query on its one GPU; the sharded result is
