@@ -288,6 +288,8 @@ class ShardedEnv:
         # phase tracing (HARK_SHARD_TRACE=1): host wall time per phase with a device sync on both sides
         self.trace_on = bool(int(os.environ.get("HARK_SHARD_TRACE", "0"))) if trace is None else trace
         self.trace = {}
+        # partial groups of small dense key domains merge with an all-reduce (HARK_DENSE_MERGE=0: always repartition)
+        self.dense_merge = os.environ.get("HARK_DENSE_MERGE", "1") != "0"
         # K8c peer-memory exchange: on when the engine offers it and CUDA IPC works (HARK_PEER=0 forces NCCL;
         # HARK_PEER_ARENA_GB sizes the receive arena, default 24)
         self.peer = False
@@ -353,26 +355,53 @@ class ShardedEnv:
     def all_counts(self, n_local: int) -> List[int]:
         if self.world == 1:
             return [n_local]
-        out = [None] * self.world
-        self.dist.all_gather_object(out, int(n_local), group=self.group)
-        return [int(x) for x in out]
+        import torch
+        t = torch.tensor([int(n_local)], dtype=torch.int64, device=self.engine.device)
+        outs = [torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(outs, t, group=self.group)
+        return [int(x) for x in torch.cat(outs).cpu().tolist()]
+
+    PACK_LIMIT_BYTES = 32 << 20      # below this an exchange is latency-bound: all columns travel in ONE all-to-all
 
     def exchange(self, local, counts: Sequence[int]):
         """Rows of `local` are grouped by destination (counts[d] rows for rank d, in order).  Returns the engine
-        table made of what every rank sent here, in source-rank order."""
+        table made of what every rank sent here, in source-rank order.  Small tables (partial groups) are packed
+        row-major into one byte buffer so that the whole exchange is two collectives (counts + data); large ones
+        (ORDER BY shards) go column by column without a packing copy."""
         import torch
         eng, dist = self.engine, self.dist
         dts = local.dtypes
         cols = eng.columns_torch(local)
         dev = cols[0].device if cols else "cpu"
-        send = torch.tensor(list(counts), dtype=torch.int64, device=dev)
+        counts = [int(c) for c in counts]
+        send = torch.tensor(counts, dtype=torch.int64, device=dev)
         recv = torch.empty_like(send)
         dist.all_to_all_single(recv, send, group=self.group)
         recv_l = [int(x) for x in recv.cpu().tolist()]
+        n_out = sum(recv_l)
+        widths = [c.element_size() for c in cols]
+        rowb = sum(widths)
+        if len(cols) > 1 and rowb * max(sum(counts), n_out) <= self.PACK_LIMIT_BYTES:
+            n_in = sum(counts)
+            buf = torch.empty((n_in, rowb), dtype=torch.uint8, device=dev)
+            off = 0
+            for col, w in zip(cols, widths):
+                if n_in:
+                    buf[:, off:off + w] = col.reshape(-1).clone().view(torch.uint8).view(n_in, w)
+                off += w
+            got = torch.empty((n_out, rowb), dtype=torch.uint8, device=dev)
+            dist.all_to_all_single(got, buf, recv_l, counts, group=self.group)
+            outs, off = [], 0
+            for col, w in zip(cols, widths):
+                x = torch.empty(n_out * w, dtype=torch.uint8, device=dev)      # a fresh, aligned buffer per column
+                x.view(n_out, w).copy_(got[:, off:off + w])
+                outs.append(x.view(col.dtype))
+                off += w
+            return eng.from_torch(outs, dts)
         outs = []
-        for c, col in enumerate(cols):
-            out = torch.empty(sum(recv_l), dtype=col.dtype, device=dev)
-            dist.all_to_all_single(out, col.contiguous(), recv_l, list(counts), group=self.group)
+        for col in cols:
+            out = torch.empty(n_out, dtype=col.dtype, device=dev)
+            dist.all_to_all_single(out, col.contiguous(), recv_l, counts, group=self.group)
             outs.append(out)
         return eng.from_torch(outs, dts)
 
@@ -493,20 +522,103 @@ class ShardedEnv:
                 t.free()
 
     # ---- GROUP BY ----
+    DENSE_MERGE_SLOTS = 1 << 22      # key domains up to this many values merge with a reduce instead of an exchange
+
+    def _merge_dense(self, part, p_ops, pinned_u32):
+        """Partial groups of a small, dense key domain are merged with a REDUCE over NVLink instead of a repartition
+        (north_star: "partial aggregates merge with an NCCL reduce"): every rank scatters its partial columns into
+        dense per-slot arrays (slot = key - global min key), one all-reduce per reduction class (integer sums and
+        counts as int64 — a 32-bit SUM wraps exactly like the low word of the 64-bit one —, float sums as f64, integer
+        MIN / MAX as int64 with MAX negated), and rank r compacts the non-empty slots of the r-th slice of the domain:
+        concatenation in rank order is key order, as after a range repartition.  Returns None when the shape does not
+        fit (PROD, float MIN / MAX, a sparse or huge domain): the caller then repartitions."""
+        import torch
+        eng, dist = self.engine, self.dist
+        dts = part.dtypes
+        kdt = dts[0]
+        if kdt not in (I32, U32, I64):
+            return None
+        for op, dt in zip(p_ops, dts[1:]):
+            if op == AGG_PROD or (op in (AGG_MAX, AGG_MIN) and dt in (F32, F64)):
+                return None
+        cols = eng.columns_torch(part)
+        dev = cols[0].device
+        key = cols[0].to(torch.int64)
+        if kdt == U32:
+            key = key & 0xFFFFFFFF
+        big = torch.iinfo(torch.int64).max
+        mm = torch.stack([key.min() if key.numel() else torch.tensor(big, device=dev),
+                          -key.max() if key.numel() else torch.tensor(big, device=dev)])
+        dist.all_reduce(mm, op=dist.ReduceOp.MIN, group=self.group)
+        kmin, nkmax = (int(x) for x in mm.cpu().tolist())
+        if kmin == big:                     # no group anywhere
+            return eng.from_torch([c[:0] for c in cols], dts)
+        R = -nkmax - kmin + 1
+        if R > self.DENSE_MERGE_SLOTS:
+            return None
+        slot = key - kmin
+        isum, fsum, imin = [], [], []      # (partial column index, source tensor as the reduction dtype)
+        for j, (op, dt) in enumerate(zip(p_ops, dts[1:]), start=1):
+            c = cols[j]
+            if op in (AGG_MAX, AGG_MIN):
+                v = c.to(torch.int64)
+                if dt == U32:
+                    v = v & 0xFFFFFFFF
+                imin.append((j, -v if op == AGG_MAX else v))
+            elif dt in (F32, F64):
+                fsum.append((j, c.to(torch.float64)))
+            else:
+                isum.append((j, c.to(torch.int64)))
+        bi = torch.zeros((len(isum) + 1, R), dtype=torch.int64, device=dev)   # last row: presence
+        for r, (_, v) in enumerate(isum):
+            bi[r, slot] = v
+        bi[len(isum), slot] = 1
+        dist.all_reduce(bi, group=self.group)
+        bf = bm = None
+        if fsum:
+            bf = torch.zeros((len(fsum), R), dtype=torch.float64, device=dev)
+            for r, (_, v) in enumerate(fsum):
+                bf[r, slot] = v
+            dist.all_reduce(bf, group=self.group)
+        if imin:
+            bm = torch.full((len(imin), R), big, dtype=torch.int64, device=dev)
+            for r, (_, v) in enumerate(imin):
+                bm[r, slot] = v
+            dist.all_reduce(bm, op=dist.ReduceOp.MIN, group=self.group)
+        s0, s1 = R * self.rank // self.world, R * (self.rank + 1) // self.world
+        idx = torch.nonzero(bi[len(isum), s0:s1] > 0).reshape(-1) + s0
+        out = [None] * len(dts)
+        out[0] = (idx + kmin).to(cols[0].dtype)             # u32 keys above 2^31 wrap back into their i32 bit pattern
+        for r, (j, _) in enumerate(isum):
+            out[j] = bi[r, idx].to(cols[j].dtype)
+        for r, (j, _) in enumerate(fsum):
+            out[j] = bf[r, idx].to(cols[j].dtype)
+        for r, (j, _) in enumerate(imin):
+            v = bm[r, idx]
+            out[j] = (-v if p_ops[j - 1] == AGG_MAX else v).to(cols[j].dtype)
+        return eng.from_torch(out, dts)
+
     def _merge_groups(self, part, ops, pinned_u32, having=()):
         """part: shard-local partial groups [key, partials...] (consumed).  Returns this rank's final groups."""
         eng = self.engine
         p_ops = expand_partial_ops(list(range(len(ops))), ops, pinned_u32)[1]
         if self.world > 1:
-            recv = self.repartition(part, [0], [0], sorted_by_key=True)     # partial groups come out key-ordered
-            part.free()
-            m = recv.shape[1]
-            with self.phase("merge"):
-                if pinned_u32:
-                    merged = eng.query_groupby(recv, 0, list(range(1, m)), merge_ops_for(p_ops))
-                else:
-                    merged = eng.query_groupby_ex(recv, 0, list(range(1, m)), merge_ops_for(p_ops))
-            recv.free()
+            merged = None
+            if self.dense_merge:
+                with self.phase("merge_reduce"):
+                    merged = self._merge_dense(part, p_ops, pinned_u32)
+            if merged is not None:
+                part.free()
+            else:
+                recv = self.repartition(part, [0], [0], sorted_by_key=True)     # partial groups come out key-ordered
+                part.free()
+                m = recv.shape[1]
+                with self.phase("merge"):
+                    if pinned_u32:
+                        merged = eng.query_groupby(recv, 0, list(range(1, m)), merge_ops_for(p_ops))
+                    else:
+                        merged = eng.query_groupby_ex(recv, 0, list(range(1, m)), merge_ops_for(p_ops))
+                recv.free()
         else:
             merged = part
         if pinned_u32:
