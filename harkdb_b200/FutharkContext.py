@@ -13,7 +13,7 @@ Tables are uploaded once at ``create_table`` and stay resident in HBM as SoA col
 
 import numpy as np
 
-from .hark_ffi import DeviceTable, Futhark, I32, U32, I64
+from .hark_ffi import AGG_SUM, AGG_SUM64, DeviceTable, Futhark, I32, U32, I64
 from .parse import finalize_pred, sql_parse
 from .table import HostColumns, Table
 
@@ -52,12 +52,19 @@ class FutharkContext:
         return np.asarray(t).dtype.kind in "iub"
 
     def _is_u32_compatible(self, t):
+        """May this table take the reference-pinned u32 entries (main.fut:9, join.fut:52)?  They compare keys and
+        combine values as UNSIGNED 32-bit, so a column with a negative value would sort after every positive one and
+        come back as 4294967295-ish: only tables whose values all lie in [0, 2^32) qualify (Table.is_u32_exact, carried
+        on the handle); anything else takes the typed entries, with or without a WHERE clause."""
+        flag = getattr(t, "u32_exact", None)
         if self._is_table(t):
-            return all(d in (I32, U32) for d in t.dtypes)
+            if flag is not None:
+                return bool(flag) and all(d in (I32, U32) for d in t.dtypes)
+            return all(d == U32 for d in t.dtypes)          # unknown provenance: only u32 columns are safe
         if isinstance(t, HostColumns):
-            return all(c.dtype in (np.int32, np.uint32) for c in t)
+            return bool(flag) and all(c.dtype in (np.int32, np.uint32) for c in t)
         a = np.asarray(t)
-        return a.dtype.kind in "iub"
+        return a.dtype.kind in "iub" and (a.size == 0 or (int(a.min()) >= 0 and int(a.max()) < 2 ** 32))
 
     def _as_device(self, t):
         """(device table, temporary?)"""
@@ -144,13 +151,19 @@ class FutharkContext:
             if tmp:
                 t.free()
 
+    @staticmethod
+    def _exact_sums(ops):
+        """SQL's SUM does not wrap at the column width: on the extension routes code 2 (the reference's u32 `+`,
+        groupby.fut:37) becomes HARK_AGG_SUM64 — integer columns accumulate in 64 bits and come back as i64."""
+        return [AGG_SUM64 if int(op) == AGG_SUM else int(op) for op in ops]
+
     def _sql_groupby_ext(self, plan):
         env = self.FutEnv
         t, tmp = self._as_device(plan["table"])
         try:
             multi = "g_cols" in plan                      # GROUP BY a, b, ... (parse.py:64's TODO)
             g_cols = list(plan["g_cols"]) if multi else [plan["g_col"]]
-            s_cols, ops = list(plan["select"]), list(plan["groupbys"])
+            s_cols, ops = list(plan["select"]), self._exact_sums(plan["groupbys"])
             cur, cur_tmp = t, False
             if "where" in plan:
                 preds = [finalize_pred(p, self._is_int_col(t, p[0])) for p in plan["where"]]
@@ -181,7 +194,7 @@ class FutharkContext:
         t, tmp = self._as_device(plan["table"])
         cur, cur_tmp = t, False
         try:
-            s_cols, ops = list(plan["select"]), list(plan["groupbys"])
+            s_cols, ops = list(plan["select"]), self._exact_sums(plan["groupbys"])
             if "where" in plan:
                 preds = [finalize_pred(p, self._is_int_col(t, p[0])) for p in plan["where"]]
                 need = list(dict.fromkeys(s_cols))
@@ -242,10 +255,17 @@ class FutharkContext:
             try:
                 if grouped:
                     res = env.join_groupby(f1, f2, m1[col1], m2[col2], m2[plan["g_col"]], [m1[c] for c in plan["select"]],
-                                           plan["groupbys"])
-                else:
+                                           self._exact_sums(plan["groupbys"]))
+                elif (self._is_u32_compatible(t1) and self._is_u32_compatible(t2)) or not hasattr(env, "join_ex"):
                     res = env.join(f1, f2, m1[col1], m2[col2], [m1[c] for c in plan["select"]],
-                                   [m2[c] for c in plan["select2"]])
+                                   [m2[c] for c in plan["select2"]])         # join.fut:52, u32
+                else:
+                    # typed tables (negative values, 64-bit or float columns): same row order, columns keep their dtypes
+                    if f1.dtypes[m1[col1]] != f2.dtypes[m2[col2]]:
+                        raise Exception("JOIN: the key columns are stored with different dtypes "
+                                        f"({f1.dtypes[m1[col1]]} vs {f2.dtypes[m2[col2]]}); load both with one integer type")
+                    res = env.join_ex(f1, f2, m1[col1], m2[col2], [m1[c] for c in plan["select"]],
+                                      [m2[c] for c in plan["select2"]], 1)
             finally:
                 if ftmp1:
                     f1.free()

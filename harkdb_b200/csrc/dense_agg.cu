@@ -522,8 +522,7 @@ __global__ void __launch_bounds__(dagg_threads(NV), 1) hk_dagg_kernel(const __gr
 //                      probe the same slice of the lookup at the same time (the slice stays L2-resident);
 //   MODE 2 (hash)      slot + 1 = the entry of an open-addressing table keyed by hk_hash_key (join.cu), same dealing.
 // ------------------------------------------------------------------------------------------------
-constexpr int TG = 4;   // segments per warp and iteration
-constexpr int TU = 2;   // row loads per segment, lane and iteration
+constexpr int TG = 8;   // segments (tiles of one bin) per warp and iteration
 
 template <int KW>
 __device__ __forceinline__ uint32_t hash_probe(const void *htab, uint64_t hmask, typename KRaw<KW>::T key) {
@@ -586,86 +585,121 @@ __device__ __forceinline__ void acc_dispatch1(uint32_t *tab, uint32_t K, const u
     }
 }
 
-// TG segments of bin `b`, tiles t0 .. t0+TG-1 (those < t_end), by one warp
-template <int KW, int MODE, int NV>
+// SPEC: the accumulator programme, decided on the host so that the row loop carries no run-time switch for the
+// common shapes: 0 generic (any list of accumulators), 1 COUNT only, 2 COUNT + exact 64-bit sum of i32 values of value
+// column 0 (SUM + COUNT + AVG of one column: config 3), 3 COUNT + 32-bit wrap-around sum (config 5), 4 COUNT + exact
+// fixed-point sum of f32 values (config 3, f32 variant).  Specialised programmes keep their accumulator at table word 1.
+enum { SPEC_GENERIC = 0, SPEC_COUNT = 1, SPEC_SUM64S = 2, SPEC_SUM32 = 3, SPEC_FX32 = 4 };
+
+// TG segments of bin `b` (tiles t0 .. t0+TG-1, those < t_end) by one warp.  The segments differ in length by a few
+// rows, so the lanes walk them through a common WINDOW: virtual row v = g * W + off (W = longest of the TG runs, at
+// least 32) belongs to segment g, offset off; off >= length is a hole.  Lanes 0..TG-1 hold the directory words, a row
+// fetches its segment's (start, length) with one indexed shuffle.  Lane utilisation = mean / max run length (~85 % for
+// 64 bins) where a per-segment loop in steps of 32 rows reaches 41 % (ncu, round 2).
+template <int KW, int MODE, int NV, int SPEC>
 __device__ __forceinline__ void dagg_segments(const DAggParams &P, uint32_t *tab, int b, long long t0, long long t_end, int lane) {
     using KT = typename KRaw<KW>::T;
     constexpr int RW = KW / 4 + NV;
-    constexpr int N = TG * TU;
-    uint32_t s[TG], e[TG];
-    uint32_t maxlen = 0;
+    constexpr int U = RW <= 2 ? 8 : 4; // rows per lane in flight
+    uint32_t w = 0;
+    if (lane < TG && t0 + lane < t_end) w = __ldg(P.t_dir + (size_t)(t0 + lane) * P.nbins + b);
+    const uint32_t seg_s = w & 0xffffu, seg_len = (w >> 16) - seg_s;
+    const uint32_t packed = seg_s | (seg_len << 16);
+    uint32_t W = seg_len;
+    W = max(W, __shfl_xor_sync(HK_FULL_MASK, W, 1));
+    W = max(W, __shfl_xor_sync(HK_FULL_MASK, W, 2));
+    W = max(W, __shfl_xor_sync(HK_FULL_MASK, W, 4));
+    W = __shfl_sync(HK_FULL_MASK, W, 0);
+    if (W == 0) return;
+    W = max(W, 32u);
+    const uint32_t total = W * TG;
+    const uint32_t *base = P.t_rows + (size_t)t0 * HK_TPART_TILE * RW;
+    const uint32_t K = P.K;
+    const uint32_t slot0 = MODE == 0 ? (uint32_t)(P.g_lo + ((uint64_t)b << P.shift)) : 0u; // low word is enough: slots < K
+    const uint64_t slot0_64 = MODE == 0 ? (P.g_lo + ((uint64_t)b << P.shift)) : 0ull;
+    uint32_t g = 0, off = (uint32_t)lane; // lane's current virtual row (W >= 32 > lane)
+    for (uint32_t v0 = 0; v0 < total; v0 += 32 * U) {
+        KT k[U];
+        uint32_t x[NV > 0 ? NV : 1][U];
+        uint32_t okm = 0;
 #pragma unroll
-    for (int g = 0; g < TG; g++) {
-        s[g] = e[g] = 0;
-        if (t0 + g < t_end) {
-            const uint32_t w = __ldg(P.t_dir + (size_t)(t0 + g) * P.nbins + b);
-            s[g] = w & 0xffffu;
-            e[g] = w >> 16;
-        }
-        maxlen = max(maxlen, e[g] - s[g]);
-    }
-    const uint64_t slot0 = MODE == 0 ? ((uint64_t)b << P.shift) : 0ull;
-    for (uint32_t j = 0; j < maxlen; j += 32 * TU) {
-        KT k[N];
-        uint32_t x[NV > 0 ? NV : 1][N];
-        uint32_t okm = 0; // bit q: row q of this lane exists
+        for (int u = 0; u < U; u++) {
+            const uint32_t pk = __shfl_sync(HK_FULL_MASK, packed, (int)g); // lanes >= TG hold 0: past the last segment
+            k[u] = 0;
+            if (off < (pk >> 16)) {
+                okm |= 1u << u;
+                const uint32_t *row = base + (size_t)(g * HK_TPART_TILE + (pk & 0xffffu) + off) * RW;
+                if constexpr (RW == 1) {
+                    k[u] = __ldcs(row);
+                } else if constexpr (RW == 2) {
+                    const uint2 q = __ldcs(reinterpret_cast<const uint2 *>(row));
+                    if constexpr (KW == 4) { k[u] = q.x; x[0][u] = q.y; }
+                    else k[u] = (uint64_t)q.x | ((uint64_t)q.y << 32);
+                } else if constexpr (RW == 4) {
+                    const uint4 q = __ldcs(reinterpret_cast<const uint4 *>(row));
+                    if constexpr (KW == 4) { k[u] = q.x; x[0][u] = q.y; x[1][u] = q.z; x[2][u] = q.w; }
+                    else { k[u] = (uint64_t)q.x | ((uint64_t)q.y << 32); x[0][u] = q.z; x[1][u] = q.w; }
+                } else {
+                    uint32_t ww[RW];
 #pragma unroll
-        for (int g = 0; g < TG; g++)
+                    for (int i = 0; i < RW; i++) ww[i] = __ldcs(row + i);
+                    if constexpr (KW == 4) k[u] = ww[0];
+                    else k[u] = (uint64_t)ww[0] | ((uint64_t)ww[1] << 32);
 #pragma unroll
-            for (int u = 0; u < TU; u++) {
-                const int q = g * TU + u;
-                const uint32_t r = s[g] + j + u * 32 + lane;
-                k[q] = 0;
-                if (r < e[g]) {
-                    okm |= 1u << q;
-                    const uint32_t *row = P.t_rows + ((size_t)(t0 + g) * HK_TPART_TILE + r) * RW;
-                    if constexpr (RW == 1) {
-                        k[q] = __ldcs(row);
-                    } else if constexpr (RW == 2) {
-                        const uint2 v = __ldcs(reinterpret_cast<const uint2 *>(row));
-                        if constexpr (KW == 4) { k[q] = v.x; x[0][q] = v.y; }
-                        else k[q] = (uint64_t)v.x | ((uint64_t)v.y << 32);
-                    } else if constexpr (RW == 4) {
-                        const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(row));
-                        if constexpr (KW == 4) { k[q] = v.x; x[0][q] = v.y; x[1][q] = v.z; x[2][q] = v.w; }
-                        else { k[q] = (uint64_t)v.x | ((uint64_t)v.y << 32); x[0][q] = v.z; x[1][q] = v.w; }
-                    } else {
-                        uint32_t w[RW];
-#pragma unroll
-                        for (int i = 0; i < RW; i++) w[i] = __ldcs(row + i);
-                        if constexpr (KW == 4) k[q] = w[0];
-                        else k[q] = (uint64_t)w[0] | ((uint64_t)w[1] << 32);
-#pragma unroll
-                        for (int v = 0; v < NV; v++) x[v][q] = w[KW / 4 + v];
-                    }
+                    for (int v = 0; v < NV; v++) x[v][u] = ww[KW / 4 + v];
                 }
             }
-        uint32_t idx[N];
+            off += 32;
+            if (off >= W) {
+                off -= W;
+                g++;
+            }
+        }
+        uint32_t idx[U];
 #pragma unroll
-        for (int q = 0; q < N; q++) {
-            idx[q] = 0xffffffffu;
-            if ((okm >> q) & 1u) {
+        for (int u = 0; u < U; u++) {
+            idx[u] = 0xffffffffu;
+            if ((okm >> u) & 1u) {
                 if constexpr (MODE == 1) {
                     long long v;
-                    if constexpr (KW == 4) v = (P.key_dtype == HARK_U32 ? (long long)(uint32_t)k[q] : (long long)(int32_t)k[q]) - P.pk_min;
-                    else v = (long long)k[q] - P.pk_min;
-                    if (v >= 0 && v < P.pk_span) idx[q] = __ldg(P.lut + v) - 1u;
+                    if constexpr (KW == 4) v = (P.key_dtype == HARK_U32 ? (long long)(uint32_t)k[u] : (long long)(int32_t)k[u]) - P.pk_min;
+                    else v = (long long)k[u] - P.pk_min;
+                    if (v >= 0 && v < P.pk_span) idx[u] = __ldg(P.lut + v) - 1u;
                 } else if constexpr (MODE == 2) {
-                    idx[q] = hash_probe<KW>(P.htab, P.hmask, k[q]);
+                    idx[u] = hash_probe<KW>(P.htab, P.hmask, k[u]);
+                } else if constexpr (KW == 4) {
+                    idx[u] = hk_ordkey32(k[u], P.key_dtype) - slot0;
                 } else {
-                    idx[q] = (uint32_t)(ordkey_of<KW>(k[q], P.key_dtype) - P.g_lo - slot0);
+                    idx[u] = (uint32_t)(hk_ordkey64(k[u], P.key_dtype) - slot0_64);
                 }
             }
         }
+        if constexpr (SPEC == SPEC_GENERIC) {
 #pragma unroll
-        for (int q = 0; q < N; q++)
-            if (idx[q] != 0xffffffffu) atomicAdd(&tab[idx[q]], 1u);
+            for (int u = 0; u < U; u++)
+                if (idx[u] != 0xffffffffu) atomicAdd(&tab[idx[u]], 1u);
 #pragma unroll 1
-        for (int ai = 0; ai < P.nacc; ai++) {
-            const int kind = P.acc[ai].kind, word = P.acc[ai].word, vcol = P.acc[ai].vcol;
+            for (int ai = 0; ai < P.nacc; ai++) {
+                const int kind = P.acc[ai].kind, word = P.acc[ai].word, vcol = P.acc[ai].vcol;
 #pragma unroll
-            for (int v = 0; v < NV; v++)
-                if (v == vcol) acc_dispatch1<N>(tab, P.K, idx, kind, word, x[v], P.acc[ai].fscale);
+                for (int v = 0; v < NV; v++)
+                    if (v == vcol) acc_dispatch1<U>(tab, K, idx, kind, word, x[v], P.acc[ai].fscale);
+            }
+        } else {
+            [[maybe_unused]] const float fscale = P.acc[0].fscale;
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (idx[u] == 0xffffffffu) continue;
+                atomicAdd(&tab[idx[u]], 1u);
+                if constexpr (SPEC == SPEC_SUM32) {
+                    atomicAdd(&tab[K + idx[u]], x[0][u]);
+                } else if constexpr (SPEC == SPEC_SUM64S || SPEC == SPEC_FX32) {
+                    const uint32_t xv = SPEC == SPEC_FX32 ? (uint32_t)(int32_t)fx_of(x[0][u], fscale) : x[0][u];
+                    const uint32_t old = atomicAdd(&tab[K + idx[u]], xv);
+                    const int delta = (int)((uint32_t)(old + xv) < old) - (int)((int32_t)xv < 0);
+                    if (delta != 0) atomicAdd(reinterpret_cast<int *>(&tab[2 * K + idx[u]]), delta);
+                }
+            }
         }
     }
 }
@@ -692,7 +726,7 @@ __global__ void __launch_bounds__(256) hk_tile_block_rows_kernel(const uint32_t 
     }
 }
 
-template <int KW, int MODE, int NV>
+template <int KW, int MODE, int NV, int SPEC>
 __global__ void __launch_bounds__(dagg_threads(NV), 1) hk_dagg_tiles_kernel(const __grid_constant__ DAggParams P) {
     constexpr int AT = dagg_threads(NV);
     constexpr int NW = AT / 32;
@@ -738,7 +772,7 @@ __global__ void __launch_bounds__(dagg_threads(NV), 1) hk_dagg_tiles_kernel(cons
             const long long ba = max(e0, b * NB) - b * NB, bb = min(e1, (b + 1) * NB) - b * NB;
             const long long t_lo = ba * TBLK, t_hi = min(NT, bb * TBLK);
             for (long long t = t_lo + (long long)warp * TG; t < t_hi; t += (long long)NW * TG)
-                dagg_segments<KW, MODE, NV>(P, tab, (int)b, t, t_hi, lane);
+                dagg_segments<KW, MODE, NV, SPEC>(P, tab, (int)b, t, t_hi, lane);
             __syncthreads();
             if (t_lo < t_hi)
                 for (uint32_t i = tid; i < K; i += AT) flush_slot(tab, K, i, ((uint64_t)b << P.shift) + i, P);
@@ -747,7 +781,7 @@ __global__ void __launch_bounds__(dagg_threads(NV), 1) hk_dagg_tiles_kernel(cons
     } else {
         for (long long u = (long long)blockIdx.x * NW + warp; u < total; u += (long long)gridDim.x * NW) {
             const long long b = u / groups_per_bin;
-            dagg_segments<KW, MODE, NV>(P, tab, (int)b, (u - b * groups_per_bin) * TG, NT, lane);
+            dagg_segments<KW, MODE, NV, SPEC>(P, tab, (int)b, (u - b * groups_per_bin) * TG, NT, lane);
         }
         __syncthreads();
         for (uint32_t i = tid; i < K; i += AT) flush_slot(tab, K, i, (uint64_t)i, P);
@@ -807,7 +841,7 @@ __global__ void __launch_bounds__(1024) hk_dense_scan_kernel(const uint32_t *cou
 }
 
 enum OutKind { O_COUNT = 0, O_COPY32, O_LOW32_OF_U64, O_AVG_S64, O_AVG_U64, O_AVG_F64, O_F32_OF_F64, O_F64, O_F64_OF_S64, O_F64_OF_U64,
-               O_F32_OF_FX, O_AVG_FX, O_F64_OF_FX };
+               O_F32_OF_FX, O_AVG_FX, O_F64_OF_FX, O_COPY64 };
 struct OutSpec {
     int kind;
     const void *src; // dense accumulator
@@ -864,6 +898,7 @@ __global__ void __launch_bounds__(CT) hk_dense_compact_kernel(const __grid_const
             case O_F32_OF_F64: reinterpret_cast<float *>(o.dst)[g] = (float)reinterpret_cast<const double *>(o.src)[r]; break;
             case O_F64_OF_S64: reinterpret_cast<double *>(o.dst)[g] = (double)reinterpret_cast<const long long *>(o.src)[r]; break;
             case O_F64_OF_U64: reinterpret_cast<double *>(o.dst)[g] = (double)reinterpret_cast<const unsigned long long *>(o.src)[r]; break;
+            case O_COPY64: reinterpret_cast<unsigned long long *>(o.dst)[g] = reinterpret_cast<const unsigned long long *>(o.src)[r]; break;
             case O_F32_OF_FX: reinterpret_cast<float *>(o.dst)[g] = (float)((double)reinterpret_cast<const long long *>(o.src)[r] * o.oscale); break;
             case O_AVG_FX: reinterpret_cast<double *>(o.dst)[g] = (double)reinterpret_cast<const long long *>(o.src)[r] * o.oscale / (double)cnt[e]; break;
             case O_F64_OF_FX: reinterpret_cast<double *>(o.dst)[g] = (double)reinterpret_cast<const long long *>(o.src)[r] * o.oscale; break;
@@ -1029,7 +1064,8 @@ int hk_dense_groupby(hark_ctx *ctx, hark_table **out, const hk_dense_req &rq, bo
     // exact 64-bit sums serve both SUM (low word) and AVG; if a column only needs SUM, a 32-bit sum is enough
     std::vector<bool> col_needs_avg((size_t)std::max(rq.nvals, 1), false);
     for (int j = 0; j < rq.c; j++)
-        if ((rq.agg_code[j] == HARK_AGG_AVG || rq.agg_code[j] == HARK_AGG_SUMF64) && rq.agg_val[j] >= 0) col_needs_avg[rq.agg_val[j]] = true;
+        if ((rq.agg_code[j] == HARK_AGG_AVG || rq.agg_code[j] == HARK_AGG_SUMF64 || rq.agg_code[j] == HARK_AGG_SUM64) && rq.agg_val[j] >= 0)
+            col_needs_avg[rq.agg_val[j]] = true; // these need the exact 64-bit sum
     // f32 SUM / AVG: exact fixed point when the column's zone map allows it (every value a multiple of 2^lo, below
     // 2^(hi+1)): v / 2^lo is an integer of B = hi + 1 - lo bits.  B <= 31 -> one 32-bit addend per row (the integer
     // path's cost); B + log2(n) <= 62 -> 64-bit addends; else (or non-finite values) the f64 compare-and-swap path.
@@ -1045,7 +1081,7 @@ int hk_dense_groupby(hark_ctx *ctx, hark_table **out, const hk_dense_req &rq, bo
             bool wanted = false;
             for (int j = 0; j < rq.c; j++)
                 wanted = wanted || (rq.agg_val[j] == v && (rq.agg_code[j] == HARK_AGG_SUM || rq.agg_code[j] == HARK_AGG_AVG ||
-                                                           rq.agg_code[j] == HARK_AGG_SUMF64));
+                                                           rq.agg_code[j] == HARK_AGG_SUMF64 || rq.agg_code[j] == HARK_AGG_SUM64));
             if (!wanted) continue;
             FxStats st;
             HK_TRY(hk_f32_fxstats(ctx, rq.vals[v], rq.val_cols[v], n, &st));
@@ -1088,6 +1124,12 @@ int hk_dense_groupby(hark_ctx *ctx, hark_table **out, const hk_dense_req &rq, bo
             else if (is_f) outs.push_back({O_AVG_F64, acc_index(vi, A_FSUM, 2), HARK_F64});
             else outs.push_back({is_s ? O_AVG_S64 : O_AVG_U64, acc_index(vi, is_s ? A_SUM64S : A_SUM64U, 2), HARK_F64});
             break;
+        case HARK_AGG_SUM64:
+            if (!is_f) {
+                outs.push_back({O_COPY64, acc_index(vi, is_s ? A_SUM64S : A_SUM64U, 2), HARK_I64});
+                break;
+            }
+            // float columns: SUM64 = SUMF64
         case HARK_AGG_SUMF64:
             if (is_f && fxp[vi].kind >= 0) outs.push_back({O_F64_OF_FX, acc_index(vi, fxp[vi].kind, 2), HARK_F64});
             else if (is_f) outs.push_back({O_F64, acc_index(vi, A_FSUM, 2), HARK_F64});
@@ -1291,12 +1333,24 @@ int hk_dense_groupby(hark_ctx *ctx, hark_table **out, const hk_dense_req &rq, bo
     {
         cudaError_t e;
         void (*kern)(const DAggParams) = nullptr;
+        // accumulator programme of the tile kernel (see SPEC_*): specialised when there is at most one accumulator, on
+        // value column 0, sitting at table word 1
+        int spec = SPEC_GENERIC;
+        if (accs.empty()) spec = SPEC_COUNT;
+        else if (accs.size() == 1 && accs[0].vcol == 0 && word_of[0] == 1 && rq.nvals == 1 && ctx->opt("dense.spec", 1) != 0)
+            spec = accs[0].kind == A_SUM64S ? SPEC_SUM64S : accs[0].kind == A_SUM32 ? SPEC_SUM32 : accs[0].kind == A_FXSUM32 ? SPEC_FX32 : SPEC_GENERIC;
+#define HK_DAGG_TILES1(KWv, MODEv)                                                                      \
+    (spec == SPEC_SUM64S ? hk_dagg_tiles_kernel<KWv, MODEv, 1, SPEC_SUM64S>                            \
+     : spec == SPEC_SUM32 ? hk_dagg_tiles_kernel<KWv, MODEv, 1, SPEC_SUM32>                            \
+     : spec == SPEC_FX32 ? hk_dagg_tiles_kernel<KWv, MODEv, 1, SPEC_FX32> : hk_dagg_tiles_kernel<KWv, MODEv, 1, SPEC_GENERIC>)
 #define HK_DAGG_PICK(KWv, MODEv)                                                                       \
     switch (rq.nvals) {                                                                                \
-    case 0: kern = use_tiles ? hk_dagg_tiles_kernel<KWv, MODEv, 0> : hk_dagg_kernel<KWv, MODEv, 0>; break; \
-    case 1: kern = use_tiles ? hk_dagg_tiles_kernel<KWv, MODEv, 1> : hk_dagg_kernel<KWv, MODEv, 1>; break; \
-    case 2: kern = use_tiles ? hk_dagg_tiles_kernel<KWv, MODEv, 2> : hk_dagg_kernel<KWv, MODEv, 2>; break; \
-    case 3: kern = use_tiles ? hk_dagg_tiles_kernel<KWv, MODEv, 3> : hk_dagg_kernel<KWv, MODEv, 3>; break; \
+    case 0: kern = use_tiles ? (spec == SPEC_COUNT ? hk_dagg_tiles_kernel<KWv, MODEv, 0, SPEC_COUNT>   \
+                                                   : hk_dagg_tiles_kernel<KWv, MODEv, 0, SPEC_GENERIC>) \
+                             : hk_dagg_kernel<KWv, MODEv, 0>; break;                                   \
+    case 1: kern = use_tiles ? HK_DAGG_TILES1(KWv, MODEv) : hk_dagg_kernel<KWv, MODEv, 1>; break;      \
+    case 2: kern = use_tiles ? hk_dagg_tiles_kernel<KWv, MODEv, 2, SPEC_GENERIC> : hk_dagg_kernel<KWv, MODEv, 2>; break; \
+    case 3: kern = use_tiles ? hk_dagg_tiles_kernel<KWv, MODEv, 3, SPEC_GENERIC> : hk_dagg_kernel<KWv, MODEv, 3>; break; \
     default: kern = hk_dagg_kernel<KWv, MODEv, 4>; break;                                              \
     }
         if (hash_mode) {
@@ -1307,6 +1361,7 @@ int hk_dense_groupby(hark_ctx *ctx, hark_table **out, const hk_dense_req &rq, bo
             if (kw == 4) { HK_DAGG_PICK(4, 0) } else { HK_DAGG_PICK(8, 0) }
         }
 #undef HK_DAGG_PICK
+#undef HK_DAGG_TILES1
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) kern<<<grid, dagg_threads(rq.nvals), smem, ctx->stream>>>(P);
         if (e == cudaSuccess) e = cudaGetLastError();

@@ -204,12 +204,20 @@ __device__ __forceinline__ void load_vals(const void *in, int in_dtype, int64_t 
 #pragma unroll
         for (int e = 0; e < 4; e++)
             if (r + e < n) x[e] = __uint_as_float(v[e]);
-    } else if constexpr (std::is_same<A, uint64_t>::value) { // CLS_U64
-        uint64_t v[4];
-        load4<uint64_t>(reinterpret_cast<const uint64_t *>(in), r, v);
+    } else if constexpr (std::is_same<A, uint64_t>::value) { // CLS_U64 (4-byte inputs are widened: SUM64)
+        if (in_dtype == HARK_I32 || in_dtype == HARK_U32) {
+            uint32_t v[4];
+            load4<uint32_t>(reinterpret_cast<const uint32_t *>(in), r, v);
 #pragma unroll
-        for (int e = 0; e < 4; e++)
-            if (r + e < n) x[e] = v[e];
+            for (int e = 0; e < 4; e++)
+                if (r + e < n) x[e] = in_dtype == HARK_I32 ? (uint64_t)(int64_t)(int32_t)v[e] : (uint64_t)v[e];
+        } else {
+            uint64_t v[4];
+            load4<uint64_t>(reinterpret_cast<const uint64_t *>(in), r, v);
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+                if (r + e < n) x[e] = v[e];
+        }
     } else { // double: CLS_F64ACC (any input dtype) and CLS_F64MM (f64 input)
         if (in_dtype == HARK_F64 || in_dtype == HARK_I64) {
             uint64_t v[4];
@@ -455,6 +463,7 @@ int hk_segmented_aggregate(hark_ctx *ctx, hark_table **out, int64_t n, const voi
         const int32_t vdt = aggs[j].first >= 0 ? val_dtypes[aggs[j].first] : HARK_I64;
         if (code == HARK_AGG_COUNT) odt[1 + j] = HARK_I64;
         else if (code == HARK_AGG_AVG || code == HARK_AGG_SUMF64) odt[1 + j] = HARK_F64;
+        else if (code == HARK_AGG_SUM64 && !pinned_u32) odt[1 + j] = hk_dtype_int(vdt) ? HARK_I64 : HARK_F64;
         else odt[1 + j] = pinned_u32 ? HARK_U32 : vdt;
     }
     if (n == 0) return hk_table_alloc(ctx, out, 0, 0, odt.data(), 1 + c);
@@ -509,7 +518,7 @@ int hk_segmented_aggregate(hark_ctx *ctx, hark_table **out, int64_t n, const voi
             F.dst[j] = t->cols[1 + j].ptr;
             continue;
         }
-        if (code < HARK_AGG_PROD || code > HARK_AGG_SUMF64) code = HARK_AGG_MIN; // groupby.fut:41
+        if (code < HARK_AGG_PROD || code > HARK_AGG_SUM64 || (pinned_u32 && code > HARK_AGG_MIN)) code = HARK_AGG_MIN; // groupby.fut:41
         const int vi = aggs[j].first;
         const int32_t vdt = pinned_u32 ? HARK_U32 : val_dtypes[vi];
         AggSpec &ag = P.agg[nagg++];
@@ -518,6 +527,14 @@ int hk_segmented_aggregate(hark_ctx *ctx, hark_table **out, int64_t n, const voi
         const bool is_f = (vdt == HARK_F32 || vdt == HARK_F64);
         const bool is_signed = (vdt == HARK_I32 || vdt == HARK_I64);
         const int w = hk_dtype_size(vdt);
+        if (code == HARK_AGG_SUM64 && !is_f) { // exact integer sum: 64-bit accumulator over sign- / zero-extended inputs
+            ag.cls = CLS_U64;
+            ag.op = OP_SUM;
+            ag.acc = t->cols[1 + j].ptr;
+            HK_TRY(fill<uint64_t>(ctx, ag.acc, 0ull, G));
+            continue;
+        }
+        if (code == HARK_AGG_SUM64) code = HARK_AGG_SUMF64;
         if (code == HARK_AGG_AVG || code == HARK_AGG_SUMF64 || (is_f && (code == HARK_AGG_SUM || code == HARK_AGG_PROD))) {
             ag.cls = CLS_F64ACC;
             ag.op = code == HARK_AGG_PROD ? OP_PROD : OP_SUM;
@@ -612,7 +629,7 @@ int hk_groupby(hark_ctx *ctx, hark_table **out, const hark_table *db, int32_t g_
         for (int64_t j = 0; j < c && eligible; j++) {
             int code = ops[j];
             if (pinned_u32 && (code < HARK_AGG_PROD || code > HARK_AGG_MIN)) code = HARK_AGG_MIN; // groupby.fut:41
-            if (!pinned_u32 && (code < HARK_AGG_PROD || code > HARK_AGG_SUMF64)) code = HARK_AGG_MIN;
+            if (!pinned_u32 && (code < HARK_AGG_PROD || code > HARK_AGG_SUM64)) code = HARK_AGG_MIN;
             rq.agg_code[j] = code;
             if (code == HARK_AGG_COUNT) {
                 rq.agg_val[j] = -1;

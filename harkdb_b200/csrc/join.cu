@@ -874,7 +874,7 @@ int hk_join_groupby(hark_ctx *ctx, hark_table **out, const hark_table *fact, con
         std::vector<int> val_of_col((size_t)mf, -1);
         for (int64_t j = 0; j < c && eligible; j++) {
             int code = ops[j];
-            if (code < HARK_AGG_PROD || code > HARK_AGG_SUMF64) code = HARK_AGG_MIN;
+            if (code < HARK_AGG_PROD || code > HARK_AGG_SUM64) code = HARK_AGG_MIN;
             rq.agg_code[j] = code;
             if (code == HARK_AGG_COUNT) {
                 rq.agg_val[j] = -1;

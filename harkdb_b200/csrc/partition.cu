@@ -360,30 +360,118 @@ __device__ __forceinline__ void tp_bulk_store(void *gdst, const void *ssrc, uint
                  : "memory");
 }
 
-template <int KW>
-__device__ __forceinline__ uint32_t tpart_digit(typename KRaw<KW>::T raw, const TPartParams &P) {
-    if (P.hash) return (uint32_t)((hk_hash_key<KW>(raw) & P.hmask) >> P.f.shift);
-    return part_digit<KW>(raw, P.f);
+// bin of a row with the partition constants in registers (HASH: slices of a hash table, else key ranges)
+template <int KW, bool HASH>
+__device__ __forceinline__ uint32_t tpart_digit(typename KRaw<KW>::T raw, typename KRaw<KW>::T xmask, typename KRaw<KW>::T base,
+                                                typename KRaw<KW>::T last, int shift, uint64_t hmask) {
+    if constexpr (HASH) {
+        return (uint32_t)((hk_hash_key<KW>(raw) & hmask) >> shift);
+    } else {
+        const typename KRaw<KW>::T u = (raw ^ xmask) - base;
+        return u <= last ? (uint32_t)(u >> shift) : 0u;
+    }
 }
 
-template <int KW, int NV>
+// One tile: rank (one shared-memory atomic per row, all of a thread's atomics issued back to back), scan, scatter of the
+// packed rows into the stage, request of the next tile, bulk copy out.  FULL = the tile has all TP_TILE rows (no bounds
+// checks anywhere).
+template <int KW, int NV, bool HASH, bool FULL>
+__device__ __forceinline__ void tpart_tile(const TPartParams &P, const PartParams &L, uint32_t *s_stage, uint32_t *s_hist,
+                                           uint32_t *s_binstart, uint32_t *s_wtot, int64_t tile, int count, int next_count,
+                                           typename KRaw<KW>::T (&key)[PI], uint32_t (&val)[NV > 0 ? NV : 1][PI],
+                                           typename KRaw<KW>::T xmask, typename KRaw<KW>::T base, typename KRaw<KW>::T last, int shift) {
+    using KT = typename KRaw<KW>::T;
+    constexpr int RW = KW / 4 + NV;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t d[PI], rk[PI];
+#pragma unroll
+    for (int i = 0; i < PI; i++) d[i] = tpart_digit<KW, HASH>(key[i], xmask, base, last, shift, P.hmask);
+#pragma unroll
+    for (int i = 0; i < PI; i++) {
+        const int idx = ((i >> 2) * TP_T + tid) * 4 + (i & 3);
+        if (FULL || idx < count) rk[i] = atomicAdd(&s_hist[d[i]], 1u);
+    }
+    // the bulk copy of the previous tile must have finished READING the stage before anyone overwrites it
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncthreads();
+    // ---- thread b owns bin b: start of the bin's run inside the tile, directory word ----
+    {
+        const uint32_t sum = tid < 256 ? s_hist[tid] : 0u;
+        if (tid < 256) s_hist[tid] = 0;
+        const uint32_t inc = hk_warp_incl_scan_u32(sum);
+        if (lane == 31 && warp < 8) s_wtot[warp] = inc;
+        __syncthreads();
+        if (tid < 256) {
+            uint32_t woff = 0;
+            for (int w = 0; w < warp; w++) woff += s_wtot[w];
+            const uint32_t binstart = woff + inc - sum;
+            s_binstart[tid] = binstart;
+            if (tid < P.nbins) P.dir[(size_t)tile * P.nbins + tid] = binstart | ((binstart + sum) << 16);
+        }
+    }
+    __syncthreads();
+    // ---- the packed rows go to their slot of the stage ----
+#pragma unroll
+    for (int i = 0; i < PI; i++) {
+        const int idx = ((i >> 2) * TP_T + tid) * 4 + (i & 3);
+        if (FULL || idx < count) {
+            const uint32_t pos = s_binstart[d[i]] + rk[i];
+            uint32_t w[RW];
+            if constexpr (KW == 4) {
+                w[0] = key[i];
+            } else {
+                w[0] = (uint32_t)key[i];
+                w[1] = (uint32_t)(key[i] >> 32);
+            }
+#pragma unroll
+            for (int v = 0; v < NV; v++) w[KW / 4 + v] = val[v][i];
+            if constexpr (RW == 2) {
+                reinterpret_cast<uint2 *>(s_stage)[pos] = make_uint2(w[0], w[1]);
+            } else if constexpr (RW == 4) {
+                reinterpret_cast<uint4 *>(s_stage)[pos] = make_uint4(w[0], w[1], w[2], w[3]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < RW; q++) s_stage[pos * RW + q] = w[q];
+            }
+        }
+    }
+    // ---- the registers are free: request the next tile before this one leaves ----
+    if (next_count > 0) part_load_tile<KW, NV, TP_T>(L, (tile + 1) * TP_TILE, next_count, tid, key, val);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy stores -> visible to the bulk copy
+    __syncthreads();
+    if (tid == 0) {
+        // the whole tile block is written (rows past a ragged last tile's count are never read: the directory bounds
+        // every run); 16 KB pieces
+        constexpr uint32_t BYTES = (uint32_t)TP_TILE * RW * 4;
+        unsigned char *g = reinterpret_cast<unsigned char *>(P.rows_out) + (size_t)tile * BYTES;
+        const unsigned char *sm = reinterpret_cast<const unsigned char *>(s_stage);
+#pragma unroll 1
+        for (uint32_t o = 0; o < BYTES; o += 16384u) tp_bulk_store(g + o, sm + o, min(16384u, BYTES - o));
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+}
+
+template <int KW, int NV, bool HASH>
 __global__ void __launch_bounds__(TP_T, 2) hk_tpart_kernel(const __grid_constant__ TPartParams P) {
     using KT = typename KRaw<KW>::T;
     constexpr int RW = KW / 4 + NV;
-    extern __shared__ __align__(128) uint32_t s_stage[]; // TP_TILE rows x RW words
-    __shared__ uint32_t s_hist[256];
-    __shared__ uint32_t s_binstart[256];
-    __shared__ uint32_t s_wtot[8];
+    extern __shared__ __align__(128) uint32_t s_dyn32[]; // stage (TP_TILE rows x RW words), then the small arrays
+    uint32_t *s_stage = s_dyn32;
+    uint32_t *s_hist = s_dyn32 + (size_t)TP_TILE * RW;
+    uint32_t *s_binstart = s_hist + 256;
+    uint32_t *s_wtot = s_binstart + 256;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int64_t t0 = (int64_t)blockIdx.x * P.tiles_per_cta;
     const int64_t t1 = min(P.num_tiles, t0 + P.tiles_per_cta);
     if (tid < 256) s_hist[tid] = 0;
     if (t0 >= t1) return;
 
-    PartParams L; // the loader of K8a, reused: it only looks at the input pointers and n
+    PartParams L; // the loader of K8a, reused: it only looks at the input pointers
     L.key_in = P.key_in;
     for (int v = 0; v < PMAXV; v++) L.val_in[v] = P.val_in[v];
+    const KT xmask = (KT)P.f.xmask, base = (KT)P.f.base, last = (KT)P.f.last;
+    const int shift = P.f.shift;
     KT key[PI];
     uint32_t val[NV > 0 ? NV : 1][PI];
     int count = (int)min((int64_t)TP_TILE, P.n - t0 * TP_TILE);
@@ -391,88 +479,20 @@ __global__ void __launch_bounds__(TP_T, 2) hk_tpart_kernel(const __grid_constant
     __syncthreads();
 
     for (int64_t tile = t0; tile < t1; tile++) {
-        // ---- rank inside the tile: one shared-memory atomic per row (bin << 16 | rank) ----
-        uint32_t rd[PI];
-#pragma unroll
-        for (int i = 0; i < PI; i++) {
-            const int idx = ((i >> 2) * TP_T + tid) * 4 + (i & 3);
-            if (count == TP_TILE || idx < count) {
-                const uint32_t d = tpart_digit<KW>(key[i], P);
-                rd[i] = (d << 16) | atomicAdd(&s_hist[d], 1u);
-            } else {
-                rd[i] = 0xffffffffu;
-            }
-        }
-        // the bulk copy of the previous tile must have finished READING the stage before anyone overwrites it
-        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        __syncthreads();
-        // ---- thread b owns bin b: start of the bin's run inside the tile, directory word ----
-        {
-            const uint32_t sum = tid < 256 ? s_hist[tid] : 0u;
-            if (tid < 256) s_hist[tid] = 0;
-            const uint32_t inc = hk_warp_incl_scan_u32(sum);
-            if (lane == 31 && warp < 8) s_wtot[warp] = inc;
-            __syncthreads();
-            if (tid < 256) {
-                uint32_t woff = 0;
-                for (int w = 0; w < warp; w++) woff += s_wtot[w];
-                const uint32_t binstart = woff + inc - sum;
-                s_binstart[tid] = binstart;
-                if (tid < P.nbins) P.dir[(size_t)tile * P.nbins + tid] = binstart | ((binstart + sum) << 16);
-            }
-        }
-        __syncthreads();
-        // ---- the packed rows go to their slot of the stage ----
-#pragma unroll
-        for (int i = 0; i < PI; i++) {
-            if (rd[i] != 0xffffffffu) {
-                const uint32_t pos = s_binstart[rd[i] >> 16] + (rd[i] & 0xffffu);
-                uint32_t w[RW];
-                if constexpr (KW == 4) {
-                    w[0] = key[i];
-                } else {
-                    w[0] = (uint32_t)key[i];
-                    w[1] = (uint32_t)(key[i] >> 32);
-                }
-#pragma unroll
-                for (int v = 0; v < NV; v++) w[KW / 4 + v] = val[v][i];
-                if constexpr (RW == 2) {
-                    reinterpret_cast<uint2 *>(s_stage)[pos] = make_uint2(w[0], w[1]);
-                } else if constexpr (RW == 4) {
-                    reinterpret_cast<uint4 *>(s_stage)[pos] = make_uint4(w[0], w[1], w[2], w[3]);
-                } else {
-#pragma unroll
-                    for (int q = 0; q < RW; q++) s_stage[pos * RW + q] = w[q];
-                }
-            }
-        }
-        // ---- the registers are free: request the next tile before this one leaves ----
-        const int cur_count = count;
-        if (tile + 1 < t1) {
-            count = (int)min((int64_t)TP_TILE, P.n - (tile + 1) * TP_TILE);
-            part_load_tile<KW, NV, TP_T>(L, (tile + 1) * TP_TILE, count, tid, key, val);
-        }
-        (void)cur_count;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy stores -> visible to the bulk copy
-        __syncthreads();
-        if (tid == 0) {
-            // the whole tile block is written (rows past a ragged last tile's count are never read: the directory
-            // bounds every run); 16 KB pieces
-            constexpr uint32_t BYTES = (uint32_t)TP_TILE * RW * 4;
-            unsigned char *g = reinterpret_cast<unsigned char *>(P.rows_out) + (size_t)tile * BYTES;
-            const unsigned char *sm = reinterpret_cast<const unsigned char *>(s_stage);
-#pragma unroll 1
-            for (uint32_t o = 0; o < BYTES; o += 16384u) tp_bulk_store(g + o, sm + o, min(16384u, BYTES - o));
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
+        const int next_count = tile + 1 < t1 ? (int)min((int64_t)TP_TILE, P.n - (tile + 1) * TP_TILE) : 0;
+        if (count == TP_TILE)
+            tpart_tile<KW, NV, HASH, true>(P, L, s_stage, s_hist, s_binstart, s_wtot, tile, count, next_count, key, val, xmask, base, last, shift);
+        else
+            tpart_tile<KW, NV, HASH, false>(P, L, s_stage, s_hist, s_binstart, s_wtot, tile, count, next_count, key, val, xmask, base, last, shift);
+        count = next_count;
     }
     if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // shared memory must outlive the copy
 }
 
 template <int KW, int NV>
 int launch_tpart(hark_ctx *ctx, const TPartParams &P, unsigned grid) {
-    const size_t smem = (size_t)TP_TILE * (KW / 4 + NV) * 4;
-    auto kern = hk_tpart_kernel<KW, NV>;
+    const size_t smem = (size_t)TP_TILE * (KW / 4 + NV) * 4 + (256 + 256 + 8) * 4;
+    void (*kern)(const TPartParams) = P.hash ? hk_tpart_kernel<KW, NV, true> : hk_tpart_kernel<KW, NV, false>;
     HK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, TP_T, smem, ctx->stream>>>(P);
     HK_CHECK_LAUNCH(ctx);

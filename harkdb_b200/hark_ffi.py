@@ -28,7 +28,7 @@ DTYPE_CODES = {v: k for k, v in NP_DTYPES.items()}
 GT, GE, LT, LE, EQ, NE = 0, 1, 2, 3, 4, 5
 CMP_CODES = {">": GT, ">=": GE, "<": LT, "<=": LE, "=": EQ, "==": EQ, "!=": NE, "<>": NE,
              "gt": GT, "gte": GE, "lt": LT, "lte": LE, "eq": EQ, "neq": NE}
-AGG_KEY, AGG_PROD, AGG_SUM, AGG_MAX, AGG_MIN, AGG_COUNT, AGG_AVG, AGG_SUMF64 = 0, 1, 2, 3, 4, 5, 6, 7
+AGG_KEY, AGG_PROD, AGG_SUM, AGG_MAX, AGG_MIN, AGG_COUNT, AGG_AVG, AGG_SUMF64, AGG_SUM64 = 0, 1, 2, 3, 4, 5, 6, 7, 8
 GEN_UNIFORM, GEN_AFFINE, GEN_CONST, GEN_LOGUNIFORM, GEN_AFFINE_UNIFORM = 0, 1, 2, 3, 4
 
 STATUS = {0: "HARK_OK", 1: "HARK_ERR_ARG", 2: "HARK_ERR_CUDA", 3: "HARK_ERR_OOM", 4: "HARK_ERR_UNSUPPORTED"}

@@ -363,6 +363,10 @@ def _plan_join(js_obj, name1, table1, pj, aliases):
     """FROM t1 JOIN t2 ON t1.a = t2.b, plain select list (join.fut:52 argument order) or
     GROUP BY over a t2 column with aggregates over t1 columns (hark_entry_join_groupby)."""
     name2, table2 = pj["name2"], pj["table2"]
+    if name1 == name2:
+        # both aliases would resolve to one schema entry: the ON columns and every qualified column of the second alias
+        # would silently be read from the first.  Refuse instead of planning a wrong query.
+        raise Exception(f"self-join of {name1} is not supported: register the table under a second name with create_table")
     schema = {name1: table1.get_schema(), name2: table2.get_schema()}
 
     def locate(name):

@@ -28,7 +28,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 I32, U32, I64, F32, F64 = 0, 1, 2, 3, 4
-AGG_KEY, AGG_PROD, AGG_SUM, AGG_MAX, AGG_MIN, AGG_COUNT, AGG_AVG, AGG_SUMF64 = 0, 1, 2, 3, 4, 5, 6, 7
+AGG_KEY, AGG_PROD, AGG_SUM, AGG_MAX, AGG_MIN, AGG_COUNT, AGG_AVG, AGG_SUMF64, AGG_SUM64 = 0, 1, 2, 3, 4, 5, 6, 7, 8
 NP_DTYPES = {I32: np.dtype(np.int32), U32: np.dtype(np.uint32), I64: np.dtype(np.int64),
              F32: np.dtype(np.float32), F64: np.dtype(np.float64)}
 
@@ -49,7 +49,7 @@ def expand_partial_ops(s_cols: Sequence[int], ops: Sequence[int], pinned_u32: bo
         op = int(op)
         if pinned_u32:
             op = op if op in (AGG_PROD, AGG_SUM, AGG_MAX, AGG_MIN) else AGG_MIN        # groupby.fut:41
-        elif op < AGG_PROD or op > AGG_SUMF64:
+        elif op < AGG_PROD or op > AGG_SUM64:
             op = AGG_MIN
         if op == AGG_AVG:
             p_s += [c, c]
@@ -62,7 +62,7 @@ def expand_partial_ops(s_cols: Sequence[int], ops: Sequence[int], pinned_u32: bo
 
 def merge_ops_for(p_ops: Sequence[int]) -> List[int]:
     """Operator that combines two partials of each partial column (counts and sums add)."""
-    return [AGG_SUM if op in (AGG_SUM, AGG_COUNT, AGG_SUMF64) else op for op in p_ops]
+    return [AGG_SUM if op in (AGG_SUM, AGG_COUNT, AGG_SUMF64, AGG_SUM64) else op for op in p_ops]
 
 
 def final_ops_for(ops: Sequence[int], pinned_u32: bool = False) -> List[int]:
@@ -71,7 +71,7 @@ def final_ops_for(ops: Sequence[int], pinned_u32: bool = False) -> List[int]:
         op = int(op)
         if pinned_u32:
             op = op if op in (AGG_PROD, AGG_SUM, AGG_MAX, AGG_MIN) else AGG_MIN
-        elif op < AGG_PROD or op > AGG_SUMF64:
+        elif op < AGG_PROD or op > AGG_SUM64:
             op = AGG_MIN
         out.append(op)
     return out

@@ -153,6 +153,29 @@ class Table:
     def get_name(self):
         return self._table_name
 
+    def is_u32_exact(self):
+        """True when every column is an integer column whose values all lie in [0, 2^32): only then do the
+        reference-pinned u32 entries (groupby.fut / join.fut compare and combine as u32) compute what SQL means; a
+        table with negative values must take the typed entries (signed order, signed MIN / MAX)."""
+        if getattr(self, "_u32_exact", None) is None:
+            srcs = self._columns if self._columns is not None else [self._data]
+            ok = True
+            for a in srcs:
+                a = np.asarray(a)
+                if a.dtype.kind not in "iub":
+                    ok = False
+                elif a.size and (int(a.min()) < 0 or int(a.max()) >= 2 ** 32):
+                    ok = False
+            self._u32_exact = ok
+        return self._u32_exact
+
+    def _tag(self, handle):
+        try:
+            handle.u32_exact = self.is_u32_exact()
+        except AttributeError:        # a plain ndarray cannot carry attributes: FutharkContext looks at its values
+            pass
+        return handle
+
     # ---- device residency (new) ----
     def upload(self, env):
         """Transpose to device SoA once; later queries use the resident handle."""
@@ -161,6 +184,7 @@ class Table:
                 self._device = env.from_columns([c.astype(entry_dtype(c), copy=False) for c in self._columns])
             else:
                 self._device = env.to_device(self._data, entry_dtype(self._data))
+            self._tag(self._device)
         return self._device
 
     def get_column_dtypes(self):
@@ -175,7 +199,7 @@ class Table:
         if self._device is not None:
             return self._device
         if self._columns is not None:
-            return HostColumns(c.astype(entry_dtype(c), copy=False) for c in self._columns)
+            return self._tag(HostColumns(c.astype(entry_dtype(c), copy=False) for c in self._columns))
         return self._data
 
     def release(self):

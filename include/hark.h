@@ -73,7 +73,9 @@ typedef struct {
 typedef enum {
     HARK_AGG_KEY = 0, HARK_AGG_PROD = 1, HARK_AGG_SUM = 2, HARK_AGG_MAX = 3, HARK_AGG_MIN = 4,
     HARK_AGG_COUNT = 5, HARK_AGG_AVG = 6,
-    HARK_AGG_SUMF64 = 7 /* f64 sum as its own f64 column: the partial aggregate behind a distributed AVG */
+    HARK_AGG_SUMF64 = 7, /* f64 sum as its own f64 column: the partial aggregate behind a distributed AVG */
+    HARK_AGG_SUM64 = 8   /* exact SUM: integer columns accumulate in 64 bits -> i64 column (SQL's SUM; code 2 keeps the
+                            reference's wrap-around in the column width, groupby.fut:37); float columns: as code 7 */
 } hark_agg;
 
 /* Synthetic column generator (hark_table_synth).  Value of (column c, global row r) is a pure
@@ -168,7 +170,7 @@ int hark_entry_join(hark_ctx *ctx, hark_table **out, const hark_table *db1, cons
 int hark_entry_query_filter(hark_ctx *ctx, hark_table **out, const hark_table *db, const int32_t *cols, int64_t k,
                             const hark_pred *preds, int64_t np);
 /* Typed GROUP BY: key column any integer dtype, ordered by its own signedness; value columns any
- * dtype; codes 0-6; SUM/PROD wrap in the column's width, COUNT -> i64 column, AVG -> f64 column;
+ * dtype; codes 0-8; SUM/PROD wrap in the column's width (SUM64 does not), COUNT -> i64 column, AVG -> f64 column;
  * HAVING = conjunction over OUTPUT column indices (0 = key).                                   */
 int hark_entry_query_groupby_ex(hark_ctx *ctx, hark_table **out, const hark_table *db, int32_t g_col,
                                 const int32_t *s_cols, const int32_t *ops, int64_t c, const hark_pred *having,

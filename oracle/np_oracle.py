@@ -30,7 +30,7 @@ NP_DTYPES = {I32: np.int32, U32: np.uint32, I64: np.int64, F32: np.float32, F64:
 DTYPE_CODES = {np.dtype(v): k for k, v in NP_DTYPES.items()}
 
 GT, GE, LT, LE, EQ, NE = 0, 1, 2, 3, 4, 5
-AGG_KEY, AGG_PROD, AGG_SUM, AGG_MAX, AGG_MIN, AGG_COUNT, AGG_AVG, AGG_SUMF64 = 0, 1, 2, 3, 4, 5, 6, 7
+AGG_KEY, AGG_PROD, AGG_SUM, AGG_MAX, AGG_MIN, AGG_COUNT, AGG_AVG, AGG_SUMF64, AGG_SUM64 = 0, 1, 2, 3, 4, 5, 6, 7, 8
 GEN_UNIFORM, GEN_AFFINE, GEN_CONST, GEN_LOGUNIFORM, GEN_AFFINE_UNIFORM = 0, 1, 2, 3, 4
 
 Pred = Tuple[int, int, int, float]  # (col, op, ival, fval) — include/hark.h hark_pred
@@ -289,7 +289,10 @@ def _agg_typed(op: int, v: np.ndarray, starts: np.ndarray, counts: np.ndarray) -
     G = len(starts)
     if op == AGG_COUNT:
         return counts.astype(np.int64)
-    if op == AGG_AVG or op == AGG_SUMF64:
+    if op == AGG_SUM64 and code in (I32, U32, I64):      # exact integer sum (wraps only at 2^64)
+        with np.errstate(over="ignore"):
+            return np.add.reduceat(v.astype(np.int64), starts) if G else np.zeros(0, np.int64)
+    if op == AGG_AVG or op == AGG_SUMF64 or op == AGG_SUM64:
         s = np.add.reduceat(v.astype(np.float64), starts) if G else np.zeros(0, np.float64)
         return s / counts.astype(np.float64) if op == AGG_AVG else s
     if G == 0:
@@ -326,6 +329,8 @@ def _agg_typed(op: int, v: np.ndarray, starts: np.ndarray, counts: np.ndarray) -
 def agg_out_dtype(op: int, code: int) -> int:
     if op == AGG_COUNT:
         return I64
+    if op == AGG_SUM64:
+        return I64 if code in (I32, U32, I64) else F64
     if op == AGG_AVG or op == AGG_SUMF64:
         return F64
     return code
