@@ -294,6 +294,8 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"       # NCCL would print its version banner on stdout, next to the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():

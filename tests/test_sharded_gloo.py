@@ -114,6 +114,33 @@ def _scn_groupby(senv):
         _check(senv.gather_columns(r), NO.query_groupby_ex(cols, 0, s_cols, ops, having=hv), "groupby having")
 
 
+def _scn_groupby_dense(senv):
+    """Shapes the all-reduce merge takes (sums, counts, AVG, integer MIN / MAX over a small dense key domain): negative
+    keys, u32 keys above 2^31, a rank without rows, HAVING, SUM64; then the same query with the reduce switched off
+    must give the same answer through the repartition."""
+    rng = np.random.default_rng(12)
+    for kdt, n in ((np.int32, 20011), (np.uint32, 5003), (np.int64, 1), (np.int32, 0)):
+        lo = {np.int32: -700, np.uint32: 2 ** 31 - 300, np.int64: -(2 ** 40)}[kdt]
+        cols = [(lo + rng.integers(0, 900, n)).astype(kdt), rng.integers(-1000, 1000, n).astype(np.int32),
+                rng.random(n).astype(np.float32), rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32)]
+        t = _shard(senv, cols)
+        ops = [NO.AGG_SUM, NO.AGG_COUNT, NO.AGG_AVG, NO.AGG_MAX, NO.AGG_MIN, NO.AGG_SUM, NO.AGG_AVG, NO.AGG_MAX, NO.AGG_MIN, NO.AGG_SUM64]
+        s_cols = [1, 1, 1, 1, 1, 2, 2, 3, 3, 3]
+        for hv in ((), [(2, NO.GT, 20, 0.0)]):
+            exp = NO.query_groupby_ex(cols, 0, s_cols, ops, having=list(hv))
+            for dense in (True, False):
+                senv.dense_merge = dense
+                senv.pop_trace()
+                senv.trace_on = True
+                r = senv.query_groupby_ex(t, 0, s_cols, ops, hv)
+                tr = senv.pop_trace()
+                senv.trace_on = False
+                assert ("merge_reduce" in tr) == (dense and senv.world > 1), tr
+                assert ("exchange" in tr) == (not dense and senv.world > 1), tr
+                _check(senv.gather_columns(r), exp, f"groupby dense={dense} {kdt} {n} {hv}")
+    senv.dense_merge = True
+
+
 def _scn_groupby_multi(senv):
     rng = np.random.default_rng(8)
     n = 15013
@@ -233,7 +260,7 @@ def _scn_sql_join(senv):
 
 
 # ------------------------------------------------------------------ tests
-@pytest.mark.parametrize("scenario", ["filter", "groupby", "groupby_multi", "groupby_pinned", "orderby", "join", "sql", "sql_join"])
+@pytest.mark.parametrize("scenario", ["filter", "groupby", "groupby_dense", "groupby_multi", "groupby_pinned", "orderby", "join", "sql", "sql_join"])
 def test_sharded_world2(scenario):
     _run(scenario, 2)
 
