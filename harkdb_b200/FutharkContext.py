@@ -13,7 +13,7 @@ Tables are uploaded once at ``create_table`` and stay resident in HBM as SoA col
 
 import numpy as np
 
-from .hark_ffi import AGG_SUM, AGG_SUM64, DeviceTable, Futhark, I32, U32, I64
+from .hark_ffi import AGG_COUNT, AGG_SUM, AGG_SUM64, DeviceTable, Futhark, I32, U32, I64
 from .parse import finalize_pred, sql_parse
 from .table import HostColumns, Table
 
@@ -206,6 +206,12 @@ class FutharkContext:
                 grouped = env.query_groupby_ex(keyed, 0, [c + 1 for c in s_cols], ops)
             finally:
                 keyed.free()
+            if grouped.shape[0] == 0:
+                # no qualifying row: SQL still answers with ONE row — COUNT = 0 and NULL elsewhere.  There are no NULLs
+                # here, so NULL is NaN and the row is float64 (a zero-row GROUP BY would have produced no row at all)
+                grouped.free()
+                row = np.array([[0.0 if int(op) == AGG_COUNT else np.nan for op in ops]], dtype=np.float64)
+                return row if plan.get("limit") is None else row[:plan["limit"]]
             res = env.query_filter(grouped, list(range(1, 1 + len(ops))), [])
             grouped.free()
             return self._finish(res, plan.get("limit"))

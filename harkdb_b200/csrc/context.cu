@@ -263,10 +263,7 @@ int hk_table_alloc(hark_ctx *ctx, hark_table **out, int64_t n, int64_t cap, cons
 
 extern "C" int hark_table_free(hark_ctx *ctx, hark_table *t) {
     HK_ENTER(ctx);
-    if (!t) return HARK_OK;
-    for (auto &c : t->cols)
-        if (c.owned) ctx->dfree(c.ptr);
-    delete t;
+    hk_table_free(ctx, t);
     return HARK_OK;
 }
 
@@ -437,7 +434,7 @@ extern "C" int hark_table_from_host(hark_ctx *ctx, hark_table **out, const void 
     if (e != cudaSuccess && rc == HARK_OK)
         rc = ctx->fail(HARK_ERR_CUDA, std::string("table_from_host: ") + cudaGetErrorString(e));
     if (rc != HARK_OK) {
-        hark_table_free(ctx, t);
+        hk_table_free(ctx, t);
         return rc;
     }
     *out = t;
@@ -457,7 +454,7 @@ extern "C" int hark_table_from_columns(hark_ctx *ctx, hark_table **out, const vo
         cudaError_t e = cudaMemcpyAsync(t->cols[c].ptr, host_cols[c], (size_t)n * hk_dtype_size(dtypes[c]),
                                         cudaMemcpyHostToDevice, ctx->stream);
         if (e != cudaSuccess) {
-            hark_table_free(ctx, t);
+            hk_table_free(ctx, t);
             return ctx->fail(HARK_ERR_CUDA, std::string("table_from_columns: ") + cudaGetErrorString(e));
         }
     }
@@ -616,7 +613,7 @@ extern "C" int hark_table_synth(hark_ctx *ctx, hark_table **out, int64_t n, int6
         }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) {
-            hark_table_free(ctx, t);
+            hk_table_free(ctx, t);
             return ctx->fail(HARK_ERR_CUDA, std::string("table_synth: ") + cudaGetErrorString(e));
         }
     }
@@ -642,7 +639,7 @@ extern "C" int hark_table_slice(hark_ctx *ctx, hark_table **out, const hark_tabl
     HK_TRY(hk_table_alloc(ctx, &r, nrows, nrows, dts.data(), m));
     int rc = hk_copy_columns(ctx, r, t, idx.data(), m, row0, nrows, 0);
     if (rc != HARK_OK) {
-        hark_table_free(ctx, r);
+        hk_table_free(ctx, r);
         return rc;
     }
     *out = r;
@@ -666,7 +663,7 @@ extern "C" int hark_table_concat(hark_ctx *ctx, hark_table **out, const hark_tab
     int rc = hk_copy_columns(ctx, r, a, idx.data(), m, 0, a->n, 0);
     if (rc == HARK_OK) rc = hk_copy_columns(ctx, r, b, idx.data(), m, 0, b->n, a->n);
     if (rc != HARK_OK) {
-        hark_table_free(ctx, r);
+        hk_table_free(ctx, r);
         return rc;
     }
     *out = r;

@@ -1407,7 +1407,7 @@ int hk_dense_groupby(hark_ctx *ctx, hark_table **out, const hk_dense_req &rq, bo
         cudaError_t e = cudaGetLastError();
         ctx->count_launch();
         if (e != cudaSuccess) {
-            hark_table_free(ctx, t);
+            hk_table_free(ctx, t);
             return ctx->fail(HARK_ERR_CUDA, std::string("dense compact: ") + cudaGetErrorString(e));
         }
     }

@@ -840,7 +840,7 @@ int hk_filter(hark_ctx *ctx, hark_table **out, const hark_table *db, const int32
         int rc = hk_copy_columns(ctx, t, db, cols, k, 0, n, 0);
         ctx->kernel_end();
         if (rc != HARK_OK) {
-            hark_table_free(ctx, t);
+            hk_table_free(ctx, t);
             return rc;
         }
         for (int64_t j = 0; j < k; j++) alg_bytes += 2 * n * hk_dtype_size(dts[j]);
@@ -859,7 +859,7 @@ int hk_filter(hark_ctx *ctx, hark_table **out, const hark_table *db, const int32
     const size_t scratch_bytes = (size_t)(num_tiles + 2) * sizeof(uint64_t);
     int rc = ctx->dalloc((void **)&scratch, scratch_bytes);
     if (rc != HARK_OK) {
-        hark_table_free(ctx, t);
+        hk_table_free(ctx, t);
         return rc;
     }
 
@@ -961,7 +961,7 @@ int hk_filter(hark_ctx *ctx, hark_table **out, const hark_table *db, const int32
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     ctx->dfree(scratch);
     if (e != cudaSuccess) {
-        hark_table_free(ctx, t);
+        hk_table_free(ctx, t);
         return ctx->fail(HARK_ERR_CUDA, std::string("query_filter: ") + cudaGetErrorString(e));
     }
     n_out = ctx->h_scalars[0];

@@ -105,7 +105,7 @@ template <typename A>
 static int wrap_out(struct futhark_context *ctx, A **out, hark_table *t) {
     A *a = new (std::nothrow) A();
     if (!a) {
-        hark_table_free(ctx->h, t);
+        hk_table_free(ctx->h, t);
         return HARK_ERR_OOM;
     }
     a->t = t;

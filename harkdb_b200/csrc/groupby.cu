@@ -491,7 +491,7 @@ int hk_segmented_aggregate(hark_ctx *ctx, hark_table **out, int64_t n, const voi
     struct Guard {
         hark_ctx *ctx;
         hark_table *t;
-        ~Guard() { if (t) hark_table_free(ctx, t); }
+        ~Guard() { if (t) hk_table_free(ctx, t); }
     } guard{ctx, t};
     unsigned long long *d_pos = nullptr;
     HK_TRY(scratch.alloc((void **)&d_pos, sizeof(unsigned long long) * (size_t)G));
@@ -660,7 +660,7 @@ int hk_groupby(hark_ctx *ctx, hark_table **out, const hark_table *db, int32_t g_
                     for (int64_t j = 0; j < 1 + c; j++) all.push_back((int32_t)j);
                     hark_table *f = nullptr;
                     int rc = hk_filter(ctx, &f, t, all.data(), 1 + c, having, nh);
-                    hark_table_free(ctx, t);
+                    hk_table_free(ctx, t);
                     if (rc != HARK_OK) return rc;
                     t = f;
                 }
@@ -729,7 +729,7 @@ int hk_groupby(hark_ctx *ctx, hark_table **out, const hark_table *db, int32_t g_
         for (int64_t j = 0; j < 1 + c; j++) all.push_back((int32_t)j);
         hark_table *f = nullptr;
         rc = hk_filter(ctx, &f, t, all.data(), 1 + c, having, nh);
-        hark_table_free(ctx, t);
+        hk_table_free(ctx, t);
         if (rc != HARK_OK) return rc;
         t = f;
     }

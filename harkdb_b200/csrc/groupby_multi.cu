@@ -216,7 +216,7 @@ int hk_groupby_multi(hark_ctx *ctx, hark_table **out, const hark_table *db, cons
     hark_table *keys = nullptr;
     rc = hk_table_alloc(ctx, &keys, G, G, odt.data(), ng);
     if (rc != HARK_OK) {
-        hark_table_free(ctx, g);
+        hk_table_free(ctx, g);
         return rc;
     }
     if (G > 0) {
@@ -230,8 +230,8 @@ int hk_groupby_multi(hark_ctx *ctx, hark_table **out, const hark_table *db, cons
         cudaError_t e = cudaGetLastError();
         ctx->count_launch();
         if (e != cudaSuccess) {
-            hark_table_free(ctx, g);
-            hark_table_free(ctx, keys);
+            hk_table_free(ctx, g);
+            hk_table_free(ctx, keys);
             return ctx->fail(HARK_ERR_CUDA, std::string("query_groupby_multi(unpack): ") + cudaGetErrorString(e));
         }
     }
@@ -241,14 +241,14 @@ int hk_groupby_multi(hark_ctx *ctx, hark_table **out, const hark_table *db, cons
         g->cols[j].owned = false;
     }
     t->cap = std::min(t->cap, g->cap);
-    hark_table_free(ctx, g);
+    hk_table_free(ctx, g);
 
     if (nh > 0) { // HAVING over the output columns (K1 on the small group table)
         std::vector<int32_t> all;
         for (int64_t j = 0; j < ng + c; j++) all.push_back((int32_t)j);
         hark_table *f = nullptr;
         rc = hk_filter(ctx, &f, t, all.data(), ng + c, having, nh);
-        hark_table_free(ctx, t);
+        hk_table_free(ctx, t);
         if (rc != HARK_OK) return rc;
         t = f;
     }

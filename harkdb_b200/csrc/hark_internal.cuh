@@ -131,6 +131,15 @@ static inline bool hk_dtype_int(int dt) { return dt == HARK_I32 || dt == HARK_U3
 
 void hk_peer_destroy(hark_ctx *ctx); // repartition.cu
 
+// frees a table from INSIDE an operator: unlike the ABI's hark_table_free it does not pass through HK_ENTER, which
+// would reset entry_depth (and with it the outer entry's statistics) in the middle of a nested operator
+static inline void hk_table_free(hark_ctx *ctx, hark_table *t) {
+    if (!t) return;
+    for (auto &c : t->cols)
+        if (c.owned) ctx->dfree(c.ptr);
+    delete t;
+}
+
 // new table with m owned columns of capacity cap rows (uninitialised)
 int hk_table_alloc(hark_ctx *ctx, hark_table **out, int64_t n, int64_t cap, const int32_t *dtypes, int64_t m);
 

@@ -703,7 +703,7 @@ int hk_join_ex(hark_ctx *ctx, hark_table **out, const hark_table *db1, const har
             cudaError_t e = cudaGetLastError();
             ctx->count_launch();
             if (e != cudaSuccess) {
-                hark_table_free(ctx, t);
+                hk_table_free(ctx, t);
                 return ctx->fail(HARK_ERR_CUDA, std::string("join(expand): ") + cudaGetErrorString(e));
             }
         }
@@ -747,7 +747,7 @@ int hk_join_ex(hark_ctx *ctx, hark_table **out, const hark_table *db1, const har
             cudaError_t e = cudaGetLastError();
             ctx->count_launch();
             if (e != cudaSuccess) {
-                hark_table_free(ctx, t);
+                hk_table_free(ctx, t);
                 return ctx->fail(HARK_ERR_CUDA, std::string("join(hash expand): ") + cudaGetErrorString(e));
             }
         }
@@ -1031,7 +1031,7 @@ int hk_join_groupby(hark_ctx *ctx, hark_table **out, const hark_table *fact, con
     HK_TRY(hk_filter(ctx, &matched, &tmp, sel.data(), (int64_t)sel.size(), &only_hits, 1));
     hark_table *res = nullptr;
     int rc = hk_groupby(ctx, &res, matched, 0, s2.data(), ops2.data(), c, nullptr, 0, false);
-    hark_table_free(ctx, matched);
+    hk_table_free(ctx, matched);
     if (rc != HARK_OK) return rc;
     int64_t alg = 0;
     alg += nf * hk_dtype_size(fk_dtype);

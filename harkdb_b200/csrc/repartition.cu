@@ -205,7 +205,7 @@ extern "C" int hark_table_partition_by_splitters(hark_ctx *ctx, hark_table **out
         }
         ctx->dfree(arrays[1].result);
         if (rc != HARK_OK) {
-            hark_table_free(ctx, t);
+            hk_table_free(ctx, t);
             return rc;
         }
     }
@@ -301,7 +301,7 @@ extern "C" int hark_entry_groupby_finalize(hark_ctx *ctx, hark_table **out, cons
         }
     }
     if (rc != HARK_OK) {
-        hark_table_free(ctx, t);
+        hk_table_free(ctx, t);
         return rc;
     }
     ctx->entry_end(0, G, G);

@@ -136,7 +136,11 @@ int hark_table_from_host(hark_ctx *ctx, hark_table **out, const void *rowmajor, 
 /* m host column arrays, one dtype each. */
 int hark_table_from_columns(hark_ctx *ctx, hark_table **out, const void *const *host_cols,
                             const int32_t *dtypes, int64_t n, int64_t m);
-/* m device column arrays (16-byte aligned), borrowed: the table never frees them.             */
+/* m device column arrays, borrowed: the table never frees them.  Contract for borrowed columns: (1) 16-byte aligned
+ * and readable up to the next multiple of 256 bytes past the last row (the kernels read ragged ends with 128-bit
+ * loads; cudaMalloc / torch allocations satisfy this); (2) the caller may change the buffers BETWEEN entries — the
+ * library keeps no statistics (min / max, zone maps) of borrowed columns, only of columns it owns — but not while an
+ * entry is running on the context's stream.                                                                       */
 int hark_table_from_device(hark_ctx *ctx, hark_table **out, void *const *dev_cols, const int32_t *dtypes,
                            int64_t n, int64_t m);
 /* Generated on the device; rows are global rows row0 .. row0+n-1 of the synthetic relation.    */
