@@ -434,6 +434,49 @@ def run_gpu_arm(args):
                                "note": "bytes crossing PCIe per step / step time, against a pinned 1 GiB torch copy timed in this run"}
             except Exception as ex:      # never lose the bench line over a diagnostic
                 e2e["pcie"] = {"error": repr(ex)[:200]}
+            # the same query when the host table is COLUMNAR (one pinned array per column, what create_table keeps for
+            # DataFrames / Arrow / dict tables): only the 3 columns the statement names cross PCIe (12 of the 32 B per row)
+            try:
+                need = sorted(set(SEL_COLS) | {p[0] for p in PREDS})
+                hcols, hptrs = {}, []
+                for c in need:
+                    hp = lib.hark_host_alloc(e2e_rows * 4)
+                    hptrs.append(hp)
+                    hcols[c] = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_float)), shape=(e2e_rows,))
+                    hcols[c][:] = host_in[:, c]
+                sub_sel = [need.index(c) for c in SEL_COLS]
+                sub_preds = [(need.index(p[0]),) + tuple(p[1:]) for p in PREDS]
+
+                def col_step():
+                    t = env.from_columns([hcols[c] for c in need])          # H2D of the needed columns
+                    r = env.query_filter(t, sub_sel, sub_preds)
+                    kk = r.shape[0]
+                    r.to_numpy(out=host_out[:kk])                          # D2H of the result
+                    r.free()
+                    t.free()
+                    return kk
+
+                for _ in range(3):
+                    kc = col_step()
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(args.e2e_steps):
+                    kc = col_step()
+                barrier()
+                dtc = time.perf_counter() - t0
+                if world > 1:
+                    tm = torch.tensor([dtc], device="cuda", dtype=torch.float64)
+                    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                    dtc = float(tm.item())
+                e2e["columnar_host_table"] = {
+                    "value": world * e2e_rows * args.e2e_steps / dtc, "unit": "rows/s", "ms_per_step": 1e3 * dtc / args.e2e_steps,
+                    "h2d_bytes_per_step": e2e_rows * 4 * len(need), "d2h_bytes_per_step": int(kc) * 8, "rows_out_match": bool(kc == k),
+                    "path": "pinned host columns -> hark_table_from_columns (H2D of the 3 columns the query names) -> "
+                            "hark_entry_query_filter -> hark_table_to_host (D2H), all inside the timed step"}
+                for hp in hptrs:
+                    lib.hark_host_free(hp)
+            except Exception as ex:
+                e2e["columnar_host_table"] = {"error": repr(ex)[:200]}
             # and the product's default (resident table, only the result crosses PCIe)
             t0 = time.perf_counter()
             for _ in range(args.e2e_steps):

@@ -90,13 +90,46 @@ class FutharkContext:
         """sql_parse(tables, sql_statement) -> plan -> libhark entries -> 2-D ndarray."""
         val_dic = sql_parse(self.tables, sql_statement)
         if isinstance(val_dic["table"], HostColumns) and "join" not in val_dic:
-            # not resident and one dtype per column: upload the columns for this query, then take the usual routes
+            # not resident and one dtype per column: upload for this query — and only the columns the statement names
+            # (a scan over 3 of 8 columns moves 3/8 of the bytes across PCIe) — then take the usual routes
+            val_dic = self._pruned(val_dic)
             dev, _ = self._as_device(val_dic["table"])
             try:
                 return self._dispatch({**val_dic, "table": dev})
             finally:
                 dev.free()
         return self._dispatch(val_dic)
+
+    @staticmethod
+    def _pruned(plan):
+        """Plan over a HostColumns table -> the same plan over the sub-table of the columns it uses, indices remapped."""
+        t = plan["table"]
+        grouped = "groupbys" in plan
+        used = set(int(c) for c in plan["select"])
+        used |= {int(p[0]) for p in plan.get("where", [])}
+        if "g_cols" in plan:
+            used |= {int(g) for g in plan["g_cols"]}
+        if "g_col" in plan:
+            used.add(int(plan["g_col"]))
+        if not grouped and not plan.get("global"):
+            used |= {int(k) for k, _ in plan.get("orderby", [])}          # ORDER BY keys of a plain select are table columns
+        used = sorted(used)
+        if len(used) == len(t):
+            return plan
+        m = {c: i for i, c in enumerate(used)}
+        sub = HostColumns(t[c] for c in used)
+        if hasattr(t, "u32_exact"):
+            sub.u32_exact = t.u32_exact
+        out = dict(plan, table=sub, select=[m[int(c)] for c in plan["select"]])
+        if "where" in plan:
+            out["where"] = [(m[int(p[0])],) + tuple(p[1:]) for p in plan["where"]]
+        if "g_cols" in plan:
+            out["g_cols"] = [m[int(g)] for g in plan["g_cols"]]
+        if "g_col" in plan:
+            out["g_col"] = m[int(plan["g_col"])]
+        if not grouped and not plan.get("global") and "orderby" in plan:
+            out["orderby"] = [(m[int(k)], d) for k, d in plan["orderby"]]
+        return out
 
     def _dispatch(self, val_dic):
         t1 = val_dic["table"]

@@ -16,6 +16,8 @@ error messages are the reference's.  Differences, all invisible in query results
   single homogeneous array cannot hold (README.md:8 blames the Futhark compiler).  ``get_data()`` is still the
   homogeneous 2-D array the reference would have built (``df.to_numpy()``, table.py:9).
 * ``pyarrow.Table`` objects and ``.parquet`` files load column by column.
+* a ``dict`` of 1-D arrays (name -> column) is taken as it is, WITHOUT a copy: the columns may live in pinned host memory
+  (``hark_host_alloc``), and a query over such a non-resident table uploads only the columns it names.
 """
 
 import numpy as np
@@ -75,6 +77,8 @@ def _is_arrow(obj):
 
 def source_columns(table):
     """Per-column host arrays of a source that has them (DataFrame, csv, Arrow, parquet), else None."""
+    if isinstance(table, dict):
+        return [np.asarray(c) for c in table.values()]
     if isinstance(table, pd.DataFrame):
         return [np.ascontiguousarray(table[c].to_numpy()) for c in table.columns]
     if _is_arrow(table):
@@ -88,7 +92,25 @@ def source_columns(table):
     return None
 
 
+class _LazyStack:
+    """Stand-in for the homogeneous 2-D array of a dict-of-columns table: built only if somebody asks for it."""
+
+    def __init__(self, cols):
+        self._cols = cols
+        self.ndim = 2
+        self.shape = (len(cols[0]) if cols else 0, len(cols))
+
+    def __array__(self, dtype=None, copy=None):
+        a = np.column_stack(self._cols) if self._cols else np.zeros((0, 0))
+        return a.astype(dtype) if dtype is not None else a
+
+
 def load_table(table_name, table):
+    if isinstance(table, dict):
+        cols = [np.asarray(c) for c in table.values()]
+        if any(c.ndim != 1 or len(c) != len(cols[0]) for c in cols):
+            raise Exception("a dict table needs 1-D columns of one length")
+        return _LazyStack(cols), list(table.keys())
     if isinstance(table, pd.DataFrame):
         return load_df(table)
     elif isinstance(table, np.ndarray):
@@ -129,7 +151,8 @@ class Table:
     def __init__(self, table_name, file_name):
         self._table_name = table_name
         table, headers = load_table(table_name, file_name)
-        table = np.asarray(table)
+        if not isinstance(table, _LazyStack):
+            table = np.asarray(table)
         if table.ndim != 2:
             raise Exception("Table data must be two-dimensional")
         self._schema = list(headers)
@@ -138,7 +161,7 @@ class Table:
         # one dtype per column when the source has them and they differ (else the homogeneous array is the table)
         self._columns = None
         cols = source_columns(file_name)
-        if cols is not None and len(cols) == table.shape[1] and len({c.dtype for c in cols}) > 1:
+        if cols is not None and len(cols) == table.shape[1] and (len({c.dtype for c in cols}) > 1 or isinstance(file_name, dict)):
             for c, h in zip(cols, self._schema):
                 if c.dtype.kind not in "iubf":
                     raise Exception(f"column {h} has dtype {c.dtype}; tables are numeric")
@@ -148,6 +171,8 @@ class Table:
         return self._schema
 
     def get_data(self):
+        if isinstance(self._data, _LazyStack):
+            self._data = np.asarray(self._data)
         return self._data
 
     def get_name(self):

@@ -102,5 +102,26 @@ def test_sharded_env_end_to_end_on_the_available_ranks():
     """world 1 under plain pytest; all GPUs under `torchrun -m pytest tests/test_gpu_sharded.py -m gpu`."""
     from tests import test_sharded_gloo as G
     senv = _sharded_env()
-    for name in ("filter", "groupby", "groupby_multi", "groupby_pinned", "orderby", "join", "sql", "sql_join"):
+    for name in ("filter", "groupby", "groupby_dense", "groupby_multi", "groupby_pinned", "orderby", "join", "sql", "sql_join"):
         getattr(G, "_scn_" + name)(senv)
+
+
+@pytest.mark.parametrize("peer", ["1", "0"])
+def test_two_ranks_when_two_gpus_are_visible(peer):
+    """Multi-rank parity where the driver can see it: with >= 2 devices and no torchrun around this session, spawn
+    `torch.distributed.run --nproc-per-node 2` over the end-to-end scenario test above — once with the K8c peer-memory
+    exchange, once with HARK_PEER=0 (K8b partition + NCCL all-to-all)."""
+    need_gpu()
+    import subprocess
+    import sys
+    import torch
+    if "RANK" in os.environ:
+        pytest.skip("already running under torchrun")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, HARK_PEER=peer, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29541" if peer == "1" else "29542", "-m", "pytest", "tests/test_gpu_sharded.py", "-m", "gpu", "-q", "-x",
+                        "-p", "no:cacheprovider", "-k", "end_to_end"], cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-2000:])

@@ -42,6 +42,19 @@ def test_oracle_matches_sqlite(idx):
     _check_case(fc, GOLDEN["cases"][idx])
 
 
+def test_oracle_matches_sqlite_non_resident_column_tables():
+    """Tables given as dicts of columns and NOT resident: every statement uploads only the columns it names
+    (FutharkContext._pruned) and must still answer like sqlite."""
+    from harkdb_b200.sharded import ShardedFutharkContext
+    from tests.oracle_engine import OracleEngine
+    fc = ShardedFutharkContext(engine=OracleEngine())
+    fc.resident = False
+    for name, df in _frames().items():
+        fc.create_table(name, {c: df[c].to_numpy() for c in df.columns})
+    for case in GOLDEN["cases"]:
+        _check_case(fc, case)
+
+
 @pytest.mark.gpu
 def test_cuda_path_matches_sqlite():
     from tests.gpu_util import need_gpu
@@ -58,6 +71,12 @@ def test_cuda_path_matches_sqlite():
         fc2.create_table(name, df)
     for case in GOLDEN["cases"]:
         _check_case(fc2, case)
+    # dict-of-columns tables, not resident: only the columns a statement names cross PCIe
+    fc3 = FutharkContext(resident=False)
+    for name, df in _frames().items():
+        fc3.create_table(name, {c: df[c].to_numpy() for c in df.columns})
+    for case in GOLDEN["cases"]:
+        _check_case(fc3, case)
 
 
 def test_vectors_are_current():
