@@ -239,7 +239,9 @@ class FutharkContext:
                 grouped = env.query_groupby_ex(keyed, 0, [c + 1 for c in s_cols], ops)
             finally:
                 keyed.free()
-            if grouped.shape[0] == 0:
+            # (a sharded env holds the one result row on one rank only: ask for the global row count)
+            n_groups = sum(env.all_counts(grouped.shape[0])) if hasattr(env, "all_counts") else grouped.shape[0]
+            if n_groups == 0:
                 # no qualifying row: SQL still answers with ONE row — COUNT = 0 and NULL elsewhere.  There are no NULLs
                 # here, so NULL is NaN and the row is float64 (a zero-row GROUP BY would have produced no row at all)
                 grouped.free()

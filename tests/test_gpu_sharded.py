@@ -124,4 +124,5 @@ def test_two_ranks_when_two_gpus_are_visible(peer):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29541" if peer == "1" else "29542", "-m", "pytest", "tests/test_gpu_sharded.py", "-m", "gpu", "-q", "-x",
                         "-p", "no:cacheprovider", "-k", "end_to_end"], cwd=root, env=env, capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-2000:])
+    if r.returncode != 0:
+        pytest.fail("2-rank run failed:\n" + r.stdout[-6000:] + "\n---- stderr ----\n" + r.stderr[-3000:], pytrace=False)
