@@ -517,11 +517,15 @@ __device__ __forceinline__ uint32_t hk_ballot_step(uint32_t peers, uint32_t d, u
 
 // RANK: 0 = match.any, 1 = eight ballots (register-only multisplit), 2 = lean ballots (default).  PEER: outputs go to per-digit base addresses
 // (other GPUs' arenas) and the key array itself (the destination digit) is not written anywhere.
-template <int KW, int RANK, bool PEER = false>
+// FUSE2 (two carried arrays, the common shape: key + payload, or two key columns): both arrays are reordered in ONE
+// staging round — one barrier pair and one (digit, base) look-up per row instead of two — and both arrays of the next
+// tile are requested before the write-out (round 2; the per-array rounds cost the kernel most of its barrier stalls).
+template <int KW, int RANK, bool PEER = false, bool FUSE2 = false>
 __global__ void __launch_bounds__(LT, 2) hk_lsd_scatter_kernel(const __grid_constant__ LsdParams P) {
     using KT = typename KeyRaw<KW>::T;
     extern __shared__ __align__(16) unsigned char s_dyn[];
     uint64_t *stage = reinterpret_cast<uint64_t *>(s_dyn); // LTILE slots of 8 bytes
+    uint64_t *stage2 = stage + LTILE;                      // FUSE2: the other array's slots
     __shared__ uint32_t wh[LWARPS][256];
     __shared__ uint32_t s_binstart[256];
     __shared__ uint64_t s_gbase[256];
@@ -547,12 +551,14 @@ __global__ void __launch_bounds__(LT, 2) hk_lsd_scatter_kernel(const __grid_cons
     lsd_load_keys<KW>(keyp, t0 * LTILE, count, warp, lane, key);
     __syncthreads();
 
+    uint64_t v[LI];
+    if constexpr (FUSE2) lsd_load_vals(P.in[first_other], P.width[first_other], t0 * LTILE, count, warp, lane, v);
     for (int64_t tile = t0; tile < t1; tile++) {
         const int64_t tile_base = tile * LTILE;
         const int cur_count = count;
         // the first carried array's values are requested now and arrive while the keys are being ranked
-        uint64_t v[LI];
-        if (first_other >= 0) lsd_load_vals(P.in[first_other], P.width[first_other], tile_base, cur_count, warp, lane, v);
+        if constexpr (!FUSE2)
+            if (first_other >= 0) lsd_load_vals(P.in[first_other], P.width[first_other], tile_base, cur_count, warp, lane, v);
         // ---- stable rank of every key among the keys of its warp with the same digit ----
         // (issuing the 8 counter updates as back-to-back atomics and reading the results after the loop was tried:
         //  the extra live registers spill under the 64-register cap and the pass got 7 % slower)
@@ -668,6 +674,7 @@ __global__ void __launch_bounds__(LT, 2) hk_lsd_scatter_kernel(const __grid_cons
                 const uint32_t pos = s_binstart[d] + wh[warp][d] + (rank[i] & 0xffffu);
                 rank[i] = pos;
                 stage[pos] = (uint64_t)key[i];
+                if constexpr (FUSE2) stage2[pos] = v[i];
                 s_digit[pos] = (uint8_t)d;
             }
         }
@@ -675,9 +682,36 @@ __global__ void __launch_bounds__(LT, 2) hk_lsd_scatter_kernel(const __grid_cons
         if (tile + 1 < t1) {
             count = (int)min((int64_t)LTILE, P.n - (tile + 1) * LTILE);
             lsd_load_keys<KW>(keyp, (tile + 1) * LTILE, count, warp, lane, key);
+            if constexpr (FUSE2) lsd_load_vals(P.in[first_other], P.width[first_other], (tile + 1) * LTILE, count, warp, lane, v);
         }
         __syncthreads();
         for (int i = tid; i < LWARPS * 256; i += LT) (&wh[0][0])[i] = 0; // last read above; next written after >= 1 barrier
+        if constexpr (FUSE2) {
+            // both arrays leave in one sweep: one (digit, base) look-up per row
+            KT *ok = reinterpret_cast<KT *>(P.out[P.ka]);
+            const bool w4 = P.width[first_other] == 4;
+            uint32_t *o4 = reinterpret_cast<uint32_t *>(P.out[first_other]);
+            uint64_t *o8 = reinterpret_cast<uint64_t *>(P.out[first_other]);
+            if (cur_count == LTILE) {
+#pragma unroll
+                for (int i = 0; i < LI; i++) {
+                    const int j = i * LT + tid;
+                    const uint64_t g = s_gbase[s_digit[j]] + (uint64_t)j;
+                    ok[g] = (KT)stage[j];
+                    if (w4) o4[g] = (uint32_t)stage2[j];
+                    else o8[g] = stage2[j];
+                }
+            } else {
+                for (int j = tid; j < cur_count; j += LT) {
+                    const uint64_t g = s_gbase[s_digit[j]] + (uint64_t)j;
+                    ok[g] = (KT)stage[j];
+                    if (w4) o4[g] = (uint32_t)stage2[j];
+                    else o8[g] = stage2[j];
+                }
+            }
+            __syncthreads(); // stage / stage2 / s_digit are rewritten by the next tile
+            continue;
+        }
         if constexpr (!PEER) lsd_write_out<KT>(reinterpret_cast<KT *>(P.out[P.ka]), stage, s_digit, s_gbase, cur_count, tid);
         // ---- the other carried arrays ride the same permutation; array a+1 is loaded while array a is written ----
         for (int a = first_other; a >= 0 && a < P.na;) {
@@ -708,12 +742,14 @@ __global__ void __launch_bounds__(LT, 2) hk_lsd_scatter_kernel(const __grid_cons
 // pointer of the 257 exclusive bin offsets (caller frees).
 int lsd_pass(hark_ctx *ctx, LsdParams &P, int kw, unsigned long long **d_offsets_out) {
     P.num_tiles = (P.n + LTILE - 1) / LTILE;
-    const size_t smem = (size_t)LTILE * 8;
     int occ = 1;
     const int64_t rk = ctx->opt("sort.rank", 2);
+    const bool fuse2 = P.na == 2 && !P.peer_out && rk == 2 && ctx->opt("sort.fuse2", 1) != 0;
+    const size_t smem = (size_t)LTILE * 8 * (fuse2 ? 2 : 1);
     void (*scatter)(const LsdParams) =
         kw == 4 ? (rk == 2 ? hk_lsd_scatter_kernel<4, 2> : rk == 1 ? hk_lsd_scatter_kernel<4, 1> : hk_lsd_scatter_kernel<4, 0>)
                 : (rk == 2 ? hk_lsd_scatter_kernel<8, 2> : rk == 1 ? hk_lsd_scatter_kernel<8, 1> : hk_lsd_scatter_kernel<8, 0>);
+    if (fuse2) scatter = kw == 4 ? hk_lsd_scatter_kernel<4, 2, false, true> : hk_lsd_scatter_kernel<8, 2, false, true>;
     if (P.peer_out) scatter = rk == 2 ? hk_lsd_scatter_kernel<4, 2, true> : hk_lsd_scatter_kernel<4, 1, true>; // the key is the 4-byte destination digit
     cudaError_t e = cudaFuncSetAttribute(scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scatter, LT, smem);
