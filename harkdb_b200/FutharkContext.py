@@ -76,18 +76,30 @@ class FutharkContext:
         return self.FutEnv.to_device(t, entry_dtype(np.asarray(t))), True
 
     def _finish(self, res, limit=None):
-        """Result table (consumed) -> ndarray.  LIMIT is applied on the device, so only `limit` rows cross PCIe."""
+        """Result table (consumed) -> ndarray.  LIMIT is applied on the device, so only `limit` rows cross PCIe.
+        Under sql(..., device=True) the (LIMITed) result stays on the device and its handle is returned instead."""
         env = self.FutEnv
         if limit is not None and limit > 0 and hasattr(env, "slice") and isinstance(res, DeviceTable) and res.shape[0] > limit:
             head = env.slice(res, 0, int(limit))
             res.free()
             res = head
+        if getattr(self, "_want_device", False) and (limit is None or not hasattr(res, "shape") or res.shape[0] <= limit):
+            return res
         out = env.from_futhark(res)
         res.free()
         return out if limit is None else out[:limit]
 
-    def sql(self, sql_statement):
-        """sql_parse(tables, sql_statement) -> plan -> libhark entries -> 2-D ndarray."""
+    def sql(self, sql_statement, device=False):
+        """sql_parse(tables, sql_statement) -> plan -> libhark entries -> 2-D ndarray (the reference's return type).
+        device=True keeps the result resident: a DeviceTable (column handles, `.columns()`, `.to_numpy()`, `.free()`) that
+        can be registered again with create_table-free chaining (`FutEnv` entries take it directly) — nothing crosses PCIe."""
+        self._want_device = bool(device)
+        try:
+            return self._sql(sql_statement)
+        finally:
+            self._want_device = False
+
+    def _sql(self, sql_statement):
         val_dic = sql_parse(self.tables, sql_statement)
         if isinstance(val_dic["table"], HostColumns) and "join" not in val_dic:
             # not resident and one dtype per column: upload for this query — and only the columns the statement names

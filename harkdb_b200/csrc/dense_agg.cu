@@ -656,6 +656,57 @@ __device__ __forceinline__ void dagg_segments(const DAggParams &P, uint32_t *tab
             }
         }
         uint32_t idx[U];
+        if constexpr (MODE == 2) {
+            // hash probes: the FIRST probe of every row is issued before any is looked at (U independent loads in
+            // flight, like the lookup mode); only rows whose first entry holds another key walk on
+            if constexpr (KW == 4) {
+                const uint2 *ht = reinterpret_cast<const uint2 *>(P.htab);
+                uint64_t h[U];
+                uint2 e0[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    h[u] = hk_hash_key<4>(k[u]) & P.hmask;
+                    e0[u] = make_uint2(0u, 0u);
+                    if ((okm >> u) & 1u) e0[u] = __ldg(ht + h[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    idx[u] = 0xffffffffu;
+                    if ((okm >> u) & 1u) {
+                        uint2 e = e0[u];
+                        uint64_t hh = h[u];
+                        while (e.y != 0u && e.x != k[u]) {
+                            hh = (hh + 1) & P.hmask;
+                            e = __ldg(ht + hh);
+                        }
+                        if (e.y != 0u) idx[u] = e.y - 1u;
+                    }
+                }
+            } else {
+                const ulonglong2 *ht = reinterpret_cast<const ulonglong2 *>(P.htab);
+                uint64_t h[U];
+                ulonglong2 e0[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    h[u] = hk_hash_key<8>(k[u]) & P.hmask;
+                    e0[u] = make_ulonglong2(0ull, 0ull);
+                    if ((okm >> u) & 1u) e0[u] = __ldg(ht + h[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    idx[u] = 0xffffffffu;
+                    if ((okm >> u) & 1u) {
+                        ulonglong2 e = e0[u];
+                        uint64_t hh = h[u];
+                        while ((uint32_t)e.y != 0u && e.x != k[u]) {
+                            hh = (hh + 1) & P.hmask;
+                            e = __ldg(ht + hh);
+                        }
+                        if ((uint32_t)e.y != 0u) idx[u] = (uint32_t)e.y - 1u;
+                    }
+                }
+            }
+        } else {
 #pragma unroll
         for (int u = 0; u < U; u++) {
             idx[u] = 0xffffffffu;
@@ -665,14 +716,13 @@ __device__ __forceinline__ void dagg_segments(const DAggParams &P, uint32_t *tab
                     if constexpr (KW == 4) v = (P.key_dtype == HARK_U32 ? (long long)(uint32_t)k[u] : (long long)(int32_t)k[u]) - P.pk_min;
                     else v = (long long)k[u] - P.pk_min;
                     if (v >= 0 && v < P.pk_span) idx[u] = __ldg(P.lut + v) - 1u;
-                } else if constexpr (MODE == 2) {
-                    idx[u] = hash_probe<KW>(P.htab, P.hmask, k[u]);
                 } else if constexpr (KW == 4) {
                     idx[u] = hk_ordkey32(k[u], P.key_dtype) - slot0;
                 } else {
                     idx[u] = (uint32_t)(hk_ordkey64(k[u], P.key_dtype) - slot0_64);
                 }
             }
+        }
         }
         if constexpr (SPEC == SPEC_GENERIC) {
 #pragma unroll

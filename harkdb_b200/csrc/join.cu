@@ -170,6 +170,40 @@ __global__ void __launch_bounds__(256) hk_hash_build_kernel(const void *pk, cons
     }
 }
 
+// The same build over K8t's output (dimension rows [pk, g] sorted by hash-table SLICE inside every tile): all warps walk
+// slice 0 of every tile, then slice 1, ... so the compare-and-swaps of a slice land while it is L2-resident instead of
+// being 10^8 random atomics over a table of gigabytes.  4-byte keys, 4-byte group column, group-slot payload.
+__global__ void __launch_bounds__(256) hk_hash_build_tiles_kernel(const uint32_t *__restrict__ rows, const uint32_t *__restrict__ dir,
+                                                                   long long num_tiles, int nbins, int g_dtype, unsigned long long g_lo,
+                                                                   void *htab, unsigned long long hmask, unsigned int *dup_flag) {
+    unsigned long long *t = reinterpret_cast<unsigned long long *>(htab);
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (int b = 0; b < nbins; b++) {
+        for (long long u = warp0; u < num_tiles; u += nwarps) {
+            const uint32_t w = __ldg(dir + (size_t)u * nbins + b);
+            const uint32_t s = w & 0xffffu, e = w >> 16;
+            for (uint32_t r = s + lane; r < e; r += 32) {
+                const uint2 row = __ldcs(reinterpret_cast<const uint2 *>(rows) + (size_t)u * HK_TPART_TILE + r);
+                const uint32_t key = row.x;
+                const uint32_t pay1 = (uint32_t)((unsigned long long)hk_ordkey32(row.y, g_dtype) - g_lo) + 1u;
+                const unsigned long long packed = (unsigned long long)key | ((unsigned long long)pay1 << 32);
+                unsigned long long h = hk_hash_key<4>(key) & hmask;
+                while (true) {
+                    const unsigned long long old = atomicCAS(t + h, 0ull, packed);
+                    if (old == 0ull) break;
+                    if ((uint32_t)old == key) {
+                        *dup_flag = 1u;
+                        break;
+                    }
+                    h = (h + 1) & hmask;
+                }
+            }
+        }
+    }
+}
+
 // 8-byte keys: every row must be the first entry with its key on its probe sequence
 __global__ void __launch_bounds__(256) hk_hash_verify_kernel(const void *pk, int64_t n_dim, const void *htab, unsigned long long hmask,
                                                               unsigned int *dup_flag) {
@@ -473,26 +507,34 @@ __global__ void __launch_bounds__(256) hk_hj_build_kernel(const void *key_col, i
     }
 }
 
-// visits the build rows matching `key`; F(row) for each
+// entry type of the multiset table and its first-probe load: the first probes of a thread's rows are all issued before
+// any of them is examined (independent loads in flight), only collisions walk on
+template <int KW> struct HjEntry;
+template <> struct HjEntry<4> { using T = uint2; };
+template <> struct HjEntry<8> { using T = ulonglong2; };
+
+template <int KW>
+__device__ __forceinline__ typename HjEntry<KW>::T hj_first(const void *htab, unsigned long long hmask, typename JRaw<KW>::T key,
+                                                            unsigned long long *h) {
+    *h = hk_hash_key<KW>(key) & hmask;
+    return __ldg(reinterpret_cast<const typename HjEntry<KW>::T *>(htab) + *h);
+}
+
+// visits the build rows matching `key`, starting from the preloaded first entry; F(row) for each
 template <int KW, typename F>
-__device__ __forceinline__ void hj_for_matches(const void *htab, unsigned long long hmask, typename JRaw<KW>::T key, F f) {
-    unsigned long long h = hk_hash_key<KW>(key) & hmask;
-    if constexpr (KW == 4) {
-        const uint2 *t = reinterpret_cast<const uint2 *>(htab);
-        while (true) {
-            const uint2 e = __ldg(t + h);
+__device__ __forceinline__ void hj_for_matches(const void *htab, unsigned long long hmask, typename JRaw<KW>::T key,
+                                               typename HjEntry<KW>::T e, unsigned long long h, F f) {
+    const typename HjEntry<KW>::T *t = reinterpret_cast<const typename HjEntry<KW>::T *>(htab);
+    while (true) {
+        if constexpr (KW == 4) {
             if (e.y == 0u) return;
             if (e.x == key) f((int64_t)e.y - 1);
-            h = (h + 1) & hmask;
-        }
-    } else {
-        const ulonglong2 *t = reinterpret_cast<const ulonglong2 *>(htab);
-        while (true) {
-            const ulonglong2 e = __ldg(t + h);
+        } else {
             if ((uint32_t)e.y == 0u) return;
             if (e.x == key) f((int64_t)(uint32_t)e.y - 1);
-            h = (h + 1) & hmask;
         }
+        h = (h + 1) & hmask;
+        e = __ldg(t + h);
     }
 }
 
@@ -521,10 +563,20 @@ __global__ void __launch_bounds__(HJ_T) hk_hj_count_kernel(const __grid_constant
         if (tile >= P.num_tiles) break;
         const int64_t i0 = tile * HJ_TILE;
         unsigned long long mine = 0;
+        KT key[HJ_I];
+        typename HjEntry<KW>::T e0[HJ_I];
+        unsigned long long h0[HJ_I];
 #pragma unroll
         for (int e = 0; e < HJ_I; e++) {
             const int64_t i = i0 + e * HJ_T + threadIdx.x;
-            if (i < P.n1) hj_for_matches<KW>(P.htab, P.hmask, k1[i], [&](int64_t) { mine++; });
+            key[e] = i < P.n1 ? k1[i] : (KT)0;
+        }
+#pragma unroll
+        for (int e = 0; e < HJ_I; e++) e0[e] = hj_first<KW>(P.htab, P.hmask, key[e], &h0[e]);
+#pragma unroll
+        for (int e = 0; e < HJ_I; e++) {
+            const int64_t i = i0 + e * HJ_T + threadIdx.x;
+            if (i < P.n1) hj_for_matches<KW>(P.htab, P.hmask, key[e], e0[e], h0[e], [&](int64_t) { mine++; });
         }
         unsigned long long total;
         mj_block_excl_scan(mine, s_w, &total);
@@ -544,29 +596,47 @@ __global__ void __launch_bounds__(HJ_T) hk_hj_expand_kernel(const __grid_constan
     using KT = typename JRaw<KW>::T;
     __shared__ unsigned long long s_w[HJ_T / 32];
     const KT *k1 = reinterpret_cast<const KT *>(P.k1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int64_t tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
-        const int64_t i0 = tile * HJ_TILE;
-        // thread-contiguous rows so that the result is grouped by probe row in row order
+        // a warp owns 128 consecutive probe rows, striped over its lanes (row = warp range + e * 32 + lane): loads and —
+        // with one match per row — stores coalesce, and the result stays grouped by probe row in row order
+        const int64_t i0 = tile * HJ_TILE + (int64_t)warp * (32 * HJ_I);
         KT key[HJ_I];
-        unsigned long long cnt[HJ_I], mine = 0;
+        typename HjEntry<KW>::T e0[HJ_I];
+        unsigned long long h0[HJ_I];
+        unsigned long long cnt[HJ_I], off[HJ_I], wsum = 0;
 #pragma unroll
         for (int e = 0; e < HJ_I; e++) {
-            const int64_t i = i0 + (int64_t)threadIdx.x * HJ_I + e;
-            cnt[e] = 0;
-            key[e] = 0;
-            if (i < P.n1) {
-                key[e] = k1[i];
-                hj_for_matches<KW>(P.htab, P.hmask, key[e], [&](int64_t) { cnt[e]++; });
-            }
-            mine += cnt[e];
+            const int64_t i = i0 + e * 32 + lane;
+            key[e] = i < P.n1 ? k1[i] : (KT)0;
         }
-        unsigned long long total;
-        unsigned long long run = P.tile_base[tile] + mj_block_excl_scan(mine, s_w, &total);
+#pragma unroll
+        for (int e = 0; e < HJ_I; e++) e0[e] = hj_first<KW>(P.htab, P.hmask, key[e], &h0[e]);
 #pragma unroll
         for (int e = 0; e < HJ_I; e++) {
-            const int64_t i = i0 + (int64_t)threadIdx.x * HJ_I + e;
+            const int64_t i = i0 + e * 32 + lane;
+            cnt[e] = 0;
+            if (i < P.n1) hj_for_matches<KW>(P.htab, P.hmask, key[e], e0[e], h0[e], [&](int64_t) { cnt[e]++; });
+            unsigned long long inc = cnt[e]; // inclusive warp scan in lane order
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long t = __shfl_up_sync(HK_FULL_MASK, inc, o);
+                if (lane >= o) inc += t;
+            }
+            off[e] = wsum + inc - cnt[e];
+            wsum += __shfl_sync(HK_FULL_MASK, inc, 31);
+        }
+        if (lane == 0) s_w[warp] = wsum;
+        __syncthreads();
+        unsigned long long wbase = P.tile_base[tile];
+        for (int w = 0; w < warp; w++) wbase += s_w[w];
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < HJ_I; e++) {
+            const int64_t i = i0 + e * 32 + lane;
             if (i < P.n1 && cnt[e]) {
-                hj_for_matches<KW>(P.htab, P.hmask, key[e], [&](int64_t r2) {
+                unsigned long long run = wbase + off[e];
+                hj_for_matches<KW>(P.htab, P.hmask, key[e], e0[e], h0[e], [&](int64_t r2) {
                     join_emit(P.C, (int64_t)run, i, r2);
                     run++;
                 });
@@ -783,7 +853,28 @@ int build_hash_table(hark_ctx *ctx, Bufs &bufs, const hark_table *dim, int32_t p
     HK_CUDA(ctx, cudaMemsetAsync(dup, 0, sizeof(unsigned int), ctx->stream));
     const void *pk = dim->cols[pk_col].ptr, *g = dim->cols[g_col].ptr;
     const int g_dtype = dim->cols[g_col].dtype;
-    if (kw == 4) {
+    const int64_t slice_bytes = ctx->opt("join.lut_slice_bytes", 16ll << 20);
+    if (kw == 4 && !payload_row && hk_dtype_size(g_dtype) == 4 && (int64_t)(H * esz) > slice_bytes * 3 / 2 && nd >= ctx->opt("join.build_partition_min_rows", 1 << 16) &&
+        ctx->opt("join.build_partition", 1) != 0) {
+        // a table much larger than L2: bring the dimension rows into table-slice order first (K8t), then build slice by slice
+        hk_part_spec ps;
+        ps.dtype = dim->cols[pk_col].dtype;
+        ps.base = 0;
+        ps.span = 0;
+        ps.shift = 0;
+        while (((uint64_t)slice_bytes / esz) >> (ps.shift + 1)) ps.shift++;
+        while (((H - 1) >> ps.shift) + 1 > 256) ps.shift++;
+        ps.nbins = (int)(((H - 1) >> ps.shift) + 1);
+        hk_tpart tp;
+        const void *gv[1] = {g};
+        HK_TRY(hk_tile_partition(ctx, nd, pk, 4, ps, H - 1, 1, gv, &tp));
+        bufs.adopt(tp.rows);
+        bufs.adopt(tp.dir);
+        hk_hash_build_tiles_kernel<<<(unsigned)ctx->num_sms * 8, 256, 0, ctx->stream>>>(tp.rows, tp.dir, tp.num_tiles, tp.nbins, g_dtype, g_lo,
+                                                                                      tab, H - 1, dup);
+        HK_CHECK_LAUNCH(ctx);
+        ctx->count_launch();
+    } else if (kw == 4) {
         hk_hash_build_kernel<4><<<grid_for(ctx, nd), 256, 0, ctx->stream>>>(pk, g, g_dtype, nd, g_lo, payload_row, tab, H - 1, dup);
         HK_CHECK_LAUNCH(ctx);
         ctx->count_launch();

@@ -738,6 +738,276 @@ __global__ void __launch_bounds__(LT, 2) hk_lsd_scatter_kernel(const __grid_cons
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K3b — "sweep16": the LSD pass for the 16-byte row shape (two 8-byte carried arrays: config 4's ORDER BY col1, col2).
+//
+// Between passes the rows live ARRAY-OF-STRUCTS ({a, b} = 16 bytes, 16-byte aligned), so after the tile-local reorder
+// every digit's run in the stage is one contiguous, 16-byte aligned block whose destination is 16-byte aligned too —
+// and a run leaves the SM as ONE TMA bulk copy (cp.async.bulk shared -> global, SASS UBLKCP) issued by the thread that
+// owns the digit: 256 copies per 4096-row tile instead of 2 x 4096 look-up + store sequences.  A microbenchmark of
+// exactly this pattern (tools/micro/bulk_small.cu, profiles/r02_micro_tma_small_bulk_copies.txt) sustains 5.9 TB/s with
+// 256-byte runs.  With the write-out gone from the instruction stream the chunk histogram pre-pass goes too: tiles are
+// claimed in order from a ticket counter and find their base with a decoupled look-back per (tile, digit) over
+// status words (tag | flag | count) against the GLOBAL digit histograms, which are order-independent and therefore
+// computed once, up front, for all passes (one read of each key column).  The first pass reads the caller's SoA
+// columns, the last one writes SoA again (per-row stores), so nothing outside this file sees the AoS form.
+// Stability: tickets ascend with the input order, rows are warp-striped and ranked with ballots.
+// ------------------------------------------------------------------------------------------------
+struct SweepParams {
+    DigitFn f;
+    int kf;                 // which field of the row carries this pass's key: 0 = a, 1 = b
+    const uint64_t *a_in, *b_in; // FIRST: the two SoA inputs
+    const ulonglong2 *rows_in;   // !FIRST
+    uint64_t *a_out, *b_out;     // LAST: SoA outputs
+    ulonglong2 *rows_out;        // !LAST
+    int64_t n;
+    int64_t num_tiles;
+    uint64_t *status;            // [num_tiles][256]                                   (look-back protocol)
+    unsigned long long *ticket;
+    const unsigned long long *pass_offsets; // [256] exclusive global digit offsets of this pass
+    uint32_t tag;
+    int64_t tiles_per_chunk;     // chunk protocol (default): CTA c owns tiles [c * tiles_per_chunk, ...)
+    uint32_t *chunk_counts;      // [num_chunks][256]
+    const unsigned long long *chunk_base; // [num_chunks][256] global row where the chunk's rows of each digit start
+};
+
+// chunk histogram of one pass over SoA (FIRST) or AoS rows: the counterpart of hk_lsd_hist_kernel
+template <bool FIRST>
+__global__ void __launch_bounds__(1024) hk_sweep16_hist_kernel(const __grid_constant__ SweepParams P) {
+    __shared__ uint32_t sh[256];
+    if (threadIdx.x < 256) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t r0 = (int64_t)blockIdx.x * P.tiles_per_chunk * LTILE;
+    const int64_t r1 = min(P.n, r0 + P.tiles_per_chunk * LTILE);
+    if constexpr (FIRST) {
+        const uint64_t *p = P.kf == 0 ? P.a_in : P.b_in;
+        const int64_t nvec = r1 > r0 ? (r1 - r0) / 2 : 0; // r0 is a multiple of LTILE: 16-byte aligned
+        const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(p + r0);
+#pragma unroll 4
+        for (int64_t i = threadIdx.x; i < nvec; i += 1024) {
+            const ulonglong2 v = __ldg(q + i);
+            atomicAdd(&sh[digit_of<8>(v.x, P.f) & 0xffu], 1u);
+            atomicAdd(&sh[digit_of<8>(v.y, P.f) & 0xffu], 1u);
+        }
+        if (r1 > r0 && ((r1 - r0) & 1) && threadIdx.x == 0) atomicAdd(&sh[digit_of<8>(p[r1 - 1], P.f) & 0xffu], 1u);
+    } else {
+#pragma unroll 4
+        for (int64_t i = r0 + threadIdx.x; i < r1; i += 1024) {
+            const ulonglong2 v = __ldg(P.rows_in + i);
+            atomicAdd(&sh[digit_of<8>(P.kf == 0 ? v.x : v.y, P.f) & 0xffu], 1u);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 256) P.chunk_counts[(size_t)blockIdx.x * 256 + threadIdx.x] = sh[threadIdx.x];
+}
+
+__device__ __forceinline__ void sw_bulk_store(void *gdst, const void *ssrc, uint32_t bytes) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(gdst)), "r"(s),
+                 "r"(bytes)
+                 : "memory");
+}
+
+template <bool FIRST>
+__device__ __forceinline__ void sweep16_load(const SweepParams &P, int64_t tile_base, int count, int warp, int lane, uint64_t (&ra)[LI],
+                                             uint64_t (&rb)[LI]) {
+    const bool full = count == LTILE;
+#pragma unroll
+    for (int i = 0; i < LI; i++) {
+        const int idx = warp * (LI * 32) + i * 32 + lane;
+        ra[i] = rb[i] = 0;
+        if (full || idx < count) {
+            if constexpr (FIRST) {
+                ra[i] = __ldcs(P.a_in + tile_base + idx);
+                rb[i] = __ldcs(P.b_in + tile_base + idx);
+            } else {
+                const ulonglong2 r = __ldcs(P.rows_in + tile_base + idx);
+                ra[i] = r.x;
+                rb[i] = r.y;
+            }
+        }
+    }
+}
+
+template <bool FIRST, bool LAST, bool CHUNKED>
+__global__ void __launch_bounds__(LT, 2) hk_sweep16_kernel(const __grid_constant__ SweepParams P) {
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    ulonglong2 *stage = reinterpret_cast<ulonglong2 *>(s_dyn); // LTILE rows of 16 bytes
+    __shared__ uint32_t wh[LWARPS][256];
+    __shared__ uint32_t s_binstart[256];
+    __shared__ uint32_t s_bincount[256];
+    __shared__ uint64_t s_gbase[256];
+    __shared__ uint8_t s_digit[LAST ? LTILE : 1];
+    __shared__ uint32_t s_wtot[8];
+    __shared__ long long s_tile;
+    __shared__ uint64_t s_run[CHUNKED ? 256 : 1]; // chunk protocol: next global row of every digit for this chunk
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (int i = tid; i < LWARPS * 256; i += LT) (&wh[0][0])[i] = 0;
+    int64_t next_tile = (int64_t)blockIdx.x * P.tiles_per_chunk;
+    const int64_t end_tile = min(P.num_tiles, next_tile + P.tiles_per_chunk);
+    if constexpr (CHUNKED)
+        if (tid < 256) s_run[tid] = P.chunk_base[(size_t)blockIdx.x * 256 + tid];
+
+    uint64_t ra[LI], rb[LI];
+    bool prefetched = false;
+    while (true) {
+        if constexpr (!CHUNKED) {
+            if (tid == 0) s_tile = (long long)atomicAdd(P.ticket, 1ull);
+            __syncthreads();
+        }
+        const int64_t tile = CHUNKED ? next_tile++ : (int64_t)s_tile;
+        if (tile >= (CHUNKED ? end_tile : P.num_tiles)) break;
+        const int64_t tile_base = tile * LTILE;
+        const int count = (int)min((int64_t)LTILE, P.n - tile_base);
+        const bool full = count == LTILE;
+
+        // ---- rows, warp-striped: item i of lane l in warp w is tile row w*256 + i*32 + l.  In the chunk protocol the
+        // next tile is known: its rows were requested before the previous tile left (see below) ----
+        if (!CHUNKED || !prefetched) sweep16_load<FIRST>(P, tile_base, count, warp, lane, ra, rb);
+        // ---- digits, then the lean ballot ranking of K3 (stable rank among the warp's rows of the same digit) ----
+        uint32_t dpk[LI / 4];
+#pragma unroll
+        for (int i = 0; i < LI; i++) {
+            const uint32_t d = digit_of<8>(P.kf == 0 ? ra[i] : rb[i], P.f) & 0xffu;
+            if ((i & 3) == 0) dpk[i >> 2] = d;
+            else dpk[i >> 2] |= d << ((i & 3) * 8);
+        }
+        uint32_t rank[LI];
+        uint32_t *whw = &wh[warp][0];
+#pragma unroll
+        for (int i = 0; i < LI; i++) {
+            const int idx = warp * (LI * 32) + i * 32 + lane;
+            const uint32_t d = (dpk[i >> 2] >> ((i & 3) * 8)) & 0xffu;
+            bool valid = true;
+            uint32_t peers = 0xffffffffu;
+            if (!full) {
+                valid = idx < count;
+                peers = __ballot_sync(HK_FULL_MASK, valid);
+                if (!valid) peers = ~peers;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) peers = hk_ballot_step(peers, d, 1u << k);
+            const int leader = 31 - __clz((int)peers);
+            uint32_t old = 0;
+            if (valid && lane == leader) {
+                old = whw[d];
+                whw[d] = old + __popc(peers);
+            }
+            old = __shfl_sync(HK_FULL_MASK, old, leader);
+            rank[i] = (valid ? (d << 16) : 0xffff0000u) | (old + __popc(peers & lt_mask));
+            __syncwarp();
+        }
+        // the bulk copies of this CTA's previous tile must have finished READING the stage before it is overwritten
+        if (!LAST && tid < 256) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncthreads();
+        // ---- thread b owns digit b: warp offsets inside the bin, bin start inside the tile, look-back for the base ----
+        {
+            uint32_t sum = 0;
+            if (tid < 256) {
+#pragma unroll
+                for (int w = 0; w < LWARPS; w++) {
+                    const uint32_t c = wh[w][tid];
+                    wh[w][tid] = sum;
+                    sum += c;
+                }
+            }
+            const uint32_t inc = hk_warp_incl_scan_u32(sum);
+            if (lane == 31 && warp < 8) s_wtot[warp] = inc;
+            __syncthreads();
+            if (tid < 256) {
+                uint32_t woff = 0;
+                for (int w = 0; w < warp; w++) woff += s_wtot[w];
+                const uint32_t binstart = woff + inc - sum;
+                s_binstart[tid] = binstart;
+                s_bincount[tid] = sum;
+                if constexpr (CHUNKED) {
+                    const uint64_t run = s_run[tid];
+                    s_gbase[tid] = run;
+                    s_run[tid] = run + sum;
+                } else {
+                uint64_t *my = P.status + (size_t)tile * 256 + tid;
+                uint64_t excl = 0;
+                if (tile == 0) {
+                    hk_st_relaxed_u64(my, sw_make(P.tag, 2, sum));
+                } else {
+                    hk_st_relaxed_u64(my, sw_make(P.tag, 1, sum));
+                    int64_t t = tile - 1;
+                    while (true) {
+                        uint64_t v;
+                        do {
+                            v = hk_ld_relaxed_u64(P.status + (size_t)t * 256 + tid);
+                        } while ((uint32_t)(v >> 56) != P.tag || ((v >> 54) & 3) == 0);
+                        excl += v & SW_VAL;
+                        if (((v >> 54) & 3) == 2) break;
+                        t--;
+                    }
+                    hk_st_relaxed_u64(my, sw_make(P.tag, 2, excl + sum));
+                }
+                s_gbase[tid] = (uint64_t)P.pass_offsets[tid] + excl; // global row of this tile's first row of digit b
+                }
+            }
+        }
+        __syncthreads();
+        // ---- tile-local reorder: the row goes to its slot of the stage ----
+#pragma unroll
+        for (int i = 0; i < LI; i++) {
+            const uint32_t d = rank[i] >> 16;
+            if (d < 256u) {
+                const uint32_t pos = s_binstart[d] + wh[warp][d] + (rank[i] & 0xffffu);
+                stage[pos] = make_ulonglong2(ra[i], rb[i]);
+                if constexpr (LAST) s_digit[pos] = (uint8_t)d;
+            }
+        }
+        if constexpr (CHUNKED) { // the row registers are free: request the next tile now
+            prefetched = next_tile < end_tile;
+            if (prefetched)
+                sweep16_load<FIRST>(P, next_tile * LTILE, (int)min((int64_t)LTILE, P.n - next_tile * LTILE), warp, lane, ra, rb);
+        }
+        if constexpr (!LAST) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        for (int i = tid; i < LWARPS * 256; i += LT) (&wh[0][0])[i] = 0; // read above for the last time; rewritten after >= 1 barrier
+        if constexpr (!LAST) {
+            // ---- every digit's run leaves as ONE bulk copy ----
+            if (tid < 256) {
+                const uint32_t c = s_bincount[tid];
+                if (c) { // in pieces of at most 16 KB (a whole tile in one digit is a 64 KB run)
+                    unsigned char *g = reinterpret_cast<unsigned char *>(P.rows_out + s_gbase[tid]);
+                    const unsigned char *sm = reinterpret_cast<const unsigned char *>(stage + s_binstart[tid]);
+                    const uint32_t bytes = c * 16u;
+                    for (uint32_t o = 0; o < bytes; o += 16384u) sw_bulk_store(g + o, sm + o, min(16384u, bytes - o));
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+            if constexpr (CHUNKED) __syncthreads(); // the counters zeroed above are incremented by the next tile's ranking
+        } else {
+            // ---- last pass: back to the caller's SoA columns ----
+            if (full) {
+#pragma unroll
+                for (int i = 0; i < LI; i++) {
+                    const int j = i * LT + tid;
+                    const int d = s_digit[j];
+                    const uint64_t g = s_gbase[d] + (uint64_t)(j - (int)s_binstart[d]);
+                    const ulonglong2 r = stage[j];
+                    P.a_out[g] = r.x;
+                    P.b_out[g] = r.y;
+                }
+            } else {
+                for (int j = tid; j < count; j += LT) {
+                    const int d = s_digit[j];
+                    const uint64_t g = s_gbase[d] + (uint64_t)(j - (int)s_binstart[d]);
+                    const ulonglong2 r = stage[j];
+                    P.a_out[g] = r.x;
+                    P.b_out[g] = r.y;
+                }
+            }
+            __syncthreads(); // the stage is rewritten by the next tile
+        }
+    }
+    if (!LAST && tid < 256) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // shared memory must outlive the copies
+}
+
 // One stable pass over all carried arrays with the chunked protocol.  d_offsets_out (optional) receives the device
 // pointer of the 257 exclusive bin offsets (caller frees).
 int lsd_pass(hark_ctx *ctx, LsdParams &P, int kw, unsigned long long **d_offsets_out) {
@@ -1236,6 +1506,145 @@ int fix_truncated(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec> &
     return HARK_OK;
 }
 
+// All passes of a sort over two 8-byte carried arrays with K3b.  On success arrays[0..1].buf[(npass-1)&1] hold the
+// result (SoA), like the chunked path leaves them.
+int run_sweep16(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec> &keys, std::vector<hk_sort_array> &arrays,
+                const std::vector<Pass> &passes) {
+    const int npass = (int)passes.size();
+    const int fb = (npass - 1) & 1;
+    const int64_t num_tiles = (n + LTILE - 1) / LTILE;
+    struct Scratch {
+        hark_ctx *ctx;
+        std::vector<void *> v;
+        ~Scratch() {
+            for (void *p : v) ctx->dfree(p);
+        }
+        int alloc(void **p, size_t bytes) {
+            int rc = ctx->dalloc(p, bytes);
+            if (rc == HARK_OK) v.push_back(*p);
+            return rc;
+        }
+        void release_now(void *p) {
+            v.erase(std::remove(v.begin(), v.end(), p), v.end());
+            ctx->dfree(p);
+        }
+    } sc{ctx, {}};
+    const bool lookback = ctx->opt("sort.sweep16", 1) == 2; // kept for A/B: look-back serialises the tiles
+    unsigned long long *d_hist = nullptr;
+    uint64_t *d_status = nullptr;
+    const size_t status_words = (size_t)num_tiles * 256;
+    const int64_t want = ctx->opt("sort.ctas_per_sm", 0);
+    const int occ = want > 0 ? (int)std::min<int64_t>(2, want) : 2;
+    const int64_t max_chunks = (int64_t)ctx->num_sms * occ;
+    const int64_t tiles_per_chunk = lookback ? num_tiles : std::max<int64_t>(1, (num_tiles + max_chunks - 1) / max_chunks);
+    const int num_chunks = lookback ? 0 : (int)((num_tiles + tiles_per_chunk - 1) / tiles_per_chunk);
+    uint32_t *d_cc = nullptr;
+    unsigned long long *d_cb = nullptr, *d_off = nullptr;
+    if (lookback) {
+        // ---- global digit histograms of every pass: one read per key column, then one exclusive scan per pass ----
+        HK_TRY(sc.alloc((void **)&d_hist, sizeof(unsigned long long) * 256 * (size_t)npass));
+        HK_CUDA(ctx, cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * 256 * (size_t)npass, ctx->stream));
+        for (int p0 = 0; p0 < npass;) {
+            int p1 = p0;
+            while (p1 < npass && passes[p1].key == passes[p0].key && p1 - p0 < MAXPASS) p1++;
+            HistParams H;
+            memset(&H, 0, sizeof H);
+            H.key = arrays[keys[passes[p0].key].array].in;
+            H.n = n;
+            H.npass = p1 - p0;
+            for (int q = p0; q < p1; q++) H.f[q - p0] = passes[q].f;
+            H.hist = d_hist + (size_t)256 * p0;
+            hk_hist_kernel<8><<<grid_for(ctx, n, 4), 256, 0, ctx->stream>>>(H);
+            HK_CHECK_LAUNCH(ctx);
+            ctx->count_launch();
+            p0 = p1;
+        }
+        hk_hist_scan_kernel<<<npass, 256, 0, ctx->stream>>>(d_hist);
+        HK_CHECK_LAUNCH(ctx);
+        ctx->count_launch();
+        // ---- look-back state (tags tell the passes apart: zeroed once) and one ticket per pass ----
+        HK_TRY(sc.alloc((void **)&d_status, sizeof(uint64_t) * (status_words + (size_t)npass)));
+        HK_CUDA(ctx, cudaMemsetAsync(d_status, 0, sizeof(uint64_t) * (status_words + (size_t)npass), ctx->stream));
+    } else {
+        HK_TRY(sc.alloc((void **)&d_cc, (size_t)num_chunks * 256 * sizeof(uint32_t)));
+        HK_TRY(sc.alloc((void **)&d_cb, (size_t)num_chunks * 256 * sizeof(unsigned long long)));
+        HK_TRY(sc.alloc((void **)&d_off, 257 * sizeof(unsigned long long)));
+    }
+    // ---- AoS ping-pong buffers: pass p < last writes rows[p & 1] ----
+    void *rows[2] = {nullptr, nullptr};
+    if (npass >= 2) HK_TRY(sc.alloc(&rows[0], (size_t)n * 16));
+    if (npass >= 3) HK_TRY(sc.alloc(&rows[1], (size_t)n * 16));
+    const size_t smem = (size_t)LTILE * 16;
+    void (*kerns[2][2][2])(const SweepParams) = {
+        {{hk_sweep16_kernel<false, false, false>, hk_sweep16_kernel<false, false, true>},
+         {hk_sweep16_kernel<false, true, false>, hk_sweep16_kernel<false, true, true>}},
+        {{hk_sweep16_kernel<true, false, false>, hk_sweep16_kernel<true, false, true>},
+         {hk_sweep16_kernel<true, true, false>, hk_sweep16_kernel<true, true, true>}}};
+    for (int a = 0; a < 2; a++)
+        for (int b = 0; b < 2; b++)
+            for (int c = 0; c < 2; c++)
+                HK_CUDA(ctx, cudaFuncSetAttribute(kerns[a][b][c], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = lookback ? (unsigned)std::min<int64_t>(num_tiles, max_chunks) : (unsigned)num_chunks;
+    for (int p = 0; p < npass; p++) {
+        const bool first = p == 0, last = p == npass - 1;
+        SweepParams S;
+        memset(&S, 0, sizeof S);
+        S.f = passes[p].f;
+        S.kf = keys[passes[p].key].array;
+        S.n = n;
+        S.num_tiles = num_tiles;
+        S.tiles_per_chunk = tiles_per_chunk;
+        if (lookback) {
+            S.status = d_status;
+            S.ticket = (unsigned long long *)(d_status + status_words + p);
+            S.pass_offsets = d_hist + (size_t)256 * p;
+            S.tag = (uint32_t)p + 1;
+        } else {
+            S.chunk_counts = d_cc;
+            S.chunk_base = d_cb;
+        }
+        if (first) {
+            S.a_in = (const uint64_t *)arrays[0].in;
+            S.b_in = (const uint64_t *)arrays[1].in;
+        } else {
+            S.rows_in = (const ulonglong2 *)rows[(p - 1) & 1];
+        }
+        if (last) {
+            // the AoS buffer this pass does not read is dead: give it back before the SoA results are allocated
+            if (npass >= 3) {
+                void *dead = rows[p & 1];
+                rows[p & 1] = nullptr;
+                sc.release_now(dead);
+            }
+            for (int a = 0; a < 2; a++)
+                if (!arrays[a].buf[fb]) HK_TRY(ctx->dalloc(&arrays[a].buf[fb], (size_t)n * 8));
+            S.a_out = (uint64_t *)arrays[0].buf[fb];
+            S.b_out = (uint64_t *)arrays[1].buf[fb];
+        } else {
+            S.rows_out = (ulonglong2 *)rows[p & 1];
+        }
+        if (!lookback) {
+            // chunk histogram of this pass over its input (SoA for the first pass, AoS rows after), then the chunk bases
+            if (first) hk_sweep16_hist_kernel<true><<<grid, 1024, 0, ctx->stream>>>(S);
+            else hk_sweep16_hist_kernel<false><<<grid, 1024, 0, ctx->stream>>>(S);
+            HK_CHECK_LAUNCH(ctx);
+            LsdParams L;
+            memset(&L, 0, sizeof L);
+            L.num_chunks = num_chunks;
+            L.chunk_counts = d_cc;
+            L.chunk_base = d_cb;
+            L.offsets = d_off;
+            hk_lsd_scan_kernel<<<1, 1024, 0, ctx->stream>>>(L);
+            HK_CHECK_LAUNCH(ctx);
+            ctx->count_launch(2);
+        }
+        kerns[first ? 1 : 0][last ? 1 : 0][lookback ? 0 : 1]<<<grid, LT, smem, ctx->stream>>>(S);
+        HK_CHECK_LAUNCH(ctx);
+        ctx->count_launch();
+    }
+    return HARK_OK;
+}
+
 } // namespace
 
 // K8c: one stable pass keyed on a u32 destination digit (< HK_PEER_MAX) whose outputs are peer addresses.
@@ -1393,7 +1802,16 @@ int hk_radix_sort(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec> &
         for (int attempt = 0;; attempt++) {
             std::vector<const void *> cur(na);
             for (int a = 0; a < na; a++) cur[a] = arrays[a].in;
-            for (int p = 0; p < npass; p++) {
+            // K3b: two 8-byte carried arrays sort as 16-byte rows with TMA run stores and look-back (see hk_sweep16_kernel)
+            const bool sweep16 = na == 2 && arrays[0].width == 8 && arrays[1].width == 8 && hash_nparts == 0 && npass <= 250 &&
+                                 n >= ctx->opt("sort.sweep16_min_rows", 1 << 16) && ctx->opt("sort.sweep16", 1) != 0;
+            ctx->counters["sort.last_sweep16"] = sweep16 ? 1 : 0;
+            if (sweep16) {
+                if (attempt == 0) ctx->kernel_begin();
+                rc = run_sweep16(ctx, n, keys, arrays, passes);
+                if (rc != HARK_OK) return cleanup_fail(rc, "");
+            }
+            for (int p = 0; p < npass && !sweep16; p++) {
                 const int ob = p & 1;
                 for (int a = 0; a < na && rc == HARK_OK; a++)
                     if (!arrays[a].buf[ob]) rc = ctx->dalloc(&arrays[a].buf[ob], (size_t)n * arrays[a].width);

@@ -403,6 +403,49 @@ def test_sort_by_and_partition_by_hash():
     s.free(); t.free()
 
 
+@pytest.mark.parametrize("n", [1, 2, 4095, 4096, 4097, 8193, 100003, (1 << 20) + 5])
+@pytest.mark.parametrize("shape", ["cfg4", "ties", "one_digit", "f64_desc", "wide_both"])
+def test_orderby_sweep16_rows(n, shape):
+    """K3b (hk_sweep16_kernel: 16-byte rows, look-back, TMA run stores) on every size class and key shape: LSD over
+    several passes is only correct if every pass is stable, so agreement with the oracle on two-key inputs is also the
+    stability proof.  `one_digit`: a whole tile in one digit run (one 64 KB run); `ties`: col1 with few values."""
+    env = get_env()
+    rng = np.random.default_rng(n + len(shape))
+    if shape == "cfg4":
+        cols = [rng.integers(-2 ** 19, 2 ** 19, n).astype(np.int64), rng.integers(-2 ** 63, 2 ** 63 - 1, n).astype(np.int64)]
+        keys, desc = [0, 1], [0, 0]
+    elif shape == "ties":
+        cols = [rng.integers(0, 3, n).astype(np.int64), rng.integers(0, 1000, n).astype(np.int64)]
+        keys, desc = [0, 1], [0, 1]
+    elif shape == "one_digit":
+        cols = [np.full(n, 7, dtype=np.int64), rng.integers(0, 256, n).astype(np.int64) * 65536]
+        keys, desc = [1, 0], [0, 0]
+    elif shape == "f64_desc":
+        f = rng.normal(size=n)
+        f[::37] = np.nan
+        f[1::41] = -0.0
+        cols = [f, rng.integers(-5, 5, n).astype(np.int64)]
+        keys, desc = [1, 0], [1, 0]
+    else:
+        cols = [rng.integers(-2 ** 62, 2 ** 62, n).astype(np.int64), rng.integers(-2 ** 62, 2 ** 62, n).astype(np.int64)]
+        keys, desc = [0, 1], [1, 1]
+    t = env.from_columns(cols)
+    env.set_option("sort.sweep16_min_rows", 1)
+    try:
+        for trunc in (1, 0):
+            env.set_option("sort.trunc", trunc)
+            r = env.query_orderby(t, [0, 1], keys, desc)
+            assert env.get_option("sort.last_passes") == 0 or env.get_option("sort.last_sweep16") == 1
+            exp = NO.query_orderby(cols, [0, 1], keys, desc)
+            for g, e in zip(r.columns(), exp):
+                assert g.dtype == e.dtype and np.array_equal(g, e, equal_nan=True), (shape, n, trunc)
+            r.free()
+    finally:
+        env.set_option("sort.sweep16_min_rows", 1 << 16)
+        env.set_option("sort.trunc", 1)
+    t.free()
+
+
 # ---------------------------------------------------------------- JOIN
 @pytest.mark.parametrize("idx", [i for i, c in enumerate(VEC) if c["kind"] == "join"])
 def test_join_golden_vectors(idx):
@@ -594,6 +637,40 @@ def test_join_groupby_hash_build_sparse_keys(gb_impl, slices, kdt, match, nd, nf
     _check_cols(r.columns(), NO.join_groupby([fk, val, fval], [pk, attr], 0, 0, 1, sc, ops))
     for x in (r, dim, fact):
         x.free()
+
+
+@pytest.mark.parametrize("nd,nf", [(3, 50), (5000, 100003), (70001, 300007)])
+def test_join_groupby_hash_build_by_table_slices(nd, nf):
+    """The hash table is built slice by slice over K8t's output (hk_hash_build_tiles_kernel) when it is much larger
+    than a slice: forced here with 8 KB slices at any size; duplicates are still rejected."""
+    env = get_env()
+    from harkdb_b200.hark_ffi import HarkError
+    rng = np.random.default_rng(nd)
+    pk = _sparse_keys(rng, nd, NO.I32)
+    attr = rng.integers(-5, 90, nd).astype(np.int32)
+    fk = np.where(rng.random(nf) < 0.7, pk[rng.integers(0, nd, nf)], rng.integers(-2 ** 31, 2 ** 31, nf)).astype(np.int32)
+    val = rng.integers(-1000, 1000, nf).astype(np.int32)
+    dim, fact = env.from_columns([pk, attr]), env.from_columns([fk, val])
+    env.set_option("join.lut_slice_bytes", 8192)
+    env.set_option("join.build_partition_min_rows", 1)
+    env.set_option("join.build", 2)
+    try:
+        ops = [NO.AGG_SUM, NO.AGG_COUNT, NO.AGG_MIN]
+        r = env.join_groupby(fact, dim, 0, 0, 1, [1, 1, 1], ops)
+        _check_cols(r.columns(), NO.join_groupby([fk, val], [pk, attr], 0, 0, 1, [1, 1, 1], ops))
+        r.free()
+        pk2 = pk.copy()
+        pk2[-1] = pk2[0]
+        d2 = env.from_columns([pk2, attr])
+        if nd > 1:
+            with pytest.raises(HarkError, match="not unique"):
+                env.join_groupby(fact, d2, 0, 0, 1, [1], [NO.AGG_SUM])
+        d2.free()
+    finally:
+        env.set_option("join.lut_slice_bytes", 16 << 20)
+        env.set_option("join.build_partition_min_rows", 1 << 16)
+        env.set_option("join.build", 0)
+    dim.free(); fact.free()
 
 
 def test_join_groupby_hash_build_equals_lookup_build_and_rejects_duplicates(gb_impl, slices):

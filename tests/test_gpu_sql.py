@@ -141,3 +141,18 @@ def test_where_float_table():
     out = ctx.sql("SELECT col1,col3 FROM t WHERE col2 > 0.5 AND col5 < 0.25")
     m = (a[:, 1] > np.float32(0.5)) & (a[:, 4] < np.float32(0.25))
     assert out.dtype == np.float32 and np.array_equal(out, a[m][:, [0, 2]])
+
+
+def test_sql_device_result_stays_resident(fc):
+    """sql(..., device=True): the result is a DeviceTable that further entries consume without a download."""
+    from harkdb_b200.hark_ffi import DeviceTable
+    r = fc.sql("select col1, col3 from game_1 where col1 > 0", device=True)
+    assert isinstance(r, DeviceTable) and r.shape == (3, 2)
+    assert r.to_numpy().tolist() == [[6, 6], [6, 6], [1, 3]]
+    g = fc.FutEnv.query_groupby_ex(r, 0, [1], [NO.AGG_COUNT])          # chained on the device
+    assert [c.tolist() for c in g.columns()] == [[1, 6], [1, 2]]
+    g.free(); r.free()
+    r = fc.sql("select col1, count(col1) from game_1 group by col1 order by col1 desc limit 2", device=True)
+    assert isinstance(r, DeviceTable) and r.shape[0] == 2
+    r.free()
+    assert isinstance(fc.sql("select col1 from game_1"), np.ndarray)    # default unchanged

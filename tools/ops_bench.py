@@ -246,22 +246,26 @@ def run_orderby(env, scale, reps):
     return d
 
 
-def run_join(env, scale, reps):
+def run_join(env, scale, reps, sparse=False):
     import torch
     nf, nd = int(4 * 10 ** 9 * scale), int(10 ** 8 * min(1.0, scale * 4))
     # dim: pk = (a*r+b) mod nd with gcd(a, nd)=1 -> a permutation of 0..nd-1 (unique); attr uniform over 1024
     a = 2654435761
-    while np.gcd(a, nd) != 1:
+    while np.gcd(a, nd) != 1 and not sparse:
         a += 2
-    dim = env.synth(nd, [I32, I32], [dict(kind=1, a=a, b=12345, range=nd), dict(kind=0, lo=0, range=1024)], seed=7)
-    fact = env.synth(nf, [I32, I32], [dict(kind=0, lo=0, range=nd), dict(kind=0, lo=0, range=1000)], seed=42)
+    if sparse:      # pk = a*j + b truncated to i32 (spread over the whole 32-bit range), fk = a*U + b, U uniform over [0, nd)
+        dim = env.synth(nd, [I32, I32], [dict(kind=1, a=a, b=12345, range=0), dict(kind=0, lo=0, range=1024)], seed=7)
+        fact = env.synth(nf, [I32, I32], [dict(kind=4, a=a, b=12345, range=nd), dict(kind=0, lo=0, range=1000)], seed=42)
+    else:
+        dim = env.synth(nd, [I32, I32], [dict(kind=1, a=a, b=12345, range=nd), dict(kind=0, lo=0, range=1024)], seed=7)
+        fact = env.synth(nf, [I32, I32], [dict(kind=0, lo=0, range=nd), dict(kind=0, lo=0, range=1000)], seed=42)
     ops = [AGG_SUM, AGG_COUNT]
     st, r = timed(env, lambda: env.join_groupby(fact, dim, 0, 0, 1, [1, 1], ops), reps)
     keys, sums, cnts = r.columns()
     total = int(as_torch(fact, 1).sum(dtype=torch.int64).item())
     ok = (len(keys) == 1024 and np.array_equal(keys, np.arange(1024, dtype=np.int32)) and int(cnts.sum()) == nf
           and (int(sums.view(np.uint32).astype(np.uint64).sum()) - total) % (1 << 32) == 0)
-    d = line("join_groupby_cfg5", nf, st, {"dim_rows": nd, "groups": len(keys), "check_ok": bool(ok)})
+    d = line("join_groupby_cfg5_sparse_pk" if sparse else "join_groupby_cfg5", nf, st, {"dim_rows": nd, "groups": len(keys), "check_ok": bool(ok)})
     r.free(); dim.free(); fact.free()
     return d
 
@@ -298,6 +302,15 @@ def main():
                 res.append(run_filter_sweep(env, args.scale, args.reps))
             elif op == "join":
                 res.append(run_join(env, args.join_scale or args.scale, args.reps))
+            elif op in ("join_entry", "join_hash", "join_hash_i64"):
+                from tools.query_suite import Suite
+                su = Suite(env, reps=args.reps, scale=args.scale)
+                d = su.join_entry() if op == "join_entry" else su.join_hash(i64=op.endswith("i64"))
+                d["op"] = op
+                print(json.dumps(d), flush=True)
+                res.append(d)
+            elif op == "join_sparse":
+                res.append(run_join(env, args.join_scale or args.scale, args.reps, sparse=True))
             if args.cpu_rows > 0 and "error" not in res[-1] and op in ("groupby", "orderby", "join"):
                 res[-1]["cpu_baseline"] = cpu_leg(op, args.cpu_rows)
                 print(json.dumps({"op": op, "cpu_baseline": res[-1]["cpu_baseline"]}), flush=True)
