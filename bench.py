@@ -408,9 +408,17 @@ def run_gpu_arm(args):
                 tm = torch.tensor([dt], device="cuda", dtype=torch.float64)
                 dist.all_reduce(tm, op=dist.ReduceOp.MAX)
                 dt = float(tm.item())
-            e2e = {"value": world * e2e_rows * args.e2e_steps / dt, "unit": "rows/s",
+            # one stalled step (a page-in on a fresh box: 1.7 s against 0.16 s was seen) must not decide the number: the
+            # value is taken from the MEDIAN step of this rank, max over ranks; the mean and every step are reported too
+            med = statistics.median(a + b for a, b in phases) * 1e-3
+            if world > 1:
+                tm = torch.tensor([med], device="cuda", dtype=torch.float64)
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                med = float(tm.item())
+            e2e = {"value": world * e2e_rows / med, "unit": "rows/s", "value_from": "median step (max over ranks)",
+                   "mean_rows_per_s": world * e2e_rows * args.e2e_steps / dt,
                    "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": int(k) * 8, "rows_per_step": e2e_rows,
-                   "steps": args.e2e_steps, "warmup": args.e2e_warmup + extra, "ms_per_step": 1e3 * dt / args.e2e_steps,
+                   "steps": args.e2e_steps, "warmup": args.e2e_warmup + extra, "ms_per_step": 1e3 * med,
                    "step_phases_ms[upload+filter, download]": list(phases),
                    "path": "pinned host row-major table -> hark_table_from_host (H2D + transpose) -> "
                            "hark_entry_query_filter -> hark_table_to_host (D2H), all inside the timed step"}
@@ -429,8 +437,8 @@ def run_gpu_arm(args):
                     best_copy = tc if best_copy is None else min(best_copy, tc)
                 del hp, dp
                 moved = in_bytes + int(k) * 8
-                e2e["pcie"] = {"achieved_gbs": moved / (dt / args.e2e_steps) / 1e9, "h2d_peak_gbs": pb / best_copy / 1e9,
-                               "frac": (moved / (dt / args.e2e_steps)) / (pb / best_copy),
+                e2e["pcie"] = {"achieved_gbs": moved / med / 1e9, "h2d_peak_gbs": pb / best_copy / 1e9,
+                               "frac": (moved / med) / (pb / best_copy),
                                "note": "bytes crossing PCIe per step / step time, against a pinned 1 GiB torch copy timed in this run"}
             except Exception as ex:      # never lose the bench line over a diagnostic
                 e2e["pcie"] = {"error": repr(ex)[:200]}

@@ -377,7 +377,7 @@ __device__ __forceinline__ uint32_t tpart_digit(typename KRaw<KW>::T raw, typena
 // checks anywhere).
 template <int KW, int NV, bool HASH, bool FULL>
 __device__ __forceinline__ void tpart_tile(const TPartParams &P, const PartParams &L, uint32_t *s_stage, uint32_t *s_hist,
-                                           uint32_t *s_binstart, uint32_t *s_wtot, int64_t tile, int count, int next_count,
+                                           uint32_t *s_binstart, uint32_t *s_wtot, uint32_t *s_hot, int64_t tile, int count, int next_count,
                                            typename KRaw<KW>::T (&key)[PI], uint32_t (&val)[NV > 0 ? NV : 1][PI],
                                            typename KRaw<KW>::T xmask, typename KRaw<KW>::T base, typename KRaw<KW>::T last, int shift) {
     using KT = typename KRaw<KW>::T;
@@ -386,10 +386,33 @@ __device__ __forceinline__ void tpart_tile(const TPartParams &P, const PartParam
     uint32_t d[PI], rk[PI];
 #pragma unroll
     for (int i = 0; i < PI; i++) d[i] = tpart_digit<KW, HASH>(key[i], xmask, base, last, shift, P.hmask);
+    // Skewed keys: when one bin took more than a quarter of the previous tile, its rows are ranked with one vote and ONE
+    // atomic per warp instruction instead of one same-address atomic per row (which the hardware serialises: with Zipf
+    // keys 70 % of a tile lands in one bin).  `hot` is uniform over the CTA, so the branch does not diverge.
+    const uint32_t hot = *s_hot;
+    if (hot != 0xffffffffu) {
+        const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
-    for (int i = 0; i < PI; i++) {
-        const int idx = ((i >> 2) * TP_T + tid) * 4 + (i & 3);
-        if (FULL || idx < count) rk[i] = atomicAdd(&s_hist[d[i]], 1u);
+        for (int i = 0; i < PI; i++) {
+            const int idx = ((i >> 2) * TP_T + tid) * 4 + (i & 3);
+            const bool valid = FULL || idx < count;
+            const bool is_hot = valid && d[i] == hot;
+            const uint32_t m = __ballot_sync(HK_FULL_MASK, is_hot);
+            uint32_t base = 0;
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                if (lane == leader) base = atomicAdd(&s_hist[hot], (uint32_t)__popc(m));
+                base = __shfl_sync(HK_FULL_MASK, base, leader);
+            }
+            if (is_hot) rk[i] = base + __popc(m & lt);
+            else if (valid) rk[i] = atomicAdd(&s_hist[d[i]], 1u);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < PI; i++) {
+            const int idx = ((i >> 2) * TP_T + tid) * 4 + (i & 3);
+            if (FULL || idx < count) rk[i] = atomicAdd(&s_hist[d[i]], 1u);
+        }
     }
     // the bulk copy of the previous tile must have finished READING the stage before anyone overwrites it
     if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -407,9 +430,19 @@ __device__ __forceinline__ void tpart_tile(const TPartParams &P, const PartParam
             const uint32_t binstart = woff + inc - sum;
             s_binstart[tid] = binstart;
             if (tid < P.nbins) P.dir[(size_t)tile * P.nbins + tid] = binstart | ((binstart + sum) << 16);
+            // the fullest bin of this tile (count << 8 | bin), for the next tile's ranking
+            uint32_t best = (sum << 8) | (uint32_t)tid;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(HK_FULL_MASK, best, o));
+            if (lane == 0) s_wtot[8 + warp] = best;
         }
     }
     __syncthreads();
+    if (tid == 0) {
+        uint32_t best = 0;
+        for (int w = 0; w < 8; w++) best = max(best, s_wtot[8 + w]);
+        *s_hot = (best >> 8) > (uint32_t)(TP_TILE / 4) ? (best & 0xffu) : 0xffffffffu; // read after the next barriers
+    }
     // ---- the packed rows go to their slot of the stage ----
 #pragma unroll
     for (int i = 0; i < PI; i++) {
@@ -459,9 +492,11 @@ __global__ void __launch_bounds__(TP_T, 2) hk_tpart_kernel(const __grid_constant
     uint32_t *s_stage = s_dyn32;
     uint32_t *s_hist = s_dyn32 + (size_t)TP_TILE * RW;
     uint32_t *s_binstart = s_hist + 256;
-    uint32_t *s_wtot = s_binstart + 256;
+    uint32_t *s_wtot = s_binstart + 256; // [0..8) warp totals of the scan, [8..16) warp maxima
+    uint32_t *s_hot = s_wtot + 16;       // bin that held more than a quarter of the previous tile, or 0xffffffff
 
     const int tid = threadIdx.x;
+    if (tid == 0) *s_hot = 0xffffffffu;
     const int64_t t0 = (int64_t)blockIdx.x * P.tiles_per_cta;
     const int64_t t1 = min(P.num_tiles, t0 + P.tiles_per_cta);
     if (tid < 256) s_hist[tid] = 0;
@@ -481,9 +516,9 @@ __global__ void __launch_bounds__(TP_T, 2) hk_tpart_kernel(const __grid_constant
     for (int64_t tile = t0; tile < t1; tile++) {
         const int next_count = tile + 1 < t1 ? (int)min((int64_t)TP_TILE, P.n - (tile + 1) * TP_TILE) : 0;
         if (count == TP_TILE)
-            tpart_tile<KW, NV, HASH, true>(P, L, s_stage, s_hist, s_binstart, s_wtot, tile, count, next_count, key, val, xmask, base, last, shift);
+            tpart_tile<KW, NV, HASH, true>(P, L, s_stage, s_hist, s_binstart, s_wtot, s_hot, tile, count, next_count, key, val, xmask, base, last, shift);
         else
-            tpart_tile<KW, NV, HASH, false>(P, L, s_stage, s_hist, s_binstart, s_wtot, tile, count, next_count, key, val, xmask, base, last, shift);
+            tpart_tile<KW, NV, HASH, false>(P, L, s_stage, s_hist, s_binstart, s_wtot, s_hot, tile, count, next_count, key, val, xmask, base, last, shift);
         count = next_count;
     }
     if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // shared memory must outlive the copy
@@ -491,7 +526,7 @@ __global__ void __launch_bounds__(TP_T, 2) hk_tpart_kernel(const __grid_constant
 
 template <int KW, int NV>
 int launch_tpart(hark_ctx *ctx, const TPartParams &P, unsigned grid) {
-    const size_t smem = (size_t)TP_TILE * (KW / 4 + NV) * 4 + (256 + 256 + 8) * 4;
+    const size_t smem = (size_t)TP_TILE * (KW / 4 + NV) * 4 + (256 + 256 + 16 + 4) * 4;
     void (*kern)(const TPartParams) = P.hash ? hk_tpart_kernel<KW, NV, true> : hk_tpart_kernel<KW, NV, false>;
     HK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, TP_T, smem, ctx->stream>>>(P);
