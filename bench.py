@@ -580,6 +580,7 @@ def run_queries(args, eng, world, rank):
             out[name] = fn()
         except Exception as ex:       # one operator failing (e.g. out of memory) must not hide the others
             out[name] = {"error": repr(ex)[:300]}
+        env.trim()                    # the next query has other sizes: start it from an empty pool (outside any timed region)
         torch.cuda.empty_cache()
 
     if world == 1:
@@ -610,6 +611,7 @@ def run_queries(args, eng, world, rank):
                 res[name] = fn()
             except Exception as ex:
                 res[name] = {"error": repr(ex)[:300]}
+            env.trim()
             torch.cuda.empty_cache()
 
         sub("parity_ok", su.parity)

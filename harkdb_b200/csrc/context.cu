@@ -171,6 +171,13 @@ extern "C" int hark_context_sync(hark_ctx *ctx) {
     return HARK_OK;
 }
 
+extern "C" int hark_context_trim(hark_ctx *ctx) {
+    HK_ENTER(ctx);
+    HK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    HK_CUDA(ctx, cudaMemPoolTrimTo(ctx->pool, 0));
+    return HARK_OK;
+}
+
 extern "C" char *hark_context_get_error(hark_ctx *ctx) {
     if (!ctx || !ctx->has_err) return nullptr;
     char *s = (char *)malloc(ctx->err.size() + 1);

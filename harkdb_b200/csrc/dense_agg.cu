@@ -176,6 +176,7 @@ struct DAggParams {
     // hash mode (join + GROUP BY over sparse keys, join.cu): open addressing, slot + 1 in the entry, 0 = empty
     const void *htab;
     unsigned long long hmask;
+    unsigned long long *ticket; // lookup / hash modes: work units are dealt from this counter (zeroed by the host)
 };
 
 __device__ __forceinline__ uint32_t acc_identity(int kind, int w /* 0 or 1 for two-word kinds */) {
@@ -660,26 +661,44 @@ __device__ __forceinline__ void dagg_segments(const DAggParams &P, uint32_t *tab
             // hash probes: the FIRST probe of every row is issued before any is looked at (U independent loads in
             // flight, like the lookup mode); only rows whose first entry holds another key walk on
             if constexpr (KW == 4) {
-                const uint2 *ht = reinterpret_cast<const uint2 *>(P.htab);
+                // 8-byte entries: a probe reads the 16-byte PAIR that holds its slot (the load costs the same L2 sector as
+                // one entry would) and settles up to two probe positions per load; the first pair of every row is requested
+                // before any is examined.  Fewer trips through the walk matters twice: a warp repeats the loop until its
+                // slowest lane is done (linear probing at load 0.37: ~6 single-entry trips per warp, ~3 pair trips).
+                const uint4 *ht = reinterpret_cast<const uint4 *>(P.htab);
+                const uint64_t pmask = P.hmask >> 1;
                 uint64_t h[U];
-                uint2 e0[U];
+                uint4 e0[U];
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                     h[u] = hk_hash_key<4>(k[u]) & P.hmask;
-                    e0[u] = make_uint2(0u, 0u);
-                    if ((okm >> u) & 1u) e0[u] = __ldg(ht + h[u]);
+                    e0[u] = make_uint4(0u, 0u, 0u, 0u);
+                    if ((okm >> u) & 1u) e0[u] = __ldg(ht + (h[u] >> 1));
                 }
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                     idx[u] = 0xffffffffu;
                     if ((okm >> u) & 1u) {
-                        uint2 e = e0[u];
-                        uint64_t hh = h[u];
-                        while (e.y != 0u && e.x != k[u]) {
-                            hh = (hh + 1) & P.hmask;
-                            e = __ldg(ht + hh);
+                        uint4 e = e0[u];
+                        uint64_t pp = h[u] >> 1;
+                        bool second_only = (h[u] & 1ull) != 0; // the slot is the pair's second entry: the first is not on the probe path
+                        while (true) {
+                            if (!second_only) {
+                                if (e.y == 0u) break;
+                                if (e.x == k[u]) {
+                                    idx[u] = e.y - 1u;
+                                    break;
+                                }
+                            }
+                            if (e.w == 0u) break;
+                            if (e.z == k[u]) {
+                                idx[u] = e.w - 1u;
+                                break;
+                            }
+                            second_only = false;
+                            pp = (pp + 1) & pmask;
+                            e = __ldg(ht + pp);
                         }
-                        if (e.y != 0u) idx[u] = e.y - 1u;
                     }
                 }
             } else {
@@ -829,9 +848,21 @@ __global__ void __launch_bounds__(dagg_threads(NV), 1) hk_dagg_tiles_kernel(cons
             __syncthreads();
         }
     } else {
-        for (long long u = (long long)blockIdx.x * NW + warp; u < total; u += (long long)gridDim.x * NW) {
-            const long long b = u / groups_per_bin;
-            dagg_segments<KW, MODE, NV, SPEC>(P, tab, (int)b, (u - b * groups_per_bin) * TG, NT, lane);
+        // Units are taken from a TICKET counter, TCHUNK at a time and in bin-major order: all warps of the chip stay within
+        // a few thousand units of each other, i.e. on one or two slices of the build structure, however unevenly the CTAs
+        // run.  (A static round-robin lets them drift: over 128 bins x 26 rounds a 2 % speed difference puts the CTAs
+        // several slices apart and the probes fall out of L2 — ncu: 133 GB of DRAM reads for 32 GB of rows, r02_k2_hash.)
+        constexpr long long TCHUNK = 8;
+        while (true) {
+            long long u0 = 0;
+            if (lane == 0) u0 = (long long)atomicAdd(P.ticket, (unsigned long long)TCHUNK);
+            u0 = __shfl_sync(HK_FULL_MASK, u0, 0);
+            if (u0 >= total) break;
+            const long long u1 = min(total, u0 + TCHUNK);
+            for (long long u = u0; u < u1; u++) {
+                const long long b = u / groups_per_bin;
+                dagg_segments<KW, MODE, NV, SPEC>(P, tab, (int)b, (u - b * groups_per_bin) * TG, NT, lane);
+            }
         }
         __syncthreads();
         for (uint32_t i = tid; i < K; i += AT) flush_slot(tab, K, i, (uint64_t)i, P);
@@ -1338,6 +1369,10 @@ int hk_dense_groupby(hark_ctx *ctx, hark_table **out, const hk_dense_req &rq, bo
     P.t_rows = tp.rows;
     P.t_dir = tp.dir;
     P.t_num_tiles = tp.num_tiles;
+    if (use_tiles && lut_mode) {
+        HK_TRY(scratch.alloc((void **)&P.ticket, sizeof(unsigned long long)));
+        HK_CUDA(ctx, cudaMemsetAsync(P.ticket, 0, sizeof(unsigned long long), ctx->stream));
+    }
     if (use_tiles && !lut_mode) {
         const long long nblk = (tp.num_tiles + TBLK - 1) / TBLK, nent = nblk * nbins;
         uint32_t *blk_rows = nullptr;

@@ -175,13 +175,22 @@ __global__ void __launch_bounds__(256) hk_hash_build_kernel(const void *pk, cons
 // being 10^8 random atomics over a table of gigabytes.  4-byte keys, 4-byte group column, group-slot payload.
 __global__ void __launch_bounds__(256) hk_hash_build_tiles_kernel(const uint32_t *__restrict__ rows, const uint32_t *__restrict__ dir,
                                                                    long long num_tiles, int nbins, int g_dtype, unsigned long long g_lo,
-                                                                   void *htab, unsigned long long hmask, unsigned int *dup_flag) {
+                                                                   void *htab, unsigned long long hmask, unsigned int *dup_flag,
+                                                                   unsigned long long *ticket) {
     unsigned long long *t = reinterpret_cast<unsigned long long *>(htab);
     const int lane = threadIdx.x & 31;
-    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (int b = 0; b < nbins; b++) {
-        for (long long u = warp0; u < num_tiles; u += nwarps) {
+    // (slice, tile) units in slice-major order from a ticket counter, 16 at a time: every warp of the chip works on the
+    // same one or two slices (a static assignment lets the CTAs drift apart over the 128 slices)
+    const long long total = (long long)nbins * num_tiles;
+    while (true) {
+        long long u0 = 0;
+        if (lane == 0) u0 = (long long)atomicAdd(ticket, 16ull);
+        u0 = __shfl_sync(HK_FULL_MASK, u0, 0);
+        if (u0 >= total) break;
+        const long long u1 = min(total, u0 + 16);
+        for (long long uu = u0; uu < u1; uu++) {
+            const int b = (int)(uu / num_tiles);
+            const long long u = uu - (long long)b * num_tiles;
             const uint32_t w = __ldg(dir + (size_t)u * nbins + b);
             const uint32_t s = w & 0xffffu, e = w >> 16;
             for (uint32_t r = s + lane; r < e; r += 32) {
@@ -455,8 +464,11 @@ struct MjExpandParams {
 
 // balanced over the OUTPUT: a CTA owns result rows [q * slice, (q + 1) * slice), finds the left rows that produce them
 // with two searches, and every thread then searches only inside that (small, cached) range
+constexpr int MJ_CACHE = 6144; // left rows of a slice whose offsets are staged in shared memory
+
 __global__ void __launch_bounds__(256) hk_mj_expand_kernel(const __grid_constant__ MjExpandParams E) {
     __shared__ long long s_r[2];
+    __shared__ uint32_t s_off[MJ_CACHE]; // offs[ia + k] - p0, saturated (rows past the slice compare as "greater")
     const int64_t nslices = (E.P + E.slice - 1) / E.slice;
     for (int64_t q = blockIdx.x; q < nslices; q += gridDim.x) {
         const int64_t p0 = q * E.slice, p1 = min(E.P, p0 + E.slice);
@@ -471,11 +483,29 @@ __global__ void __launch_bounds__(256) hk_mj_expand_kernel(const __grid_constant
         }
         __syncthreads();
         const int64_t ia = s_r[0], ib = s_r[1];
+        const bool cached = ib - ia < MJ_CACHE; // the usual case: one coalesced read of the slice's offsets, searches in shared memory
+        if (cached) {
+            for (int64_t k = threadIdx.x; k <= ib - ia; k += 256) {
+                const unsigned long long o = E.offs[ia + k];
+                s_off[k] = o <= (unsigned long long)p0 ? 0u : (uint32_t)min(o - (unsigned long long)p0, 0xffffffffull);
+            }
+            __syncthreads();
+        }
         for (int64_t p = p0 + threadIdx.x; p < p1; p += 256) {
             int64_t lo = ia, hi = ib + 1;
-            while (hi - lo > 1) {
-                const int64_t mid = (lo + hi) >> 1;
-                if (E.offs[mid] <= (unsigned long long)p) lo = mid; else hi = mid;
+            if (cached) {
+                const uint32_t rel = (uint32_t)(p - p0);
+                int l = 0, h = (int)(ib - ia) + 1; // s_off[0] = 0 <= rel
+                while (h - l > 1) {
+                    const int mid = (l + h) >> 1;
+                    if (s_off[mid] <= rel) l = mid; else h = mid;
+                }
+                lo = ia + l;
+            } else {
+                while (hi - lo > 1) {
+                    const int64_t mid = (lo + hi) >> 1;
+                    if (E.offs[mid] <= (unsigned long long)p) lo = mid; else hi = mid;
+                }
             }
             const int64_t i = lo, j = p - (int64_t)E.offs[i];
             join_emit(E.C, p, (int64_t)E.rid1[i], (int64_t)E.rid2[(int64_t)E.lb[i] + j]);
@@ -870,8 +900,11 @@ int build_hash_table(hark_ctx *ctx, Bufs &bufs, const hark_table *dim, int32_t p
         HK_TRY(hk_tile_partition(ctx, nd, pk, 4, ps, H - 1, 1, gv, &tp));
         bufs.adopt(tp.rows);
         bufs.adopt(tp.dir);
+        unsigned long long *ticket = nullptr;
+        HK_TRY(bufs.alloc((void **)&ticket, sizeof(unsigned long long)));
+        HK_CUDA(ctx, cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), ctx->stream));
         hk_hash_build_tiles_kernel<<<(unsigned)ctx->num_sms * 8, 256, 0, ctx->stream>>>(tp.rows, tp.dir, tp.num_tiles, tp.nbins, g_dtype, g_lo,
-                                                                                      tab, H - 1, dup);
+                                                                                      tab, H - 1, dup, ticket);
         HK_CHECK_LAUNCH(ctx);
         ctx->count_launch();
     } else if (kw == 4) {

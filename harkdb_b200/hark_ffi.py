@@ -65,6 +65,7 @@ SIGNATURES = {
     "hark_context_new": (_P, [C.c_int, _P]),
     "hark_context_free": (None, [_P]),
     "hark_context_sync": (C.c_int, [_P]),
+    "hark_context_trim": (C.c_int, [_P]),
     "hark_context_get_error": (_P, [_P]),
     "hark_context_device": (C.c_int, [_P]),
     "hark_last_init_error": (C.c_char_p, []),
@@ -288,6 +289,10 @@ class Futhark:
 
     def sync(self):
         self._check(self.lib.hark_context_sync(self.ctx))
+
+    def trim(self):
+        """Hands the memory pool's free blocks back to the driver (between workloads of very different sizes)."""
+        self._check(self.lib.hark_context_trim(self.ctx))
 
     def set_option(self, key: str, value: int):
         self._check(self.lib.hark_context_set_option(self.ctx, key.encode(), int(value)))

@@ -124,6 +124,11 @@ int hark_abi_version(void);
 hark_ctx *hark_context_new(int device, void *stream);
 void hark_context_free(hark_ctx *ctx);
 int hark_context_sync(hark_ctx *ctx);
+/* The context's stream-ordered memory pool keeps freed blocks for the next query (no cudaMalloc in steady state).  This
+ * hands every free block back to the driver (after a synchronize) — for callers that switch between workloads of very
+ * different sizes on a nearly full device, where cached blocks of the old sizes would otherwise force a trim + re-grow
+ * inside a query.                                                                                                     */
+int hark_context_trim(hark_ctx *ctx);
 char *hark_context_get_error(hark_ctx *ctx); /* malloc'd, caller frees; NULL if no error      */
 int hark_context_device(hark_ctx *ctx);
 /* Text of the last failure of hark_context_new (static storage), for when it returned NULL.  */
