@@ -756,6 +756,10 @@ __global__ void __launch_bounds__(LT, 2) hk_lsd_scatter_kernel(const __grid_cons
 struct SweepParams {
     DigitFn f;
     int kf;                 // which field of the row carries this pass's key: 0 = a, 1 = b
+    // a digit that STRADDLES the two key columns: the low `lsh` bits come from (f, kf) — the top bits of the less
+    // significant key —, the rest from (f2, kf2) — the low bits of the more significant one
+    int two, kf2, lsh;
+    DigitFn f2;
     const uint64_t *a_in, *b_in; // FIRST: the two SoA inputs
     const ulonglong2 *rows_in;   // !FIRST
     uint64_t *a_out, *b_out;     // LAST: SoA outputs
@@ -771,6 +775,12 @@ struct SweepParams {
     const unsigned long long *chunk_base; // [num_chunks][256] global row where the chunk's rows of each digit start
 };
 
+__device__ __forceinline__ uint32_t sweep_digit(const SweepParams &P, uint64_t ra, uint64_t rb) {
+    uint32_t d = digit_of<8>(P.kf == 0 ? ra : rb, P.f);
+    if (P.two) d |= digit_of<8>(P.kf2 == 0 ? ra : rb, P.f2) << P.lsh;
+    return d & 0xffu;
+}
+
 // chunk histogram of one pass over SoA (FIRST) or AoS rows: the counterpart of hk_lsd_hist_kernel
 template <bool FIRST>
 __global__ void __launch_bounds__(1024) hk_sweep16_hist_kernel(const __grid_constant__ SweepParams P) {
@@ -779,7 +789,9 @@ __global__ void __launch_bounds__(1024) hk_sweep16_hist_kernel(const __grid_cons
     __syncthreads();
     const int64_t r0 = (int64_t)blockIdx.x * P.tiles_per_chunk * LTILE;
     const int64_t r1 = min(P.n, r0 + P.tiles_per_chunk * LTILE);
-    if constexpr (FIRST) {
+    if (FIRST && P.two) {
+        for (int64_t i = r0 + threadIdx.x; i < r1; i += 1024) atomicAdd(&sh[sweep_digit(P, __ldg(P.a_in + i), __ldg(P.b_in + i))], 1u);
+    } else if constexpr (FIRST) {
         const uint64_t *p = P.kf == 0 ? P.a_in : P.b_in;
         const int64_t nvec = r1 > r0 ? (r1 - r0) / 2 : 0; // r0 is a multiple of LTILE: 16-byte aligned
         const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(p + r0);
@@ -794,7 +806,7 @@ __global__ void __launch_bounds__(1024) hk_sweep16_hist_kernel(const __grid_cons
 #pragma unroll 4
         for (int64_t i = r0 + threadIdx.x; i < r1; i += 1024) {
             const ulonglong2 v = __ldg(P.rows_in + i);
-            atomicAdd(&sh[digit_of<8>(P.kf == 0 ? v.x : v.y, P.f) & 0xffu], 1u);
+            atomicAdd(&sh[sweep_digit(P, v.x, v.y)], 1u);
         }
     }
     __syncthreads();
@@ -870,7 +882,7 @@ __global__ void __launch_bounds__(LT, 2) hk_sweep16_kernel(const __grid_constant
         uint32_t dpk[LI / 4];
 #pragma unroll
         for (int i = 0; i < LI; i++) {
-            const uint32_t d = digit_of<8>(P.kf == 0 ? ra[i] : rb[i], P.f) & 0xffu;
+            const uint32_t d = sweep_digit(P, ra[i], rb[i]);
             if ((i & 3) == 0) dpk[i >> 2] = d;
             else dpk[i >> 2] |= d << ((i & 3) * 8);
         }
@@ -1093,7 +1105,7 @@ __global__ void __launch_bounds__(256) hk_gather_kernel(VT *__restrict__ dst, co
 constexpr int FIX_MAXK = 8;  // key columns the repair can compare
 constexpr int FIX_LMAX = 32; // longest run of equal prefixes repaired in place
 constexpr int FIX_T = 256;
-constexpr int FIX_I = 4;     // rows per thread and iteration
+constexpr int FIX_I = 8;     // rows per thread and iteration (4 in round 1: three barriers per 1024 rows kept the scan latency-bound)
 
 struct FixKey {
     const void *ptr;
@@ -1508,10 +1520,90 @@ int fix_truncated(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec> &
 
 // All passes of a sort over two 8-byte carried arrays with K3b.  On success arrays[0..1].buf[(npass-1)&1] hold the
 // result (SoA), like the chunked path leaves them.
+// One pass of K3b: a primary digit part and, when the digit straddles the two keys, a second part shifted left by lsh.
+struct SweepPass {
+    DigitFn f;
+    int key;
+    int two = 0;
+    DigitFn f2;
+    int key2 = 0, lsh = 0;
+};
+
+// The LSD pass list of build_passes re-cut into 8-bit digits over the CONCATENATED bit string (sorted bits of the less
+// significant key, then all bits of the more significant one): config 4's 20-bit col1 no longer wastes a pass on its top 4
+// bits, so the same 5 passes cover 40 bits instead of 36 and the tie repair has 16x fewer runs to fix.  Only for two keys
+// that are the two carried arrays; anything else keeps the plain list.
+std::vector<SweepPass> sweep_passes(const std::vector<hk_sort_keyspec> &keys, const std::vector<Pass> &passes, bool straddle) {
+    std::vector<SweepPass> out;
+    auto plain = [&]() {
+        out.clear();
+        for (auto &p : passes) {
+            SweepPass s;
+            s.f = p.f;
+            s.key = p.key;
+            out.push_back(s);
+        }
+        return out;
+    };
+    if (!straddle || keys.size() != 2 || passes.empty()) return plain();
+    // passes: first those of key 1 (lowest shift first), then those of key 0 from bit 0
+    int n1 = 0;
+    while (n1 < (int)passes.size() && passes[n1].key == 1) n1++;
+    if (n1 == 0 || n1 == (int)passes.size()) return plain();
+    for (int i = n1; i < (int)passes.size(); i++)
+        if (passes[i].key != 0) return plain();
+    auto width_of = [](uint32_t mask) {
+        int w = 0;
+        while (mask) {
+            w++;
+            mask >>= 1;
+        }
+        return w;
+    };
+    const DigitFn k1 = passes[0].f, k0 = passes[n1].f;
+    int sh0 = k1.shift;                                                   // lowest sorted bit of key 1
+    const int top1 = passes[n1 - 1].f.shift + width_of(passes[n1 - 1].f.mask); // bits of key 1
+    const int bits0 = passes.back().f.shift + width_of(passes.back().f.mask);  // bits of key 0
+    int B = (top1 - sh0) + bits0;
+    if (B % 8 != 0) sh0 = std::max(0, sh0 - (8 - B % 8));                  // spend the spare digit capacity on more bits of key 1
+    B = (top1 - sh0) + bits0;
+    const int L1 = top1 - sh0;
+    for (int pos = 0; pos < B; pos += 8) {
+        SweepPass s;
+        if (pos + 8 <= L1 || pos >= L1) {
+            const bool from1 = pos < L1;
+            const int sh = from1 ? sh0 + pos : pos - L1;
+            const int w = std::min(8, (from1 ? top1 : bits0) - sh);
+            s.f = from1 ? k1 : k0;
+            s.f.shift = sh;
+            s.f.mask = (1u << w) - 1u;
+            s.key = from1 ? 1 : 0;
+        } else { // the digit straddles the boundary
+            const int w1 = L1 - pos, w2 = std::min(8 - w1, bits0);
+            s.f = k1;
+            s.f.shift = sh0 + pos;
+            s.f.mask = (1u << w1) - 1u;
+            s.key = 1;
+            s.two = 1;
+            s.f2 = k0;
+            s.f2.shift = 0;
+            s.f2.mask = (1u << w2) - 1u;
+            s.key2 = 0;
+            s.lsh = w1;
+        }
+        out.push_back(s);
+    }
+    return out;
+}
+
 int run_sweep16(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec> &keys, std::vector<hk_sort_array> &arrays,
-                const std::vector<Pass> &passes) {
+                const std::vector<Pass> &passes_in) {
+    const int fb = ((int)passes_in.size() - 1) & 1; // where the caller expects the result (its own pass count decides)
+    const bool lb0 = ctx->opt("sort.sweep16", 1) == 2;
+    const std::vector<SweepPass> passes = sweep_passes(keys, passes_in, !lb0 && ctx->opt("sort.straddle", 1) != 0 &&
+                                                                          keys[0].array != keys[keys.size() - 1].array);
+    ctx->counters["sort.last_sweep16_passes"] = (int64_t)passes.size();
     const int npass = (int)passes.size();
-    const int fb = (npass - 1) & 1;
     const int64_t num_tiles = (n + LTILE - 1) / LTILE;
     struct Scratch {
         hark_ctx *ctx;
@@ -1591,6 +1683,12 @@ int run_sweep16(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec> &ke
         memset(&S, 0, sizeof S);
         S.f = passes[p].f;
         S.kf = keys[passes[p].key].array;
+        S.two = passes[p].two;
+        if (S.two) {
+            S.f2 = passes[p].f2;
+            S.kf2 = keys[passes[p].key2].array;
+            S.lsh = passes[p].lsh;
+        }
         S.n = n;
         S.num_tiles = num_tiles;
         S.tiles_per_chunk = tiles_per_chunk;
