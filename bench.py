@@ -51,7 +51,7 @@ SEED = 42
 
 def ncu_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum of one hk_filter2_kernel launch of THIS workload, from the committed
-    `ncu --set full` capture (profiles/r01_filter_v2_final_ncu.txt; bench.py never runs under a profiler)."""
+    `ncu --set full` capture (profiles/r02_filter_ncu.txt; bench.py never runs under a profiler)."""
     try:
         rd = wr = None
         for line in open(os.path.join(ROOT, "profiles", "r01_filter_v2_final_ncu.txt")):
@@ -528,7 +528,7 @@ def run_gpu_arm(args):
                    "parallelism": f"row-range shards x{world}, no collective"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic_bytes() if rows == 10 ** 9 else None,
-                     "traffic_source": "profiles/r01_filter_v2_final_ncu.txt (ncu --set full, same workload, per launch)",
+                     "traffic_source": "profiles/r02_filter_ncu.txt (ncu --set full, same workload, per launch)",
                      "kernel": "hk_filter2_kernel<4,2,2>" if args.filter_impl in (0, 3) else "hk_filter_kernel<4,2,2>", "kernel_ms": k_ms,
                      "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                      "frac_of_nominal_8TBs": achieved / 8000.0,

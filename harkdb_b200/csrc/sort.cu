@@ -1105,7 +1105,7 @@ __global__ void __launch_bounds__(256) hk_gather_kernel(VT *__restrict__ dst, co
 constexpr int FIX_MAXK = 8;  // key columns the repair can compare
 constexpr int FIX_LMAX = 32; // longest run of equal prefixes repaired in place
 constexpr int FIX_T = 256;
-constexpr int FIX_I = 8;     // rows per thread and iteration (4 in round 1: three barriers per 1024 rows kept the scan latency-bound)
+constexpr int FIX_I = 4;     // rows per thread and iteration (8 measured slower: 122.6 vs 117.1 ms on configs[4], profiles/r02_w)
 
 struct FixKey {
     const void *ptr;
