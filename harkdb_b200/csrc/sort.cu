@@ -760,6 +760,10 @@ struct SweepParams {
     // significant key —, the rest from (f2, kf2) — the low bits of the more significant one
     int two, kf2, lsh;
     DigitFn f2;
+    // integer keys (FAST): digit part = (((key ^ x) + b) >> s) & m with  asc: x = xmask, b = -base;  desc: x = ~xmask,
+    // b = base + 1 (base - u = ~u + base + 1): no dtype / direction / mode decisions per row
+    uint64_t x1, b1, x2, b2;
+    uint32_t s1, m1, s2, m2;
     const uint64_t *a_in, *b_in; // FIRST: the two SoA inputs
     const ulonglong2 *rows_in;   // !FIRST
     uint64_t *a_out, *b_out;     // LAST: SoA outputs
@@ -775,10 +779,17 @@ struct SweepParams {
     const unsigned long long *chunk_base; // [num_chunks][256] global row where the chunk's rows of each digit start
 };
 
+template <bool FAST = false>
 __device__ __forceinline__ uint32_t sweep_digit(const SweepParams &P, uint64_t ra, uint64_t rb) {
-    uint32_t d = digit_of<8>(P.kf == 0 ? ra : rb, P.f);
-    if (P.two) d |= digit_of<8>(P.kf2 == 0 ? ra : rb, P.f2) << P.lsh;
-    return d & 0xffu;
+    if constexpr (FAST) {
+        uint32_t d = (uint32_t)((((P.kf == 0 ? ra : rb) ^ P.x1) + P.b1) >> P.s1) & P.m1;
+        if (P.two) d |= ((uint32_t)((((P.kf2 == 0 ? ra : rb) ^ P.x2) + P.b2) >> P.s2) & P.m2) << P.lsh;
+        return d;
+    } else {
+        uint32_t d = digit_of<8>(P.kf == 0 ? ra : rb, P.f);
+        if (P.two) d |= digit_of<8>(P.kf2 == 0 ? ra : rb, P.f2) << P.lsh;
+        return d & 0xffu;
+    }
 }
 
 // chunk histogram of one pass over SoA (FIRST) or AoS rows: the counterpart of hk_lsd_hist_kernel
@@ -841,7 +852,7 @@ __device__ __forceinline__ void sweep16_load(const SweepParams &P, int64_t tile_
     }
 }
 
-template <bool FIRST, bool LAST, bool CHUNKED>
+template <bool FIRST, bool LAST, bool CHUNKED, bool FAST>
 __global__ void __launch_bounds__(LT, 2) hk_sweep16_kernel(const __grid_constant__ SweepParams P) {
     extern __shared__ __align__(128) unsigned char s_dyn[];
     ulonglong2 *stage = reinterpret_cast<ulonglong2 *>(s_dyn); // LTILE rows of 16 bytes
@@ -859,8 +870,10 @@ __global__ void __launch_bounds__(LT, 2) hk_sweep16_kernel(const __grid_constant
     for (int i = tid; i < LWARPS * 256; i += LT) (&wh[0][0])[i] = 0;
     int64_t next_tile = (int64_t)blockIdx.x * P.tiles_per_chunk;
     const int64_t end_tile = min(P.num_tiles, next_tile + P.tiles_per_chunk);
-    if constexpr (CHUNKED)
+    if constexpr (CHUNKED) {
         if (tid < 256) s_run[tid] = P.chunk_base[(size_t)blockIdx.x * 256 + tid];
+        __syncthreads(); // the counters zeroed above belong to other warps (the ticket barrier orders them otherwise)
+    }
 
     uint64_t ra[LI], rb[LI];
     bool prefetched = false;
@@ -882,7 +895,7 @@ __global__ void __launch_bounds__(LT, 2) hk_sweep16_kernel(const __grid_constant
         uint32_t dpk[LI / 4];
 #pragma unroll
         for (int i = 0; i < LI; i++) {
-            const uint32_t d = sweep_digit(P, ra[i], rb[i]);
+            const uint32_t d = sweep_digit<FAST>(P, ra[i], rb[i]);
             if ((i & 3) == 0) dpk[i >> 2] = d;
             else dpk[i >> 2] |= d << ((i & 3) * 8);
         }
@@ -912,7 +925,7 @@ __global__ void __launch_bounds__(LT, 2) hk_sweep16_kernel(const __grid_constant
             __syncwarp();
         }
         // the bulk copies of this CTA's previous tile must have finished READING the stage before it is overwritten
-        if (!LAST && tid < 256) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (!LAST && (tid & 1) == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncthreads();
         // ---- thread b owns digit b: warp offsets inside the bin, bin start inside the tile, look-back for the base ----
         {
@@ -977,22 +990,28 @@ __global__ void __launch_bounds__(LT, 2) hk_sweep16_kernel(const __grid_constant
             if (prefetched)
                 sweep16_load<FIRST>(P, next_tile * LTILE, (int)min((int64_t)LTILE, P.n - next_tile * LTILE), warp, lane, ra, rb);
         }
+        // every warp zeroes ITS OWN counter row (only this warp ranks into it, and it has just read it for the last
+        // time): no barrier between this tile's write-out and the next tile's ranking
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; i++) wh[warp][i * 32 + lane] = 0;
         if constexpr (!LAST) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-        for (int i = tid; i < LWARPS * 256; i += LT) (&wh[0][0])[i] = 0; // read above for the last time; rewritten after >= 1 barrier
         if constexpr (!LAST) {
-            // ---- every digit's run leaves as ONE bulk copy ----
-            if (tid < 256) {
-                const uint32_t c = s_bincount[tid];
+            // ---- every digit's run leaves as ONE bulk copy.  The copy instruction takes uniform operands, so a warp
+            // issues its lanes' copies one after the other (11 SASS instructions each): the 256 digits are spread over
+            // all 16 warps (even threads), not over the first 8 ----
+            if ((tid & 1) == 0) {
+                const int b = tid >> 1;
+                const uint32_t c = s_bincount[b];
                 if (c) { // in pieces of at most 16 KB (a whole tile in one digit is a 64 KB run)
-                    unsigned char *g = reinterpret_cast<unsigned char *>(P.rows_out + s_gbase[tid]);
-                    const unsigned char *sm = reinterpret_cast<const unsigned char *>(stage + s_binstart[tid]);
+                    unsigned char *g = reinterpret_cast<unsigned char *>(P.rows_out + s_gbase[b]);
+                    const unsigned char *sm = reinterpret_cast<const unsigned char *>(stage + s_binstart[b]);
                     const uint32_t bytes = c * 16u;
                     for (uint32_t o = 0; o < bytes; o += 16384u) sw_bulk_store(g + o, sm + o, min(16384u, bytes - o));
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
-            if constexpr (CHUNKED) __syncthreads(); // the counters zeroed above are incremented by the next tile's ranking
         } else {
             // ---- last pass: back to the caller's SoA columns ----
             if (full) {
@@ -1017,7 +1036,7 @@ __global__ void __launch_bounds__(LT, 2) hk_sweep16_kernel(const __grid_constant
             __syncthreads(); // the stage is rewritten by the next tile
         }
     }
-    if (!LAST && tid < 256) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // shared memory must outlive the copies
+    if (!LAST && (tid & 1) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // shared memory must outlive the copies
 }
 
 // One stable pass over all carried arrays with the chunked protocol.  d_offsets_out (optional) receives the device
@@ -1128,6 +1147,7 @@ struct FixParams {
     unsigned long long *work; // [cap] : run start << 8 | run length
     unsigned long long cap;
     unsigned long long *count; // [0] runs recorded, [1] flag: redo with all passes
+    uint64_t fx, fb;           // integer fast path of the scan (hk_sort_fix_find_kernel MODE 1 / 2)
 };
 
 __device__ __forceinline__ uint64_t fix_key(const FixKey &k, int64_t r) {
@@ -1170,24 +1190,39 @@ __device__ unsigned long long fix_claim_run(const FixParams &P, int64_t i) {
     return ((unsigned long long)s << 8) | (unsigned long long)(e - s);
 }
 
+// MODE 0: generic order key of the truncated key column (floats: NaN canonicalisation, IEEE flip); 1 / 2: an 8- / 4-byte
+// integer column, whose normalised key is (zext(raw) ^ fx) + fb — asc: fx = sign flip, fb = -base; desc: fx = ~sign flip,
+// fb = base + 1.  The scan itself is one coalesced read of that column: a row fetches its predecessor's key from the
+// neighbouring lane, and only candidates (same sorted prefix, not in order) look at the other key columns.  A claimed run
+// goes straight to the work list with one global atomic (runs are rare: 0.9 M in configs[4]'s 2e9 rows), so the loop has no
+// barrier and no shared memory (round 2: the per-CTA list cost three barriers per 1024 rows and, with the generic key
+// function, 84 instructions per row — 12 ms of the 117 ms ORDER BY, profiles/r02_fix_find_ncu.txt).
+template <int MODE>
+__device__ __forceinline__ uint64_t fix_scan_key(const FixParams &P, const FixKey &ks, int64_t r) {
+    if constexpr (MODE == 1) return (__ldcs(reinterpret_cast<const uint64_t *>(ks.ptr) + r) ^ P.fx) + P.fb;
+    else if constexpr (MODE == 2) return ((uint64_t)__ldcs(reinterpret_cast<const uint32_t *>(ks.ptr) + r) ^ P.fx) + P.fb;
+    else return fix_key(ks, r);
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(FIX_T) hk_sort_fix_find_kernel(const __grid_constant__ FixParams P) {
-    __shared__ unsigned long long s_list[FIX_T * FIX_I];
-    __shared__ unsigned int s_cnt;
-    __shared__ unsigned long long s_base;
     const FixKey &ks = P.key[P.kstar];
+    const int lane = threadIdx.x & 31;
     const int64_t per_iter = (int64_t)FIX_T * FIX_I;
     const int64_t iters = (P.n + per_iter - 1) / per_iter;
     for (int64_t it = blockIdx.x; it < iters; it += gridDim.x) {
-        if (threadIdx.x == 0) s_cnt = 0;
-        __syncthreads();
         const int64_t r0 = it * per_iter + threadIdx.x;
         uint64_t ta[FIX_I], tb[FIX_I];
 #pragma unroll
         for (int j = 0; j < FIX_I; j++) {
             const int64_t i = r0 + (int64_t)j * FIX_T;
-            const bool ok = i >= 1 && i < P.n;
-            ta[j] = ok ? fix_key(ks, i - 1) : 0ull;
-            tb[j] = ok ? fix_key(ks, i) : ~0ull;
+            tb[j] = i < P.n ? fix_scan_key<MODE>(P, ks, i) : ~0ull;
+        }
+#pragma unroll
+        for (int j = 0; j < FIX_I; j++) {
+            const int64_t i = r0 + (int64_t)j * FIX_T;
+            ta[j] = __shfl_up_sync(HK_FULL_MASK, tb[j], 1);
+            if (lane == 0) ta[j] = (i >= 1 && i < P.n) ? fix_scan_key<MODE>(P, ks, i - 1) : 0ull;
         }
 #pragma unroll
         for (int j = 0; j < FIX_I; j++) {
@@ -1206,22 +1241,14 @@ __global__ void __launch_bounds__(FIX_T) hk_sort_fix_find_kernel(const __grid_co
                 if (c <= 0) continue;
             }
             const unsigned long long w = fix_claim_run(P, i);
-            if (w == ~0ull) atomicExch(P.count + 1, 1ull);
-            else if (w) s_list[atomicAdd(&s_cnt, 1u)] = w;
-        }
-        __syncthreads();
-        const unsigned int c = s_cnt;
-        if (c) {
-            if (threadIdx.x == 0) s_base = atomicAdd(P.count, (unsigned long long)c);
-            __syncthreads();
-            const unsigned long long base = s_base;
-            if (base + c > P.cap) {
-                if (threadIdx.x == 0) atomicExch(P.count + 1, 1ull);
-            } else {
-                for (unsigned int j = threadIdx.x; j < c; j += FIX_T) P.work[base + j] = s_list[j];
+            if (w == ~0ull) {
+                atomicExch(P.count + 1, 1ull);
+            } else if (w) {
+                const unsigned long long slot = atomicAdd(P.count, 1ull);
+                if (slot < P.cap) P.work[slot] = w;
+                else atomicExch(P.count + 1, 1ull);
             }
         }
-        __syncthreads();
     }
 }
 
@@ -1500,7 +1527,16 @@ int fix_truncated(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec> &
     if (e == cudaSuccess) {
         const int64_t iters = (n + FIX_T * FIX_I - 1) / (FIX_T * FIX_I);
         const unsigned g = (unsigned)std::max<int64_t>(1, std::min<int64_t>(iters, (int64_t)ctx->num_sms * 8));
-        hk_sort_fix_find_kernel<<<g, FIX_T, 0, ctx->stream>>>(P);
+        const FixKey &ks = P.key[P.kstar];
+        const int mode = (hk_dtype_int(ks.dtype) && ctx->opt("sort.fix_fast", 1) != 0) ? (ks.width == 8 ? 1 : 2) : 0;
+        if (mode) {
+            const uint64_t sign = ks.dtype == HARK_I32 ? 0x80000000ull : ks.dtype == HARK_I64 ? 0x8000000000000000ull : 0ull;
+            P.fx = ks.desc ? ~sign : sign;
+            P.fb = ks.desc ? ks.base + 1ull : 0ull - ks.base;
+        }
+        if (mode == 1) hk_sort_fix_find_kernel<1><<<g, FIX_T, 0, ctx->stream>>>(P);
+        else if (mode == 2) hk_sort_fix_find_kernel<2><<<g, FIX_T, 0, ctx->stream>>>(P);
+        else hk_sort_fix_find_kernel<0><<<g, FIX_T, 0, ctx->stream>>>(P);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) {
@@ -1667,15 +1703,23 @@ int run_sweep16(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec> &ke
     if (npass >= 2) HK_TRY(sc.alloc(&rows[0], (size_t)n * 16));
     if (npass >= 3) HK_TRY(sc.alloc(&rows[1], (size_t)n * 16));
     const size_t smem = (size_t)LTILE * 16;
-    void (*kerns[2][2][2])(const SweepParams) = {
-        {{hk_sweep16_kernel<false, false, false>, hk_sweep16_kernel<false, false, true>},
-         {hk_sweep16_kernel<false, true, false>, hk_sweep16_kernel<false, true, true>}},
-        {{hk_sweep16_kernel<true, false, false>, hk_sweep16_kernel<true, false, true>},
-         {hk_sweep16_kernel<true, true, false>, hk_sweep16_kernel<true, true, true>}}};
+#define HK_SW_K(a, b, c) {hk_sweep16_kernel<a, b, c, false>, hk_sweep16_kernel<a, b, c, true>}
+    void (*kerns[2][2][2][2])(const SweepParams) = {
+        {{HK_SW_K(false, false, false), HK_SW_K(false, false, true)}, {HK_SW_K(false, true, false), HK_SW_K(false, true, true)}},
+        {{HK_SW_K(true, false, false), HK_SW_K(true, false, true)}, {HK_SW_K(true, true, false), HK_SW_K(true, true, true)}}};
+#undef HK_SW_K
     for (int a = 0; a < 2; a++)
         for (int b = 0; b < 2; b++)
             for (int c = 0; c < 2; c++)
-                HK_CUDA(ctx, cudaFuncSetAttribute(kerns[a][b][c], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                for (int d = 0; d < 2; d++)
+                    HK_CUDA(ctx, cudaFuncSetAttribute(kerns[a][b][c][d], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool allow_fast = ctx->opt("sort.sweep16_fast", 1) != 0;
+    auto fast_part = [](const DigitFn &f, uint64_t *x, uint64_t *b, uint32_t *sh, uint32_t *m) {
+        *x = f.fast == 1 ? f.xmask : ~f.xmask;
+        *b = f.fast == 1 ? 0ull - f.base : f.base + 1ull;
+        *sh = (uint32_t)f.shift;
+        *m = f.mask;
+    };
     const unsigned grid = lookback ? (unsigned)std::min<int64_t>(num_tiles, max_chunks) : (unsigned)num_chunks;
     for (int p = 0; p < npass; p++) {
         const bool first = p == 0, last = p == npass - 1;
@@ -1688,6 +1732,14 @@ int run_sweep16(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec> &ke
             S.f2 = passes[p].f2;
             S.kf2 = keys[passes[p].key2].array;
             S.lsh = passes[p].lsh;
+        }
+        const bool fast = allow_fast && S.f.fast != 0 && S.f.mode == 0 && (!S.two || (S.f2.fast != 0 && S.f2.mode == 0));
+        if (fast) {
+            fast_part(S.f, &S.x1, &S.b1, &S.s1, &S.m1);
+            if (S.two) {
+                fast_part(S.f2, &S.x2, &S.b2, &S.s2, &S.m2);
+                S.m2 &= 0xffu >> S.lsh; // the generic path masks the assembled digit with 0xff
+            }
         }
         S.n = n;
         S.num_tiles = num_tiles;
@@ -1736,7 +1788,7 @@ int run_sweep16(hark_ctx *ctx, int64_t n, const std::vector<hk_sort_keyspec> &ke
             HK_CHECK_LAUNCH(ctx);
             ctx->count_launch(2);
         }
-        kerns[first ? 1 : 0][last ? 1 : 0][lookback ? 0 : 1]<<<grid, LT, smem, ctx->stream>>>(S);
+        kerns[first ? 1 : 0][last ? 1 : 0][lookback ? 0 : 1][fast ? 1 : 0]<<<grid, LT, smem, ctx->stream>>>(S);
         HK_CHECK_LAUNCH(ctx);
         ctx->count_launch();
     }

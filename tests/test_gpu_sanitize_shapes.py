@@ -87,6 +87,21 @@ def test_orderby_shapes():
     r = env.query_orderby(t, [3], [0, 1], [0, 0])
     assert np.array_equal(r.column(0), NO.query_orderby(cols, [3], [0, 1], [0, 0])[0])
     env.set_option("sort.trunc", 1)
+    # K3b (16-byte rows, TMA run stores): chunk protocol and look-back, digits straddling the two key columns or not
+    env.set_option("sort.sweep16_min_rows", 1)
+    try:
+        exp = NO.query_orderby(cols, [0, 1], [0, 1], [0, 1])
+        for mode, straddle in ((1, 1), (1, 0), (2, 1)):
+            env.set_option("sort.sweep16", mode)
+            env.set_option("sort.straddle", straddle)
+            r = env.query_orderby(t, [0, 1], [0, 1], [0, 1])
+            assert env.get_option("sort.last_sweep16") == 1
+            _eq(r.columns(), exp)
+            r.free()
+    finally:
+        env.set_option("sort.sweep16_min_rows", 1 << 16)
+        env.set_option("sort.sweep16", 1)
+        env.set_option("sort.straddle", 1)
     t.free()
 
 
