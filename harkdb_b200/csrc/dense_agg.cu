@@ -177,6 +177,7 @@ struct DAggParams {
     const void *htab;
     unsigned long long hmask;
     unsigned long long *ticket; // lookup / hash modes: work units are dealt from this counter (zeroed by the host)
+    unsigned long long *bin_ticket; // GROUP BY mode: one counter per bin (zeroed by the host); null = static row split
 };
 
 __device__ __forceinline__ uint32_t acc_identity(int kind, int w /* 0 or 1 for two-word kinds */) {
@@ -837,6 +838,37 @@ __global__ void __launch_bounds__(dagg_threads(NV), 1) hk_dagg_tiles_kernel(cons
         }
         __syncthreads();
         const long long e0 = s_e[0], e1 = s_e[1];
+        if (P.bin_ticket) {
+            // Dynamic dealing (default).  The static split below gives every CTA the same number of ROWS, but rows do not
+            // cost the same: with Zipf keys the bin that holds the hot groups serialises on shared-memory atomics while
+            // the cold bins' short segments waste lanes, and the chip waited for a few CTAs (ncu: SMs busy 27 % of the
+            // kernel, 11 ms where the uniform table takes 2.8, profiles/r02_ad_zipf_dagg_ncu.txt).  Every bin has a
+            // ticket counter dealing units of TG tiles; a CTA starts on the bin its row share starts in, drains it with
+            // all its warps, merges its table, and moves on to the next bin that still has units — so the CTAs of cheap
+            // bins end up helping with the expensive one.  A warp asks for its next ticket before it works on the
+            // current one (the atomic's latency is hidden).
+            const int nb = P.nbins;
+            const int home = (int)min((long long)nb - 1, e0 / NB);
+            for (int step = 0; step < nb; step++) {
+                const int b = home + step < nb ? home + step : home + step - nb;
+                unsigned long long *tk = P.bin_ticket + b;
+                bool did = false;
+                long long un = 0;
+                if (lane == 0) un = (long long)atomicAdd(tk, 1ull);
+                while (true) {
+                    const long long t = __shfl_sync(HK_FULL_MASK, un, 0) * TG;
+                    if (t >= NT) break;
+                    if (lane == 0) un = (long long)atomicAdd(tk, 1ull);
+                    dagg_segments<KW, MODE, NV, SPEC>(P, tab, b, t, NT, lane);
+                    did = true;
+                }
+                if (__syncthreads_or(did ? 1 : 0)) {
+                    for (uint32_t i = tid; i < K; i += AT) flush_slot(tab, K, i, ((uint64_t)b << P.shift) + i, P);
+                    __syncthreads();
+                }
+            }
+            return;
+        }
         for (long long b = e0 / NB; b * NB < e1 && b < P.nbins; b++) {
             const long long ba = max(e0, b * NB) - b * NB, bb = min(e1, (b + 1) * NB) - b * NB;
             const long long t_lo = ba * TBLK, t_hi = min(NT, bb * TBLK);
@@ -1386,6 +1418,10 @@ int hk_dense_groupby(hark_ctx *ctx, hark_table **out, const hk_dense_req &rq, bo
         ctx->count_launch(2);
         P.t_cum = cum;
         P.t_nblk = nblk;
+        if (ctx->opt("dense.dynamic", 1) != 0) {
+            HK_TRY(scratch.alloc((void **)&P.bin_ticket, sizeof(unsigned long long) * (size_t)nbins));
+            HK_CUDA(ctx, cudaMemsetAsync(P.bin_ticket, 0, sizeof(unsigned long long) * (size_t)nbins, ctx->stream));
+        }
     }
     P.nvals = rq.nvals;
     for (int v = 0; v < rq.nvals; v++) P.vals[v] = (const uint32_t *)vals[v];
