@@ -13,7 +13,9 @@ dimension tables) far larger than the 126 MB L2.
 """
 from __future__ import annotations
 
+import gc
 import statistics
+import time
 
 import numpy as np
 
@@ -60,6 +62,7 @@ class Suite:
         self.scale = scale
         self.dist = None
         self.last_phases = None
+        self.last_host_ms = []
         if world > 1:
             import torch.distributed as dist
             self.dist = dist
@@ -96,18 +99,32 @@ class Suite:
             fn().free()
         self.last_phases = self._trace(fn)
         ms_all, r, st = [], None, None
-        for _ in range(reps or self.reps):
-            if r is not None:
-                r.free()
-            self.barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            r = fn()
-            e1.record()
-            self.barrier()
-            ms_all.append(self.allmax(e0.elapsed_time(e1)))
-            if self.world == 1:
-                st = self.env.stats()
+        self.last_host_ms = []   # host time of fn() per run, max over ranks: tells a launch-side stall from a device one
+        # Python's cyclic collector stays off inside the timed runs (as timeit does): at 8 GPUs a collection that landed in
+        # one rank's run — finalizers of the previous query's tensors and table handles — stalled that rank's launches for
+        # ~50 ms and, through the collectives, every rank's device time (profiles/r02_s_bench_n8.json, join strong).
+        gc.collect()
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+            for _ in range(reps or self.reps):
+                if r is not None:
+                    r.free()
+                self.barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0 = time.perf_counter()
+                e0.record()
+                r = fn()
+                e1.record()
+                host_ms = (time.perf_counter() - t0) * 1e3
+                self.barrier()
+                ms_all.append(self.allmax(e0.elapsed_time(e1)))
+                self.last_host_ms.append(round(self.allmax(host_ms), 3))
+                if self.world == 1:
+                    st = self.env.stats()
+        finally:
+            if gc_was_on:
+                gc.enable()
         return statistics.median(ms_all), [round(x, 3) for x in ms_all], r, st
 
     def roofline(self, alg_bytes, ms, st, kernel):
@@ -197,6 +214,7 @@ class Suite:
              "roofline": self.roofline(alg, ms, st, "hk_tpart_kernel + hk_dagg_kernel (K8t + K2)")}
         if sharded:
             d["phases_ms"] = self.last_phases
+            d["host_ms_all"] = self.last_host_ms
             d["nvlink_bytes_per_gpu"] = int(n_groups * 24 * (self.world - 1) / self.world)
         r.free()
         t.free()
@@ -269,6 +287,7 @@ class Suite:
                                             "+ 16 B read + 16 B write) per row at the measured peak")
         if sharded:
             d["phases_ms"] = self.last_phases
+            d["host_ms_all"] = self.last_host_ms
             d["rank0_load_vs_even"] = a.shape[0] / max(per, 1)
             d["nvlink_bytes_per_gpu"] = int(per * 16 * (self.world - 1) / self.world)
             self._nvlink(d, ("peer_scatter", "exchange"))
@@ -339,6 +358,7 @@ class Suite:
              "roofline": self.roofline(8 * total + 8 * nd, ms, st, "hk_tpart_kernel + hk_dagg_kernel (probe + aggregate)")}
         if sharded:
             d["phases_ms"] = self.last_phases
+            d["host_ms_all"] = self.last_host_ms
             d["nvlink_bytes_per_gpu"] = int(nd_per * 8 * (self.world - 1))
             self._nvlink(d, ("allgather_dim",))
         r.free()
