@@ -3,6 +3,7 @@
 // Replaces what futhark_ffi + the generated C API do around the entries in the reference:
 // futhark_context_new (FutharkContext.py:41), futhark_new_*_2d (the per-query copy-in at
 // FutharkContext.py:65,70), futhark_values_* / futhark_shape_* (from_futhark, :66,71).
+#include <chrono>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -21,9 +22,36 @@ static thread_local char g_init_err[512] = "";
 int hark_ctx::dalloc(void **p, size_t bytes) {
     bytes = (bytes + 255) & ~(size_t)255; // padded: a 16-byte group load of a ragged column end stays in bounds
     if (bytes == 0) bytes = 256;
+    // a cached block of this size, or up to 1/8 larger
+    if (opt("pool.cache", 1) != 0) {
+        auto it = free_blocks.lower_bound(bytes);
+        if (it != free_blocks.end() && it->first <= bytes + bytes / 8) {
+            *p = it->second;
+            cached_bytes -= it->first;
+            live_blocks[*p] = it->first;
+            free_blocks.erase(it);
+            return HARK_OK;
+        }
+    }
+    static const bool trace_alloc = getenv("HARK_TRACE_ALLOC") != nullptr; // diagnosis: allocations that take > 0.5 ms of host time
+    const auto t0 = std::chrono::steady_clock::now();
     cudaError_t e = cudaMallocFromPoolAsync(p, bytes, pool, stream);
-    if (e == cudaErrorMemoryAllocation) { // fragmented pool: hand every free block back to the driver and retry once
+    if (trace_alloc) {
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (ms > 0.5) {
+            uint64_t res = 0, used = 0, high = 0;
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &res);
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemHigh, &high);
+            size_t fr = 0, tot = 0;
+            cudaMemGetInfo(&fr, &tot);
+            fprintf(stderr, "[hark] dalloc %zu bytes took %.2f ms (device %d): pool reserved %.2f GB (high %.2f), used %.2f GB, device free %.1f GB\n",
+                    bytes, ms, device, res / 1073741824.0, high / 1073741824.0, used / 1073741824.0, fr / 1073741824.0);
+        }
+    }
+    if (e == cudaErrorMemoryAllocation) { // out of memory or fragmented: give everything unused back to the driver, retry once
         cudaGetLastError();
+        release_cached_blocks();
         cudaStreamSynchronize(stream);
         cudaMemPoolTrimTo(pool, 0);
         e = cudaMallocFromPoolAsync(p, bytes, pool, stream);
@@ -35,11 +63,42 @@ int hark_ctx::dalloc(void **p, size_t bytes) {
         snprintf(buf, sizeof buf, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
         return fail(e == cudaErrorMemoryAllocation ? HARK_ERR_OOM : HARK_ERR_CUDA, buf);
     }
+    live_blocks[*p] = bytes;
     return HARK_OK;
 }
 
 void hark_ctx::dfree(void *p) {
-    if (p) cudaFreeAsync(p, stream);
+    if (!p) return;
+    auto it = live_blocks.find(p);
+    if (it == live_blocks.end()) { // not from dalloc (should not happen): the driver knows what to do
+        cudaFreeAsync(p, stream);
+        return;
+    }
+    const size_t bytes = it->second;
+    live_blocks.erase(it);
+    // Blocks above pool.cache_block_gb (default 12) are not kept: memory in this cache is invisible to the driver, which
+    // CAN hand unused pool memory to another allocator in the process (torch's cudaMalloc) when the device runs out —
+    // a one-GPU 2e9-row sort frees 32 GB blocks that the caller's own tensors may need next.
+    if (opt("pool.cache", 1) == 0 || bytes > ((size_t)opt("pool.cache_block_gb", 12) << 30)) {
+        cudaFreeAsync(p, stream);
+        return;
+    }
+    free_blocks.emplace(bytes, p);
+    cached_bytes += bytes;
+    // bounded: beyond pool.cache_gb (default 48) the largest cached blocks go back to the driver's pool
+    const size_t cap = (size_t)opt("pool.cache_gb", 48) << 30;
+    while (cached_bytes > cap && !free_blocks.empty()) {
+        auto last = std::prev(free_blocks.end());
+        cudaFreeAsync(last->second, stream);
+        cached_bytes -= last->first;
+        free_blocks.erase(last);
+    }
+}
+
+void hark_ctx::release_cached_blocks() {
+    for (auto &kv : free_blocks) cudaFreeAsync(kv.second, stream);
+    free_blocks.clear();
+    cached_bytes = 0;
 }
 
 void hark_ctx::entry_begin() {
@@ -144,6 +203,7 @@ extern "C" hark_ctx *hark_context_new(int device, void *stream) {
 extern "C" void hark_context_free(hark_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    ctx->release_cached_blocks();
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     hk_peer_destroy(ctx);
     if (ctx->copy_stream) {
@@ -173,6 +233,7 @@ extern "C" int hark_context_sync(hark_ctx *ctx) {
 
 extern "C" int hark_context_trim(hark_ctx *ctx) {
     HK_ENTER(ctx);
+    ctx->release_cached_blocks();
     HK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     HK_CUDA(ctx, cudaMemPoolTrimTo(ctx->pool, 0));
     return HARK_OK;
@@ -194,7 +255,7 @@ extern "C" int hark_context_set_option(hark_ctx *ctx, const char *key, int64_t v
                                   "join.impl",   "upload.chunk_mb",    "dense.log2_slots",  "dense.smem_bytes",
                                   "part.ctas_per_sm", "part.threads", "join.lut_slice_bytes", "sort.impl", "sort.rank", "stats.cache",
                                   "sort.trunc", "sort.trunc_slack", "dense.part_impl", "join.build", "dense.fixed_point",
-                                  "sort.digit_bits", "dense.spec", "sort.fuse2", "sort.sweep16", "sort.sweep16_min_rows", "join.build_partition", "join.build_partition_min_rows", "sort.straddle", "sort.sweep16_fast", "sort.fix_fast", "dense.dynamic", nullptr};
+                                  "sort.digit_bits", "dense.spec", "sort.fuse2", "sort.sweep16", "sort.sweep16_min_rows", "join.build_partition", "join.build_partition_min_rows", "sort.straddle", "sort.sweep16_fast", "sort.fix_fast", "dense.dynamic", "pool.cache", "pool.cache_gb", "pool.cache_block_gb", nullptr};
     for (int i = 0; known[i]; i++)
         if (!strcmp(known[i], key)) {
             ctx->opts[key] = value;

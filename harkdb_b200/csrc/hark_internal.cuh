@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <map>
+#include <unordered_map>
 #include <string>
 #include <vector>
 
@@ -72,9 +73,18 @@ struct hark_ctx {
         return it == opts.end() ? dflt : it->second;
     }
     // stream-ordered allocation from the context's pool (never returns memory to the OS until
-    // the context dies: repeated queries do not pay cudaMalloc/cudaFree)
+    // the context dies: repeated queries do not pay cudaMalloc/cudaFree).  On top of the driver's pool sits a cache of
+    // freed blocks by size (r2): a block of a size seen before is handed out again without a driver call.  The
+    // driver's own reuse re-maps physical pages whenever a request fits no free range exactly, and that showed up as
+    // 13 ms for a 2 GB block and 27 ms for an 8 GB one, every query, in the NCCL exchange path
+    // (profiles/r02_ai_alloc_trace.txt).  Safe because every kernel that touches pool memory runs on `stream`, in host
+    // program order (the upload / download staging on copy_stream is synchronised before its buffers are freed).
     int dalloc(void **p, size_t bytes);
     void dfree(void *p);
+    void release_cached_blocks();          // hand every cached block back to the driver's pool
+    std::unordered_map<void *, size_t> live_blocks;   // size of every block handed out
+    std::multimap<size_t, void *> free_blocks;         // cached blocks by size
+    size_t cached_bytes = 0;
     void count_launch(int n = 1) {
         total_launches += n;
         entry_launches += n;

@@ -518,16 +518,26 @@ __global__ void __launch_bounds__(256) hk_mj_expand_kernel(const __grid_constant
 constexpr int HJ_T = 256, HJ_I = 4, HJ_TILE = HJ_T * HJ_I;
 
 // multiset build: every row gets its own entry (duplicates share a probe sequence)
+// *dup is raised when two build rows carry the same 4-byte key (the later one meets the earlier one's entry on its way
+// to a free slot): a table WITHOUT duplicates lets a probe stop at its first match instead of walking on to the next
+// empty slot.  8-byte keys are stored after their entry is claimed, so they cannot be compared here: *dup is set.
 template <int KW>
-__global__ void __launch_bounds__(256) hk_hj_build_kernel(const void *key_col, int64_t n, void *htab, unsigned long long hmask) {
+__global__ void __launch_bounds__(256) hk_hj_build_kernel(const void *key_col, int64_t n, void *htab, unsigned long long hmask,
+                                                          unsigned int *dup) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     unsigned long long *t = reinterpret_cast<unsigned long long *>(htab);
+    if (KW == 8 && blockIdx.x == 0 && threadIdx.x == 0) *dup = 1u;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         if constexpr (KW == 4) {
             const uint32_t key = reinterpret_cast<const uint32_t *>(key_col)[i];
             const unsigned long long packed = (unsigned long long)key | ((unsigned long long)(uint32_t)(i + 1) << 32);
             unsigned long long h = hk_hash_key<4>(key) & hmask;
-            while (atomicCAS(t + h, 0ull, packed) != 0ull) h = (h + 1) & hmask;
+            while (true) {
+                const unsigned long long old = atomicCAS(t + h, 0ull, packed);
+                if (old == 0ull) break;
+                if ((uint32_t)old == key) *dup = 1u;
+                h = (h + 1) & hmask;
+            }
         } else {
             const unsigned long long key = reinterpret_cast<const unsigned long long *>(key_col)[i];
             unsigned long long h = hk_hash_key<8>(key) & hmask;
@@ -553,15 +563,21 @@ __device__ __forceinline__ typename HjEntry<KW>::T hj_first(const void *htab, un
 // visits the build rows matching `key`, starting from the preloaded first entry; F(row) for each
 template <int KW, typename F>
 __device__ __forceinline__ void hj_for_matches(const void *htab, unsigned long long hmask, typename JRaw<KW>::T key,
-                                               typename HjEntry<KW>::T e, unsigned long long h, F f) {
+                                               typename HjEntry<KW>::T e, unsigned long long h, F f, bool first_only = false) {
     const typename HjEntry<KW>::T *t = reinterpret_cast<const typename HjEntry<KW>::T *>(htab);
     while (true) {
         if constexpr (KW == 4) {
             if (e.y == 0u) return;
-            if (e.x == key) f((int64_t)e.y - 1);
+            if (e.x == key) {
+                f((int64_t)e.y - 1);
+                if (first_only) return;
+            }
         } else {
             if ((uint32_t)e.y == 0u) return;
-            if (e.x == key) f((int64_t)(uint32_t)e.y - 1);
+            if (e.x == key) {
+                f((int64_t)(uint32_t)e.y - 1);
+                if (first_only) return;
+            }
         }
         h = (h + 1) & hmask;
         e = __ldg(t + h);
@@ -577,6 +593,7 @@ struct HjParams {
     uint64_t *state;
     unsigned long long *ticket;
     int64_t num_tiles;
+    const unsigned int *dup; // 0: the build keys are unique
     JoinCols C;
 };
 
@@ -586,6 +603,7 @@ __global__ void __launch_bounds__(HJ_T) hk_hj_count_kernel(const __grid_constant
     __shared__ unsigned long long s_w[HJ_T / 32];
     __shared__ long long s_tile;
     const KT *k1 = reinterpret_cast<const KT *>(P.k1);
+    const bool unique = *P.dup == 0u;
     while (true) {
         if (threadIdx.x == 0) s_tile = (long long)atomicAdd(P.ticket, 1ull);
         __syncthreads();
@@ -606,7 +624,7 @@ __global__ void __launch_bounds__(HJ_T) hk_hj_count_kernel(const __grid_constant
 #pragma unroll
         for (int e = 0; e < HJ_I; e++) {
             const int64_t i = i0 + e * HJ_T + threadIdx.x;
-            if (i < P.n1) hj_for_matches<KW>(P.htab, P.hmask, key[e], e0[e], h0[e], [&](int64_t) { mine++; });
+            if (i < P.n1) hj_for_matches<KW>(P.htab, P.hmask, key[e], e0[e], h0[e], [&](int64_t) { mine++; }, unique);
         }
         unsigned long long total;
         mj_block_excl_scan(mine, s_w, &total);
@@ -627,6 +645,7 @@ __global__ void __launch_bounds__(HJ_T) hk_hj_expand_kernel(const __grid_constan
     __shared__ unsigned long long s_w[HJ_T / 32];
     const KT *k1 = reinterpret_cast<const KT *>(P.k1);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool unique = *P.dup == 0u;
     for (int64_t tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
         // a warp owns 128 consecutive probe rows, striped over its lanes (row = warp range + e * 32 + lane): loads and —
         // with one match per row — stores coalesce, and the result stays grouped by probe row in row order
@@ -635,6 +654,7 @@ __global__ void __launch_bounds__(HJ_T) hk_hj_expand_kernel(const __grid_constan
         typename HjEntry<KW>::T e0[HJ_I];
         unsigned long long h0[HJ_I];
         unsigned long long cnt[HJ_I], off[HJ_I], wsum = 0;
+        uint32_t m0[HJ_I];
 #pragma unroll
         for (int e = 0; e < HJ_I; e++) {
             const int64_t i = i0 + e * 32 + lane;
@@ -646,7 +666,11 @@ __global__ void __launch_bounds__(HJ_T) hk_hj_expand_kernel(const __grid_constan
         for (int e = 0; e < HJ_I; e++) {
             const int64_t i = i0 + e * 32 + lane;
             cnt[e] = 0;
-            if (i < P.n1) hj_for_matches<KW>(P.htab, P.hmask, key[e], e0[e], h0[e], [&](int64_t) { cnt[e]++; });
+            m0[e] = 0;
+            if (i < P.n1)
+                hj_for_matches<KW>(P.htab, P.hmask, key[e], e0[e], h0[e], [&](int64_t r2) {
+                    if (cnt[e]++ == 0) m0[e] = (uint32_t)r2;
+                }, unique);
             unsigned long long inc = cnt[e]; // inclusive warp scan in lane order
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -666,10 +690,14 @@ __global__ void __launch_bounds__(HJ_T) hk_hj_expand_kernel(const __grid_constan
             const int64_t i = i0 + e * 32 + lane;
             if (i < P.n1 && cnt[e]) {
                 unsigned long long run = wbase + off[e];
-                hj_for_matches<KW>(P.htab, P.hmask, key[e], e0[e], h0[e], [&](int64_t r2) {
-                    join_emit(P.C, (int64_t)run, i, r2);
-                    run++;
-                });
+                if (cnt[e] == 1) { // the common case (a key of the build side occurs once): no second walk
+                    join_emit(P.C, (int64_t)run, i, (int64_t)m0[e]);
+                } else {
+                    hj_for_matches<KW>(P.htab, P.hmask, key[e], e0[e], h0[e], [&](int64_t r2) {
+                        join_emit(P.C, (int64_t)run, i, r2);
+                        run++;
+                    });
+                }
             }
         }
     }
@@ -816,12 +844,16 @@ int hk_join_ex(hark_ctx *ctx, hark_table **out, const hark_table *db1, const har
         void *tab = nullptr;
         HK_TRY(bufs.alloc(&tab, (size_t)H * esz));
         HK_CUDA(ctx, cudaMemsetAsync(tab, 0, (size_t)H * esz, ctx->stream));
+        unsigned int *dup = nullptr;
+        HK_TRY(bufs.alloc((void **)&dup, sizeof(unsigned int)));
+        HK_CUDA(ctx, cudaMemsetAsync(dup, 0, sizeof(unsigned int), ctx->stream));
         ctx->kernel_begin();
-        if (kw == 4) hk_hj_build_kernel<4><<<grid_for(ctx, n2), 256, 0, ctx->stream>>>(db2->cols[col2].ptr, n2, tab, H - 1);
-        else hk_hj_build_kernel<8><<<grid_for(ctx, n2), 256, 0, ctx->stream>>>(db2->cols[col2].ptr, n2, tab, H - 1);
+        if (kw == 4) hk_hj_build_kernel<4><<<grid_for(ctx, n2), 256, 0, ctx->stream>>>(db2->cols[col2].ptr, n2, tab, H - 1, dup);
+        else hk_hj_build_kernel<8><<<grid_for(ctx, n2), 256, 0, ctx->stream>>>(db2->cols[col2].ptr, n2, tab, H - 1, dup);
         HK_CHECK_LAUNCH(ctx);
         HjParams J;
         memset(&J, 0, sizeof J);
+        J.dup = dup;
         J.k1 = db1->cols[col1].ptr;
         J.n1 = n1;
         J.htab = tab;

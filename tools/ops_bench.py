@@ -279,9 +279,12 @@ def main():
     ap.add_argument("--out", default="")
     ap.add_argument("--opt", action="append", default=[], help="key=value context option")
     ap.add_argument("--cpu-rows", type=int, default=0, help="also time the CPU port on this many rows (e.g. 16777216)")
+    ap.add_argument("--own-stream", action="store_true",
+                    help="let libhark create its own stream; default: torch's current stream (what bench.py and ShardedEnv do), "
+                         "so that the torch events tools/query_suite.py times with see the kernels")
     args = ap.parse_args()
     from harkdb_b200 import hark_ffi
-    env = hark_ffi.Futhark()
+    env = hark_ffi.Futhark() if args.own_stream else hark_ffi.Futhark(stream=hark_ffi.torch_stream_handle())
     for kv in args.opt:
         k, v = kv.split("=")
         env.set_option(k, int(v))
@@ -317,6 +320,12 @@ def main():
         except Exception as e:  # keep going: one OOM must not hide the other operators' numbers
             print(json.dumps({"op": op, "error": repr(e)[:400]}), flush=True)
             res.append({"op": op, "error": repr(e)[:400]})
+        try:            # the next operator has other sizes: start it from an empty pool
+            env.trim()
+            import torch
+            torch.cuda.empty_cache()
+        except Exception:
+            pass
     if args.out:
         json.dump(res, open(args.out, "w"), indent=1)
 
