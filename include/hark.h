@@ -124,10 +124,11 @@ int hark_abi_version(void);
 hark_ctx *hark_context_new(int device, void *stream);
 void hark_context_free(hark_ctx *ctx);
 int hark_context_sync(hark_ctx *ctx);
-/* The context's stream-ordered memory pool keeps freed blocks for the next query (no cudaMalloc in steady state).  This
- * hands every free block back to the driver (after a synchronize) — for callers that switch between workloads of very
- * different sizes on a nearly full device, where cached blocks of the old sizes would otherwise force a trim + re-grow
- * inside a query.                                                                                                     */
+/* The context's stream-ordered memory pool keeps freed blocks for the next query (no cudaMalloc in steady state), and a
+ * cache of freed blocks by size sits on top of it (blocks <= "pool.cache_block_gb" = 12, at most "pool.cache_gb" = 48 in
+ * total; "pool.cache" = 0 switches it off): memory in that cache is not visible to other allocators in the process.  This
+ * call empties the cache and hands every free block back to the driver (after a synchronize) — for callers that switch
+ * between workloads of very different sizes on a nearly full device, or that need the memory for their own tensors.      */
 int hark_context_trim(hark_ctx *ctx);
 char *hark_context_get_error(hark_ctx *ctx); /* malloc'd, caller frees; NULL if no error      */
 int hark_context_device(hark_ctx *ctx);
@@ -259,8 +260,9 @@ int hark_table_concat(hark_ctx *ctx, hark_table **out, const hark_table *a, cons
 /* ---- measurement ---- */
 int hark_stats_last(hark_ctx *ctx, hark_stats *out);
 int64_t hark_stats_total_launches(hark_ctx *ctx);
-/* Tuning knobs for experiments ("filter.impl", "filter.ctas_per_sm", ...); returns HARK_ERR_ARG
- * for an unknown key.                                                                          */
+/* Tuning knobs for experiments ("filter.impl", "filter.ctas_per_sm", "dense.dynamic", "sort.straddle", "join.build",
+ * "pool.cache", ...: the list is `known[]` in csrc/context.cu, every one is described where DESIGN.md discusses its
+ * kernel); returns HARK_ERR_ARG for an unknown key.                                             */
 int hark_context_set_option(hark_ctx *ctx, const char *key, int64_t value);
 /* Reads back an option, or one of the read-only counters the last sort left behind: "sort.last_passes",
  * "sort.last_truncated" (1: only the top digits were sorted and ties repaired), "sort.last_fix_runs",

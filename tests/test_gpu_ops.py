@@ -796,6 +796,117 @@ def test_groupby_tile_partition_vs_chunk_partition(part_impl, kdt, vdts, n):
     r.free(); t.free()
 
 
+@pytest.mark.parametrize("dynamic", [1, 0])
+@pytest.mark.parametrize("skew", ["uniform", "zipf", "one_bin"])
+def test_groupby_tiles_dealt_units_vs_static_split(dynamic, skew):
+    """K2 over K8t tiles with per-bin ticket dealing (dense.dynamic=1, default) and with the static split by rows (=0):
+    same result on uniform keys, on Zipf-like keys (a few hot groups) and when every row falls into one bin."""
+    env = get_env()
+    rng = np.random.default_rng(11)
+    n = 300007
+    if skew == "uniform":
+        key = rng.integers(-3000, 3000, n)
+    elif skew == "zipf":
+        key = np.minimum(rng.zipf(1.3, n), 5999) - 3000
+    else:
+        key = rng.integers(100, 140, n)
+        key[::1001] = 2999
+        key[5] = -3000
+    cols = [key.astype(np.int32), rng.integers(-1000, 1000, n).astype(np.int32), rng.random(n).astype(np.float32)]
+    sc, ops = [1, 1, 2, 0], [NO.AGG_SUM, NO.AGG_MIN, NO.AGG_SUM, NO.AGG_COUNT]
+    t = env.from_columns(cols)
+    env.set_option("dense.log2_slots", 8)
+    env.set_option("dense.dynamic", dynamic)
+    try:
+        r = env.query_groupby_ex(t, 0, sc, ops)
+    finally:
+        env.set_option("dense.log2_slots", 0)
+        env.set_option("dense.dynamic", 1)
+    _check_cols(r.columns(), NO.query_groupby_ex(cols, 0, sc, ops))
+    r.free(); t.free()
+
+
+def test_block_cache_reuses_and_trims():
+    """The size-keyed cache of freed device blocks: results do not depend on it, a repeated query reuses
+    its blocks, trim() empties it, blocks above pool.cache_block_gb bypass it."""
+    env = get_env()
+    rng = np.random.default_rng(12)
+    n = 200003
+    cols = [rng.integers(0, 50, n).astype(np.int32), rng.integers(-2 ** 40, 2 ** 40, n).astype(np.int64)]
+    exp = NO.query_orderby(cols, [0, 1], [0, 1], [0, 1])
+    t = env.from_columns(cols)
+    for cache in (1, 0, 1):
+        env.set_option("pool.cache", cache)
+        for _ in range(3):
+            r = env.query_orderby(t, [0, 1], [0, 1], [0, 1])
+            for g, e in zip(r.columns(), exp):
+                assert np.array_equal(g, e)
+            r.free()
+        env.trim()
+    env.set_option("pool.cache_block_gb", 0)        # nothing is cacheable: every block goes back to the driver's pool
+    try:
+        r = env.query_orderby(t, [0, 1], [0, 1], [0, 1])
+        assert np.array_equal(r.column(1), exp[1])
+        r.free()
+    finally:
+        env.set_option("pool.cache_block_gb", 12)
+    t.free()
+
+
+@pytest.mark.parametrize("kdt", [NO.I32, NO.I64])
+@pytest.mark.parametrize("dups", [False, True])
+def test_hash_join_unique_and_duplicate_build_keys(kdt, dups):
+    """hark_entry_join_ex, order = 0: the build raises a duplicate flag (4-byte keys); without duplicates probes stop at
+    the first match, with duplicates they walk the whole cluster.  Misses, negative keys, one heavy duplicate key."""
+    env = get_env()
+    rng = np.random.default_rng(13 + int(dups))
+    n2, n1 = 5003, 60011
+    base = rng.permutation(40000)[:n2] - 20000
+    if dups:
+        base[::7] = base[3]                      # one key carried by many build rows
+        base[1::11] = base[1]
+    k2 = base.astype(NO.NP_DTYPES[kdt])
+    k1 = rng.integers(-25000, 25000, n1).astype(NO.NP_DTYPES[kdt])   # ~20 % of the probe keys miss
+    t1 = [k1, rng.integers(0, 1000, n1).astype(np.int32)]
+    t2 = [k2, np.arange(n2, dtype=np.int32)]
+    d1, d2 = env.from_columns(t1), env.from_columns(t2)
+    got = env.join_ex(d1, d2, 0, 0, [0, 1], [1], 0).columns()
+    exp = NO.join_ex(t1, t2, 0, 0, [0, 1], [1])
+    assert len(got[0]) == len(exp[0])
+    o1, o2 = np.lexsort((got[2], got[1], got[0])), np.lexsort((exp[2], exp[1], exp[0]))
+    for g, e in zip(got, exp):
+        assert np.array_equal(g[o1], e[o2])
+    d1.free(); d2.free()
+
+
+@pytest.mark.parametrize("carry", [1, 0])
+@pytest.mark.parametrize("cols1", [[0, 1], [1, 1, 0, 2], [3, 2, 1, 0, 4], [2]])
+def test_ordered_join_carries_left_columns_through_the_sort(carry, cols1):
+    """hark_entry_join_ex, order = 1 (reference order): the projected left columns ride through the sort instead of a row
+    id (join.carry=1, default) when at most 3 distinct non-key columns are projected; same rows, same order either way.
+    Mixed widths, a column projected twice, the key column projected, more columns than are carried."""
+    env = get_env()
+    rng = np.random.default_rng(21)
+    n1, n2 = 30011, 4001
+    t1 = [rng.integers(-200, 200, n1).astype(np.int32), rng.integers(-2 ** 50, 2 ** 50, n1).astype(np.int64),
+          rng.random(n1).astype(np.float32), rng.random(n1), np.arange(n1, dtype=np.int32)]
+    t2 = [rng.integers(-250, 150, n2).astype(np.int32), np.arange(n2, dtype=np.int64)]
+    d1, d2 = env.from_columns(t1), env.from_columns(t2)
+    env.set_option("join.carry", carry)
+    try:
+        got = env.join_ex(d1, d2, 0, 0, cols1, [1, 0], 1).columns()
+        carried = env.get_option("join.last_carry")
+    finally:
+        env.set_option("join.carry", 1)
+    distinct = len({c for c in cols1 if c != 0})
+    assert carried == (1 if carry and distinct <= 3 else 0)
+    exp = NO.join_ex(t1, t2, 0, 0, cols1, [1, 0])
+    assert len(got) == len(exp)
+    for g, e in zip(got, exp):
+        assert g.dtype == e.dtype and np.array_equal(g, e)
+    d1.free(); d2.free()
+
+
 # ---------------------------------------------------------------- SQL through FutharkContext
 def test_sql_groupby_orderby_join():
     import pandas as pd
