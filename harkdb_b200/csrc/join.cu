@@ -639,6 +639,75 @@ __global__ void __launch_bounds__(HJ_T) hk_hj_count_kernel(const __grid_constant
     }
 }
 
+// Unique build keys (the duplicate flag stayed down): every probe row has 0 or 1 match, so count, look-back and emit fit
+// in ONE pass over the probe side — the table is walked once per row instead of twice, and the host allocates the result
+// for n1 rows up front (its row count is set afterwards).  Rows are warp-striped like in hk_hj_expand_kernel, so the
+// result keeps probe-row order and the stores coalesce.
+template <int KW>
+__global__ void __launch_bounds__(HJ_T) hk_hj_unique_kernel(const __grid_constant__ HjParams P) {
+    using KT = typename JRaw<KW>::T;
+    __shared__ unsigned long long s_w[HJ_T / 32];
+    __shared__ long long s_tile;
+    __shared__ unsigned long long s_base;
+    const KT *k1 = reinterpret_cast<const KT *>(P.k1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    while (true) {
+        if (threadIdx.x == 0) s_tile = (long long)atomicAdd(P.ticket, 1ull); // tiles in order: the look-back never waits on a tile that has not started
+        __syncthreads();
+        const int64_t tile = s_tile;
+        if (tile >= P.num_tiles) break;
+        const int64_t i0 = tile * HJ_TILE + (int64_t)warp * (32 * HJ_I);
+        KT key[HJ_I];
+        typename HjEntry<KW>::T e0[HJ_I];
+        unsigned long long h0[HJ_I];
+        uint32_t m0[HJ_I], off[HJ_I], hit = 0, wsum = 0;
+#pragma unroll
+        for (int e = 0; e < HJ_I; e++) {
+            const int64_t i = i0 + e * 32 + lane;
+            key[e] = i < P.n1 ? k1[i] : (KT)0;
+        }
+#pragma unroll
+        for (int e = 0; e < HJ_I; e++) e0[e] = hj_first<KW>(P.htab, P.hmask, key[e], &h0[e]);
+#pragma unroll
+        for (int e = 0; e < HJ_I; e++) {
+            const int64_t i = i0 + e * 32 + lane;
+            bool found = false;
+            m0[e] = 0;
+            if (i < P.n1)
+                hj_for_matches<KW>(P.htab, P.hmask, key[e], e0[e], h0[e], [&](int64_t r2) {
+                    m0[e] = (uint32_t)r2;
+                    found = true;
+                }, true);
+            const uint32_t b = __ballot_sync(HK_FULL_MASK, found);
+            if (found) hit |= 1u << e;
+            off[e] = wsum + (uint32_t)__popc(b & lt_mask);
+            wsum += (uint32_t)__popc(b);
+        }
+        if (lane == 0) s_w[warp] = wsum;
+        __syncthreads();
+        unsigned long long wbase = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < HJ_T / 32; w++) {
+            const unsigned long long x = s_w[w];
+            if (w < warp) wbase += x;
+            total += x;
+        }
+        if (threadIdx.x < 32) {
+            const unsigned long long ex = hk_lookback_u64(P.state, tile, total);
+            if (threadIdx.x == 0) {
+                s_base = ex;
+                if (tile == P.num_tiles - 1) P.tile_base[P.num_tiles] = ex + total;
+            }
+        }
+        __syncthreads();
+        wbase += s_base;
+#pragma unroll
+        for (int e = 0; e < HJ_I; e++)
+            if (hit & (1u << e)) join_emit(P.C, (int64_t)(wbase + off[e]), i0 + e * 32 + lane, (int64_t)m0[e]);
+    }
+}
+
 template <int KW>
 __global__ void __launch_bounds__(HJ_T) hk_hj_expand_kernel(const __grid_constant__ HjParams P) {
     using KT = typename JRaw<KW>::T;
@@ -913,6 +982,33 @@ int hk_join_ex(hark_ctx *ctx, hark_table **out, const hark_table *db1, const har
         HK_CUDA(ctx, cudaMemsetAsync(J.state, 0, sizeof(uint64_t) * (size_t)(J.num_tiles + 1), ctx->stream));
         J.ticket = (unsigned long long *)(J.state + J.num_tiles);
         const unsigned g = (unsigned)std::min<int64_t>(J.num_tiles, (int64_t)ctx->num_sms * 8);
+        // the duplicate flag decides the plan: unique build keys -> one fused pass into a result allocated for n1 rows
+        HK_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, dup, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+        HK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const bool unique = *reinterpret_cast<const unsigned int *>(ctx->h_scalars) == 0u && ctx->opt("join.hash_one_pass", 1) != 0;
+        ctx->counters["join.last_one_pass"] = unique ? 1 : 0;
+        if (unique) {
+            HK_TRY(check_proj());
+            HK_TRY(hk_table_alloc(ctx, &t, n1, n1, odt.data(), l + k));
+            fill_join_cols(ctx, J.C, t, db1, db2, cols1, l, cols2, k);
+            if (kw == 4) hk_hj_unique_kernel<4><<<g, HJ_T, 0, ctx->stream>>>(J);
+            else hk_hj_unique_kernel<8><<<g, HJ_T, 0, ctx->stream>>>(J);
+            cudaError_t e = cudaGetLastError();
+            ctx->count_launch(2);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_scalars, J.tile_base + J.num_tiles, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) {
+                hk_table_free(ctx, t);
+                return ctx->fail(HARK_ERR_CUDA, std::string("join(hash, one pass): ") + cudaGetErrorString(e));
+            }
+            P = (int64_t)ctx->h_scalars[0];
+            t->n = P; // cap stays n1
+            ctx->kernel_end();
+            for (auto &c : t->cols) rowbytes += hk_dtype_size(c.dtype);
+            ctx->entry_end((int64_t)kw * (n1 + n2) + P * rowbytes * 2, n1 + n2, P);
+            *out = t;
+            return HARK_OK;
+        }
         if (kw == 4) hk_hj_count_kernel<4><<<g, HJ_T, 0, ctx->stream>>>(J);
         else hk_hj_count_kernel<8><<<g, HJ_T, 0, ctx->stream>>>(J);
         HK_CHECK_LAUNCH(ctx);

@@ -870,13 +870,27 @@ def test_hash_join_unique_and_duplicate_build_keys(kdt, dups):
     t1 = [k1, rng.integers(0, 1000, n1).astype(np.int32)]
     t2 = [k2, np.arange(n2, dtype=np.int32)]
     d1, d2 = env.from_columns(t1), env.from_columns(t2)
-    got = env.join_ex(d1, d2, 0, 0, [0, 1], [1], 0).columns()
+    r = env.join_ex(d1, d2, 0, 0, [0, 1], [1], 0)
+    got = r.columns()
+    # unique 4-byte build keys take the fused one-pass plan (result allocated for every probe row, row count set after)
+    assert env.get_option("join.last_one_pass") == (1 if (kdt == NO.I32 and not dups) else 0)
     exp = NO.join_ex(t1, t2, 0, 0, [0, 1], [1])
-    assert len(got[0]) == len(exp[0])
+    assert r.shape[0] == len(exp[0]) and len(got[0]) == len(exp[0])
+    if not dups:        # one match per row at most: the result keeps probe-row order
+        hit = np.isin(k1, k2)
+        assert np.array_equal(got[0], k1[hit]) and np.array_equal(got[1], t1[1][hit])
     o1, o2 = np.lexsort((got[2], got[1], got[0])), np.lexsort((exp[2], exp[1], exp[0]))
     for g, e in zip(got, exp):
         assert np.array_equal(g[o1], e[o2])
-    d1.free(); d2.free()
+    env.set_option("join.hash_one_pass", 0)     # the two-pass plan on the same input
+    try:
+        got2 = env.join_ex(d1, d2, 0, 0, [0, 1], [1], 0).columns()
+    finally:
+        env.set_option("join.hash_one_pass", 1)
+    o3 = np.lexsort((got2[2], got2[1], got2[0]))   # duplicates: the matches of one probe row come in the build's CAS order
+    for g, g2 in zip(got, got2):
+        assert np.array_equal(g, g2) if not dups else np.array_equal(g[o1], g2[o3])
+    r.free(); d1.free(); d2.free()
 
 
 @pytest.mark.parametrize("carry", [1, 0])
