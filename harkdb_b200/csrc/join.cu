@@ -520,13 +520,13 @@ constexpr int HJ_T = 256, HJ_I = 4, HJ_TILE = HJ_T * HJ_I;
 // multiset build: every row gets its own entry (duplicates share a probe sequence)
 // *dup is raised when two build rows carry the same 4-byte key (the later one meets the earlier one's entry on its way
 // to a free slot): a table WITHOUT duplicates lets a probe stop at its first match instead of walking on to the next
-// empty slot.  8-byte keys are stored after their entry is claimed, so they cannot be compared here: *dup is set.
+// empty slot.  8-byte keys are stored after their entry is claimed, so they cannot be compared here: a second launch
+// (hk_hj_dup8_kernel) looks every build row up in the finished table.
 template <int KW>
 __global__ void __launch_bounds__(256) hk_hj_build_kernel(const void *key_col, int64_t n, void *htab, unsigned long long hmask,
                                                           unsigned int *dup) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     unsigned long long *t = reinterpret_cast<unsigned long long *>(htab);
-    if (KW == 8 && blockIdx.x == 0 && threadIdx.x == 0) *dup = 1u;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         if constexpr (KW == 4) {
             const uint32_t key = reinterpret_cast<const uint32_t *>(key_col)[i];
@@ -543,6 +543,26 @@ __global__ void __launch_bounds__(256) hk_hj_build_kernel(const void *key_col, i
             unsigned long long h = hk_hash_key<8>(key) & hmask;
             while (atomicCAS(t + 2 * h + 1, 0ull, (unsigned long long)(uint32_t)(i + 1)) != 0ull) h = (h + 1) & hmask;
             t[2 * h] = key;
+        }
+    }
+}
+
+// 8-byte keys: a build row whose cluster holds another row with the same key raises *dup
+__global__ void __launch_bounds__(256) hk_hj_dup8_kernel(const void *key_col, int64_t n, const void *htab, unsigned long long hmask,
+                                                         unsigned int *dup) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const ulonglong2 *t = reinterpret_cast<const ulonglong2 *>(htab);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long key = reinterpret_cast<const unsigned long long *>(key_col)[i];
+        unsigned long long h = hk_hash_key<8>(key) & hmask;
+        while (true) {
+            const ulonglong2 e = __ldg(t + h);
+            if ((uint32_t)e.y == 0u) break;
+            if (e.x == key && (uint32_t)e.y != (uint32_t)(i + 1)) {
+                *dup = 1u;
+                break;
+            }
+            h = (h + 1) & hmask;
         }
     }
 }
@@ -969,6 +989,11 @@ int hk_join_ex(hark_ctx *ctx, hark_table **out, const hark_table *db1, const har
         if (kw == 4) hk_hj_build_kernel<4><<<grid_for(ctx, n2), 256, 0, ctx->stream>>>(db2->cols[col2].ptr, n2, tab, H - 1, dup);
         else hk_hj_build_kernel<8><<<grid_for(ctx, n2), 256, 0, ctx->stream>>>(db2->cols[col2].ptr, n2, tab, H - 1, dup);
         HK_CHECK_LAUNCH(ctx);
+        if (kw == 8) {
+            hk_hj_dup8_kernel<<<grid_for(ctx, n2), 256, 0, ctx->stream>>>(db2->cols[col2].ptr, n2, tab, H - 1, dup);
+            HK_CHECK_LAUNCH(ctx);
+            ctx->count_launch();
+        }
         HjParams J;
         memset(&J, 0, sizeof J);
         J.dup = dup;
