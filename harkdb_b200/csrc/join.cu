@@ -358,15 +358,41 @@ struct MjParams {
     uint64_t *state;     // look-back words, one per tile
     unsigned long long *ticket;
     int64_t num_tiles;
+    const long long *ranges; // [num_tiles][2] slice of k2 that can match the tile (hk_mj_tile_ranges_kernel)
 };
+
+// The slice of the sorted right side that can match left tile t: [lower_bound(first key), upper_bound(last key)).  One
+// thread per tile boundary: the ~24 dependent loads of a search over n2 run for all tiles at once instead of inside
+// every tile with 254 threads waiting at a barrier (ncu, round 2: barrier = 11.3 warps per issue in the bounds kernel).
+template <int KW>
+__global__ void __launch_bounds__(256) hk_mj_tile_ranges_kernel(const void *k1v, const void *k2v, int64_t n1, int64_t n2, int dtype,
+                                                                int64_t num_tiles, long long *ranges /* [num_tiles][2] */) {
+    using KT = typename JRaw<KW>::T;
+    const KT *k1 = reinterpret_cast<const KT *>(k1v), *k2 = reinterpret_cast<const KT *>(k2v);
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= 2 * num_tiles) return;
+    const int64_t tile = q >> 1;
+    const bool upper = q & 1;
+    const int64_t i = upper ? min(n1, (tile + 1) * (int64_t)MJ_TILE) - 1 : tile * (int64_t)MJ_TILE;
+    const uint64_t key = j_ord<KW>(k1[i], dtype);
+    int64_t lo = 0, hi = n2;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        const uint64_t x = j_ord<KW>(k2[mid], dtype);
+        if (upper ? (x <= key) : (x < key)) lo = mid + 1; else hi = mid;
+    }
+    ranges[q] = lo;
+}
+
+constexpr int MJ_STAGE = 4096; // right-side keys of a tile's slice staged in shared memory (order keys, 8 bytes each)
 
 template <int KW>
 __global__ void __launch_bounds__(MJ_T) hk_mj_bounds_kernel(const __grid_constant__ MjParams P) {
     using KT = typename JRaw<KW>::T;
     __shared__ unsigned long long s_w[MJ_T / 32];
     __shared__ long long s_tile;
-    __shared__ long long s_range[2];
     __shared__ unsigned long long s_excl;
+    __shared__ uint64_t s_k2[MJ_STAGE];
     const KT *k1 = reinterpret_cast<const KT *>(P.k1), *k2 = reinterpret_cast<const KT *>(P.k2);
     while (true) {
         if (threadIdx.x == 0) s_tile = (long long)atomicAdd(P.ticket, 1ull);
@@ -374,19 +400,11 @@ __global__ void __launch_bounds__(MJ_T) hk_mj_bounds_kernel(const __grid_constan
         const int64_t tile = s_tile;
         if (tile >= P.num_tiles) break;
         const int64_t i0 = tile * MJ_TILE, i1 = min(P.n1, i0 + MJ_TILE);
-        // ---- the slice of the right side that can match this tile: [lb(first key), ub(last key)) ----
-        if (threadIdx.x < 2) {
-            const uint64_t key = j_ord<KW>(threadIdx.x == 0 ? k1[i0] : k1[i1 - 1], P.dtype);
-            int64_t lo = 0, hi = P.n2;
-            while (lo < hi) {
-                const int64_t mid = (lo + hi) >> 1;
-                const uint64_t x = j_ord<KW>(k2[mid], P.dtype);
-                if (threadIdx.x == 0 ? (x < key) : (x <= key)) lo = mid + 1; else hi = mid;
-            }
-            s_range[threadIdx.x] = lo;
-        }
+        const int64_t L = P.ranges[2 * tile], U = P.ranges[2 * tile + 1];
+        const bool staged = U - L <= MJ_STAGE; // the usual case: the searches of the tile's rows run in shared memory
+        if (staged)
+            for (int64_t j = threadIdx.x; j < U - L; j += MJ_T) s_k2[j] = j_ord<KW>(k2[L + j], P.dtype);
         __syncthreads();
-        const int64_t L = s_range[0], U = s_range[1];
         uint32_t lbv[MJ_I];
         unsigned long long cnt[MJ_I], mine = 0;
 #pragma unroll
@@ -396,19 +414,36 @@ __global__ void __launch_bounds__(MJ_T) hk_mj_bounds_kernel(const __grid_constan
             cnt[e] = 0;
             if (i < i1) {
                 const uint64_t key = j_ord<KW>(k1[i], P.dtype);
-                int64_t lo = L, hi = U;
-                while (lo < hi) {
-                    const int64_t mid = (lo + hi) >> 1;
-                    if (j_ord<KW>(k2[mid], P.dtype) < key) lo = mid + 1; else hi = mid;
-                }
-                const int64_t lb = lo;
-                hi = U;
-                while (lo < hi) {
-                    const int64_t mid = (lo + hi) >> 1;
-                    if (j_ord<KW>(k2[mid], P.dtype) <= key) lo = mid + 1; else hi = mid;
+                int64_t lb, ub;
+                if (staged) {
+                    int lo = 0, hi = (int)(U - L);
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (s_k2[mid] < key) lo = mid + 1; else hi = mid;
+                    }
+                    lb = L + lo;
+                    hi = (int)(U - L);
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (s_k2[mid] <= key) lo = mid + 1; else hi = mid;
+                    }
+                    ub = L + lo;
+                } else {
+                    int64_t lo = L, hi = U;
+                    while (lo < hi) {
+                        const int64_t mid = (lo + hi) >> 1;
+                        if (j_ord<KW>(k2[mid], P.dtype) < key) lo = mid + 1; else hi = mid;
+                    }
+                    lb = lo;
+                    hi = U;
+                    while (lo < hi) {
+                        const int64_t mid = (lo + hi) >> 1;
+                        if (j_ord<KW>(k2[mid], P.dtype) <= key) lo = mid + 1; else hi = mid;
+                    }
+                    ub = lo;
                 }
                 lbv[e] = (uint32_t)lb;
-                cnt[e] = (unsigned long long)(lo - lb);
+                cnt[e] = (unsigned long long)(ub - lb);
             }
             mine += cnt[e];
         }
@@ -940,12 +975,21 @@ int hk_join_ex(hark_ctx *ctx, hark_table **out, const hark_table *db1, const har
         HK_TRY(bufs.alloc((void **)&M.state, sizeof(uint64_t) * (size_t)(M.num_tiles + 1)));
         HK_CUDA(ctx, cudaMemsetAsync(M.state, 0, sizeof(uint64_t) * (size_t)(M.num_tiles + 1), ctx->stream));
         M.ticket = (unsigned long long *)(M.state + M.num_tiles);
+        long long *ranges = nullptr;
+        HK_TRY(bufs.alloc((void **)&ranges, sizeof(long long) * 2 * (size_t)M.num_tiles));
+        M.ranges = ranges;
         ctx->kernel_begin();
-        const unsigned g = (unsigned)std::min<int64_t>(M.num_tiles, (int64_t)ctx->num_sms * 8);
+        {
+            const unsigned gr = (unsigned)((2 * M.num_tiles + 255) / 256);
+            if (kw == 4) hk_mj_tile_ranges_kernel<4><<<gr, 256, 0, ctx->stream>>>(k1, k2, n1, n2, kdt, M.num_tiles, ranges);
+            else hk_mj_tile_ranges_kernel<8><<<gr, 256, 0, ctx->stream>>>(k1, k2, n1, n2, kdt, M.num_tiles, ranges);
+            HK_CHECK_LAUNCH(ctx);
+        }
+        const unsigned g = (unsigned)std::min<int64_t>(M.num_tiles, (int64_t)ctx->num_sms * 6);
         if (kw == 4) hk_mj_bounds_kernel<4><<<g, MJ_T, 0, ctx->stream>>>(M);
         else hk_mj_bounds_kernel<8><<<g, MJ_T, 0, ctx->stream>>>(M);
         HK_CHECK_LAUNCH(ctx);
-        ctx->count_launch();
+        ctx->count_launch(2);
         HK_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, M.offs + n1, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
         HK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         P = (int64_t)ctx->h_scalars[0];
