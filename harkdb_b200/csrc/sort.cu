@@ -746,12 +746,17 @@ __global__ void __launch_bounds__(LT, 2) hk_lsd_scatter_kernel(const __grid_cons
 // and a run leaves the SM as ONE TMA bulk copy (cp.async.bulk shared -> global, SASS UBLKCP) issued by the thread that
 // owns the digit: 256 copies per 4096-row tile instead of 2 x 4096 look-up + store sequences.  A microbenchmark of
 // exactly this pattern (tools/micro/bulk_small.cu, profiles/r02_micro_tma_small_bulk_copies.txt) sustains 5.9 TB/s with
-// 256-byte runs.  With the write-out gone from the instruction stream the chunk histogram pre-pass goes too: tiles are
-// claimed in order from a ticket counter and find their base with a decoupled look-back per (tile, digit) over
-// status words (tag | flag | count) against the GLOBAL digit histograms, which are order-independent and therefore
-// computed once, up front, for all passes (one read of each key column).  The first pass reads the caller's SoA
-// columns, the last one writes SoA again (per-row stores), so nothing outside this file sees the AoS form.
-// Stability: tickets ascend with the input order, rows are warp-striped and ranked with ballots.
+// 256-byte runs.  Two protocols give a tile its global base per digit:
+//   CHUNKED (default)  a chunk histogram over the pass's input (hk_sweep16_hist_kernel) + scan, then every CTA walks its
+//                      contiguous chunk of tiles with running per-digit offsets; the next tile's rows are requested as
+//                      soon as the row registers are free;
+//   look-back (A/B)    global digit histograms of all passes up front (order-independent: one read of each key column),
+//                      tiles claimed in order from a ticket, a decoupled look-back per (tile, digit) over status words
+//                      (tag | flag | count).  Slower here: with ~300 tiles of 4096 rows in flight the look-back walks
+//                      ~100 predecessors of 2 KB each per tile.
+// The first pass reads the caller's SoA columns, the last one writes SoA again (per-row stores), so nothing outside this
+// file sees the AoS form.
+// Stability: chunks / tickets ascend with the input order, rows are warp-striped and ranked with ballots.
 // ------------------------------------------------------------------------------------------------
 struct SweepParams {
     DigitFn f;
