@@ -796,7 +796,7 @@ def test_groupby_tile_partition_vs_chunk_partition(part_impl, kdt, vdts, n):
     r.free(); t.free()
 
 
-@pytest.mark.parametrize("dynamic", [1, 0])
+@pytest.mark.parametrize("dynamic", [1, 2, 0])
 @pytest.mark.parametrize("skew", ["uniform", "zipf", "one_bin"])
 def test_groupby_tiles_dealt_units_vs_static_split(dynamic, skew):
     """K2 over K8t tiles with per-bin ticket dealing (dense.dynamic=1, default) and with the static split by rows (=0):
@@ -816,12 +816,14 @@ def test_groupby_tiles_dealt_units_vs_static_split(dynamic, skew):
     sc, ops = [1, 1, 2, 0], [NO.AGG_SUM, NO.AGG_MIN, NO.AGG_SUM, NO.AGG_COUNT]
     t = env.from_columns(cols)
     env.set_option("dense.log2_slots", 8)
-    env.set_option("dense.dynamic", dynamic)
+    env.set_option("dense.dynamic", 1 if dynamic else 0)
+    env.set_option("dense.home_by_rows", 1 if dynamic == 2 else 0)   # 2: dealt units, first bin from the row prefix
     try:
         r = env.query_groupby_ex(t, 0, sc, ops)
     finally:
         env.set_option("dense.log2_slots", 0)
         env.set_option("dense.dynamic", 1)
+        env.set_option("dense.home_by_rows", 0)
     _check_cols(r.columns(), NO.query_groupby_ex(cols, 0, sc, ops))
     r.free(); t.free()
 
