@@ -255,7 +255,7 @@ extern "C" int hark_context_set_option(hark_ctx *ctx, const char *key, int64_t v
                                   "join.impl",   "upload.chunk_mb",    "dense.log2_slots",  "dense.smem_bytes",
                                   "part.ctas_per_sm", "part.threads", "join.lut_slice_bytes", "sort.impl", "sort.rank", "stats.cache",
                                   "sort.trunc", "sort.trunc_slack", "dense.part_impl", "join.build", "dense.fixed_point",
-                                  "sort.digit_bits", "dense.spec", "sort.fuse2", "sort.sweep16", "sort.sweep16_min_rows", "join.build_partition", "join.build_partition_min_rows", "sort.straddle", "sort.sweep16_fast", "sort.fix_fast", "dense.dynamic", "pool.cache", "pool.cache_gb", "pool.cache_block_gb", "join.carry", "join.hash_one_pass", "dense.home_by_rows", nullptr};
+                                  "sort.digit_bits", "dense.spec", "sort.fuse2", "sort.sweep16", "sort.sweep16_min_rows", "join.build_partition", "join.build_partition_min_rows", "sort.straddle", "sort.sweep16_fast", "sort.fix_fast", "dense.dynamic", "pool.cache", "pool.cache_gb", "pool.cache_block_gb", "join.carry", "join.hash_one_pass", "dense.home_by_rows", "tpart.ctas_per_sm", nullptr};
     for (int i = 0; known[i]; i++)
         if (!strcmp(known[i], key)) {
             ctx->opts[key] = value;

@@ -485,7 +485,7 @@ __device__ __forceinline__ void tpart_tile(const TPartParams &P, const PartParam
 }
 
 template <int KW, int NV, bool HASH>
-__global__ void __launch_bounds__(TP_T, 2) hk_tpart_kernel(const __grid_constant__ TPartParams P) {
+__global__ void __launch_bounds__(TP_T, 3) hk_tpart_kernel(const __grid_constant__ TPartParams P) {
     using KT = typename KRaw<KW>::T;
     constexpr int RW = KW / 4 + NV;
     extern __shared__ __align__(128) uint32_t s_dyn32[]; // stage (TP_TILE rows x RW words), then the small arrays
@@ -629,10 +629,11 @@ int hk_tile_partition(hark_ctx *ctx, int64_t n, const void *key, int kw, const h
     P.n = n;
     P.nbins = spec.nbins;
     P.num_tiles = (n + TP_TILE - 1) / TP_TILE;
-    const int64_t max_ctas = (int64_t)ctx->num_sms * 2;
+    const int rw = kw / 4 + nv;
+    const int64_t ctas_per_sm = std::min<int64_t>(ctx->opt("tpart.ctas_per_sm", 3), rw <= 4 ? 3 : 2);
+    const int64_t max_ctas = (int64_t)ctx->num_sms * std::max<int64_t>(1, ctas_per_sm);
     P.tiles_per_cta = std::max<int64_t>(1, (P.num_tiles + max_ctas - 1) / max_ctas);
     const unsigned grid = (unsigned)((P.num_tiles + P.tiles_per_cta - 1) / P.tiles_per_cta);
-    const int rw = kw / 4 + nv;
     void *rows = nullptr, *dir = nullptr;
     HK_TRY(ctx->dalloc(&rows, (size_t)P.num_tiles * TP_TILE * rw * 4));
     int rc = ctx->dalloc(&dir, (size_t)P.num_tiles * spec.nbins * 4);
