@@ -207,7 +207,10 @@ int hark_entry_join_groupby(hark_ctx *ctx, hark_table **out, const hark_table *f
  *   order = 1: rows ordered as hark_entry_join does (join.fut:55-75: key ascending, then db1 row, then db2 row) — both
  *              sides sorted (K3) and merged; db1 and db2 below 2^32-1 rows;
  *   order = 0: hash build on db2 + probe with db1: rows grouped by db1 row, ascending, the matches of one db1 row in
- *              unspecified order (a multiset result); db1 of any size, db2 below 2^32-1 rows.                        */
+ *              unspecified order (a multiset result); db1 of any size, db2 below 2^32-1 rows.  When no key occurs
+ *              twice in db2 the join is one pass and its result columns are ALLOCATED for db1's row count (every probe
+ *              row can match once); the table reports the true row count.  "join.hash_one_pass" = 0 takes the
+ *              count-then-expand plan, which allocates exactly.                                                      */
 int hark_entry_join_ex(hark_ctx *ctx, hark_table **out, const hark_table *db1, const hark_table *db2, int32_t col1,
                        int32_t col2, const int32_t *cols1, int64_t l, const int32_t *cols2, int64_t k, int32_t order);
 

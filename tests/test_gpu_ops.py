@@ -331,6 +331,12 @@ def test_orderby_truncation_at_a_key_boundary_and_floats():
     payload = np.arange(n, dtype=np.int64)
     info = _check_orderby(env, [k0, k1, payload], [2, 1], [0, 1], [0, 1])
     assert info["truncated"] == 1 and info["passes"] == 3 and info["fix_runs"] > 0 and info["fallback"] == 0, info
+    # a signed 4-byte key, descending, as the last sorted key (the tie scan's 4-byte integer path, both directions)
+    k0s = (rng.integers(0, 1 << 24, n) - (1 << 23)).astype(np.int32)
+    k2 = rng.integers(-2 ** 62, 2 ** 62, n).astype(np.int64)
+    for d0 in (1, 0):
+        info = _check_orderby(env, [k0s, k2, payload], [2, 0], [0, 1], [d0, 1])
+        assert info["truncated"] == 1 and info["fix_runs"] > 0 and info["fallback"] == 0, info
     # f32 keys: clustered around a few exponents — whatever the planner decides, the order must be exact
     f = (rng.standard_normal(n) * 1e3).astype(np.float32)
     f[rng.integers(0, n, 30)] = np.nan
