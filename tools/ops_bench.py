@@ -75,40 +75,6 @@ def line(name, n, st, extra=None):
     return d
 
 
-def cpu_leg(kind, n_cpu):
-    """CPU numbers for the same query shapes on the box's host cores, bounded samples (oracle/ = the checker; this
-    and bench.py's cpu_baseline are the only places it is timed).  `ref_faithful` = oracle.c, the reference's own
-    algorithm (32 one-bit radix passes over rows, 1 thread, like `futhark c`); `numpy` = np_oracle (argsort-based)."""
-    from oracle import c_oracle as CO
-    from oracle import np_oracle as NO
-    out = {"rows": n_cpu, "cores": 1, "kind": "port"}
-    if kind == "groupby":
-        key = CO.synth_column(I32, dict(kind=0, lo=0, range=1 << 20), 42, 0, 0, n_cpu)
-        val = CO.synth_column(I32, dict(kind=0, lo=0, range=1000), 42, 1, 0, n_cpu)
-        db = np.ascontiguousarray(np.stack([key, val], axis=1).astype(np.uint32))
-        t0 = time.perf_counter(); CO.query_groupby(db, 0, [1], [2]); t1 = time.perf_counter()
-        NO.query_groupby_ex([key, val], 0, [1, 1, 1], [AGG_SUM, AGG_COUNT, AGG_AVG]); t2 = time.perf_counter()
-        out.update(ref_faithful_rows_per_s=n_cpu / (t1 - t0), numpy_rows_per_s=n_cpu / (t2 - t1),
-                   sample=f"{n_cpu} rows, key uniform over 2^20, oracle.c query_groupby SUM (32 passes) / np_oracle SUM,COUNT,AVG")
-    elif kind == "orderby":
-        a = CO.synth_column(I64, dict(kind=0, lo=-(2 ** 19), range=2 ** 20), 42, 0, 0, n_cpu)
-        b = CO.synth_column(I64, dict(kind=0, lo=0, range=0), 42, 1, 0, n_cpu)
-        t0 = time.perf_counter(); NO.query_orderby([a, b], [0, 1], [0, 1]); t1 = time.perf_counter()
-        out.update(numpy_rows_per_s=n_cpu / (t1 - t0), sample=f"{n_cpu} rows x (i64,i64), np_oracle stable lexsort")
-    else:
-        nd = max(n_cpu // 40, 1)
-        aa = 2654435761
-        while np.gcd(aa, nd) != 1:
-            aa += 2
-        dim = [CO.synth_column(I32, dict(kind=1, a=aa, b=12345, range=nd), 7, 0, 0, nd),
-               CO.synth_column(I32, dict(kind=0, lo=0, range=1024), 7, 1, 0, nd)]
-        fact = [CO.synth_column(I32, dict(kind=0, lo=0, range=nd), 42, 0, 0, n_cpu),
-                CO.synth_column(I32, dict(kind=0, lo=0, range=1000), 42, 1, 0, n_cpu)]
-        t0 = time.perf_counter(); NO.join_groupby(fact, dim, 0, 0, 1, [1, 1], [AGG_SUM, AGG_COUNT]); t1 = time.perf_counter()
-        out.update(numpy_rows_per_s=n_cpu / (t1 - t0), sample=f"{n_cpu} fact x {nd} dim rows, np_oracle sort/searchsorted join + group by")
-    return out
-
-
 def run_groupby(env, scale, reps):
     import torch
     n = int(10 ** 9 * scale)
@@ -278,7 +244,6 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--out", default="")
     ap.add_argument("--opt", action="append", default=[], help="key=value context option")
-    ap.add_argument("--cpu-rows", type=int, default=0, help="also time the CPU port on this many rows (e.g. 16777216)")
     ap.add_argument("--own-stream", action="store_true",
                     help="let libhark create its own stream; default: torch's current stream (what bench.py and ShardedEnv do), "
                          "so that the torch events tools/query_suite.py times with see the kernels")
@@ -314,9 +279,6 @@ def main():
                 res.append(d)
             elif op == "join_sparse":
                 res.append(run_join(env, args.join_scale or args.scale, args.reps, sparse=True))
-            if args.cpu_rows > 0 and "error" not in res[-1] and op in ("groupby", "orderby", "join"):
-                res[-1]["cpu_baseline"] = cpu_leg(op, args.cpu_rows)
-                print(json.dumps({"op": op, "cpu_baseline": res[-1]["cpu_baseline"]}), flush=True)
         except Exception as e:  # keep going: one OOM must not hide the other operators' numbers
             print(json.dumps({"op": op, "error": repr(e)[:400]}), flush=True)
             res.append({"op": op, "error": repr(e)[:400]})
